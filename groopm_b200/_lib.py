@@ -1,0 +1,80 @@
+"""ctypes binding of libgmdist.so (the C ABI declared in include/gmdist.h).
+
+There is no CPU fallback: if the shared library has not been built, importing the
+engine fails loudly; if no CUDA device is present every compute call fails with
+the CUDA error text from the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libgmdist.so"
+
+OK, ERR_BAD_ARG, ERR_NONFINITE, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+L2, L1 = 0, 1
+FORM_EXPANDED, FORM_DIRECT_L2, FORM_DIRECT_L1, FORM_AUTO = 0, 1, 2, -1
+TILE_ROWS, MAX_K, MAX_D = 64, 64, 136
+
+_i64, _int, _vp, _sz = C.c_int64, C.c_int, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/gmdist.h declares
+SIGNATURES = {
+    "gmd_last_error": (C.c_char_p, []),
+    "gmd_version": (_int, []),
+    "gmd_bmu_host_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "gmd_knn_host_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp]),
+    "gmd_tiles_bytes": (_sz, [_i64, _int]),
+    "gmd_col_mean_f64": (_int, [_vp, _i64, _int, _vp, _vp]),
+    "gmd_prep_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp]),
+    "gmd_scan_topk_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _i64, _vp, _vp, _vp]),
+    "gmd_refine_topk_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_exact_rows_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_knn_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
+    "gmd_knn_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "gmd_pick_form": (_int, [_int, _int]),
+    "gmd_pick_kk": (_int, [_int]),
+    "gmd_pick_nsplit": (_int, [_i64, _i64, _int, _int]),
+    "gmd_fp32_peak_probe": (_int, [_int, _vp, C.POINTER(C.c_double), _vp]),
+}
+
+
+class GmdistError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m groopm_b200.build` "
+            "(there is no CPU fallback for the distance engine)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB
+
+
+def check(status: int) -> None:
+    """Map a gmd_status to the exception the reference's call site would see."""
+    if status == OK:
+        return
+    msg = lib().gmd_last_error().decode("utf-8", "replace")
+    if status == ERR_NONFINITE:
+        # the reference runs under np.seterr(all='raise') (torusMesh.py:57, som.py:80)
+        raise FloatingPointError(msg)
+    if status in (ERR_BAD_ARG, ERR_WORKSPACE, ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    raise GmdistError(msg)

@@ -1,0 +1,243 @@
+// C ABI glue: error state, policy helpers, the device-level pipeline and the
+// host-level drop-ins (see include/gmdist.h for the reference call sites).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "scan_impl.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gmd_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* gmd_last_error(void) { return g_err; }
+extern "C" int gmd_version(void) { return 100; }
+
+extern "C" int gmd_pick_form(int metric, int D) {
+    if (metric == GMD_L1) return GMD_FORM_DIRECT_L1;
+    // tiny D: the direct form costs <= 6 instructions per pair and is immune to the
+    // cancellation of ||a||^2 + ||b||^2 - 2a.b on [0, 999]^3 transformedCP data
+    return D <= 3 ? GMD_FORM_DIRECT_L2 : GMD_FORM_EXPANDED;
+}
+
+extern "C" int gmd_pick_kk(int k) { return k + std::min(8, std::max(3, k / 4)); }
+
+extern "C" int gmd_pick_nsplit(int64_t Nq, int64_t Nc, int D, int kk) {
+    (void)kk;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int DP = gmd_scan_pad_dim(D);
+    const int bq = gmd_scan_block_queries(DP < 0 ? 64 : DP);
+    const int64_t nqb = (Nq + bq - 1) / bq;
+    const int64_t ntiles = gmd_ntiles(Nc);
+    const int smax = (int)std::max<int64_t>(1, std::min<int64_t>(16, ntiles / 16));
+    int best = 1;
+    double best_cost = 1e300;
+    for (int s = 1; s <= smax; ++s) {
+        const double ctas = (double)nqb * s;
+        const double waves = std::ceil(ctas / sms);
+        // per-CTA time ~ tiles scanned + a fixed cost for list warm-up and write-out
+        const double cost = waves * ((double)ntiles / s + 24.0);
+        if (cost < best_cost * 0.98) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    return best;
+}
+
+extern "C" int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc, int D, int form,
+                                 int kk, int nsplit, int64_t c_index_offset, uint32_t* cand_idx, float* cand_val,
+                                 void* stream) {
+    GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val, GMD_ERR_BAD_ARG, "scan: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan: bad sizes");
+    GMD_REQUIRE(kk >= 1 && kk <= 96 && nsplit >= 1, GMD_ERR_BAD_ARG, "scan: kk=%d nsplit=%d out of range", kk, nsplit);
+    const int DP = gmd_scan_pad_dim(D);
+    GMD_REQUIRE(DP > 0, GMD_ERR_UNSUPPORTED, "scan: D=%d not supported (max %d)", D, GMD_MAX_D);
+    gmd_scan::ScanParams p;
+    p.qtiles = qtiles;
+    p.ctiles = ctiles;
+    p.Nq = Nq;
+    p.Nc = Nc;
+    p.ntiles_q = (int)gmd_ntiles(Nq);
+    p.ntiles_c = (int)gmd_ntiles(Nc);
+    p.nsplit = nsplit;
+    p.kk = kk;
+    p.c_index_offset = c_index_offset;
+    p.cand_idx = cand_idx;
+    p.cand_val = cand_val;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (form) {
+        case GMD_FORM_EXPANDED:
+            return gmd_scan_launch_form0(DP, p, st);
+        case GMD_FORM_DIRECT_L2:
+            return gmd_scan_launch_form1(DP, p, st);
+        case GMD_FORM_DIRECT_L1:
+            return gmd_scan_launch_form2(DP, p, st);
+        default:
+            break;
+    }
+    gmd_set_error("scan: bad form %d", form);
+    return GMD_ERR_BAD_ARG;
+}
+
+// ------------------------------------------------------------------ workspace layout
+namespace {
+struct Workspace {
+    double* center;     // [D]
+    float* stats;       // [4]  (2 used by candidates, 2 scratch for queries)
+    int32_t* flags;     // [4]  flags[0] non-finite, flags[1] fail_count
+    float* ctiles;
+    float* qtiles;
+    uint32_t* cand_idx;
+    float* cand_val;
+    int32_t* fail_rows;
+    size_t bytes;
+};
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, bool same) {
+    Workspace w;
+    char* p = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        char* r = p ? p + off : nullptr;
+        off += align_up(n);
+        return r;
+    };
+    w.center = (double*)take(sizeof(double) * GMD_MAX_D);
+    w.stats = (float*)take(sizeof(float) * 4);
+    w.flags = (int32_t*)take(sizeof(int32_t) * 4);
+    w.ctiles = (float*)take(gmd_tiles_bytes(Nc, D));
+    w.qtiles = same ? w.ctiles : (float*)take(gmd_tiles_bytes(Nq, D));
+    w.cand_idx = (uint32_t*)take((size_t)Nq * nsplit * kk * sizeof(uint32_t));
+    w.cand_val = (float*)take((size_t)Nq * nsplit * kk * sizeof(float));
+    w.fail_rows = (int32_t*)take((size_t)Nq * sizeof(int32_t));
+    w.bytes = off;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t gmd_knn_workspace_bytes(int64_t Nq, int64_t Nc, int D, int k) {
+    const int kk = gmd_pick_kk(k);
+    // same policy as gmd_knn_f64; sized for separate query tiles
+    return carve(nullptr, Nq, Nc, D, kk, gmd_pick_nsplit(Nq, Nc, D, kk), false).bytes;
+}
+
+extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
+                           int form, int32_t* out_idx, double* out_dist, void* workspace, size_t workspace_bytes,
+                           int32_t* info, void* stream) {
+    GMD_REQUIRE(Q && C && out_idx && out_dist && workspace, GMD_ERR_BAD_ARG, "knn: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0, GMD_ERR_BAD_ARG, "knn: empty input (Nq=%lld Nc=%lld)", (long long)Nq, (long long)Nc);
+    GMD_REQUIRE(D >= 1 && D <= GMD_MAX_D, GMD_ERR_UNSUPPORTED, "knn: D=%d outside [1, %d]", D, GMD_MAX_D);
+    GMD_REQUIRE(k >= 1 && k <= GMD_MAX_K, GMD_ERR_UNSUPPORTED, "knn: k=%d outside [1, %d]", k, GMD_MAX_K);
+    GMD_REQUIRE(k <= Nc, GMD_ERR_BAD_ARG, "knn: k=%d exceeds the %lld candidates", k, (long long)Nc);
+    GMD_REQUIRE(metric == GMD_L2 || metric == GMD_L1, GMD_ERR_BAD_ARG, "knn: bad metric %d", metric);
+    if (form == GMD_FORM_AUTO) form = gmd_pick_form(metric, D);
+    GMD_REQUIRE((metric == GMD_L1) == (form == GMD_FORM_DIRECT_L1), GMD_ERR_BAD_ARG,
+                "knn: form %d does not compute metric %d", form, metric);
+    const int kk = gmd_pick_kk(k);
+    const int nsplit = gmd_pick_nsplit(Nq, Nc, D, kk);
+    const bool same = (Q == C && Nq == Nc);
+    Workspace w = carve(workspace, Nq, Nc, D, kk, nsplit, same);
+    GMD_REQUIRE(w.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "knn: workspace %zu B < required %zu B",
+                workspace_bytes, w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    GMD_CUDA_CHECK(cudaMemsetAsync(w.stats, 0, sizeof(float) * 4, st));
+    GMD_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, sizeof(int32_t) * 4, st));
+    int rc;
+    if ((rc = gmd_col_mean_f64(C, Nc, D, w.center, stream)) != GMD_OK) return rc;
+    if ((rc = gmd_prep_f64(C, Nc, D, w.center, form, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
+    if (!same && (rc = gmd_prep_f64(Q, Nq, D, w.center, form, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK)
+        return rc;
+    if ((rc = gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,
+                                stream)) != GMD_OK)
+        return rc;
+    if ((rc = gmd_refine_topk_f64(Q, Nq, C, Nc, D, w.center, k, kk, nsplit, metric, form, w.cand_idx, w.cand_val,
+                                  w.stats, out_idx, out_dist, w.flags + 1, w.fail_rows, stream)) != GMD_OK)
+        return rc;
+    if ((rc = gmd_exact_rows_f64(Q, Nq, C, Nc, D, k, metric, w.flags + 1, w.fail_rows, out_idx, out_dist, stream)) !=
+        GMD_OK)
+        return rc;
+    if (info) {
+        // info[0] = rows finished by the exact scan, info[1] = non-finite input seen
+        GMD_CUDA_CHECK(cudaMemcpyAsync(info, w.flags + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        GMD_CUDA_CHECK(cudaMemcpyAsync(info + 1, w.flags, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    return GMD_OK;
+}
+
+// ------------------------------------------------------------------ host-level drop-ins
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+    int alloc(size_t n, cudaStream_t s) {
+        st = s;
+        GMD_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(n, 16), s));
+        return GMD_OK;
+    }
+};
+struct StreamGuard {
+    cudaStream_t st = nullptr;
+    ~StreamGuard() {
+        if (st) cudaStreamDestroy(st);
+    }
+};
+}  // namespace
+
+extern "C" int gmd_knn_host_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
+                                int32_t* out_idx, double* out_dist) {
+    GMD_REQUIRE(Q && C && out_idx, GMD_ERR_BAD_ARG, "knn_host: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1, GMD_ERR_BAD_ARG, "knn_host: empty input");
+    GMD_REQUIRE(D <= GMD_MAX_D, GMD_ERR_UNSUPPORTED, "knn_host: D=%d > %d", D, GMD_MAX_D);
+    GMD_REQUIRE(k >= 1 && k <= GMD_MAX_K, GMD_ERR_UNSUPPORTED, "knn_host: k=%d outside [1, %d]", k, GMD_MAX_K);
+    GMD_REQUIRE(k <= Nc, GMD_ERR_BAD_ARG, "knn_host: k=%d exceeds the %lld candidates", k, (long long)Nc);
+    StreamGuard sg;
+    GMD_CUDA_CHECK(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
+    cudaStream_t st = sg.st;
+    const bool same = (Q == C && Nq == Nc);
+    DevBuf dC, dQ, dI, dD, dW, dInfo;
+    int rc;
+    const size_t cb = (size_t)Nc * D * sizeof(double), qb = (size_t)Nq * D * sizeof(double);
+    if ((rc = dC.alloc(cb, st)) != GMD_OK) return rc;
+    GMD_CUDA_CHECK(cudaMemcpyAsync(dC.p, C, cb, cudaMemcpyHostToDevice, st));
+    const double* dq = (const double*)dC.p;
+    if (!same) {
+        if ((rc = dQ.alloc(qb, st)) != GMD_OK) return rc;
+        GMD_CUDA_CHECK(cudaMemcpyAsync(dQ.p, Q, qb, cudaMemcpyHostToDevice, st));
+        dq = (const double*)dQ.p;
+    }
+    const size_t wsb = gmd_knn_workspace_bytes(Nq, Nc, D, k);
+    if ((rc = dI.alloc((size_t)Nq * k * sizeof(int32_t), st)) != GMD_OK) return rc;
+    if ((rc = dD.alloc((size_t)Nq * k * sizeof(double), st)) != GMD_OK) return rc;
+    if ((rc = dW.alloc(wsb, st)) != GMD_OK) return rc;
+    if ((rc = dInfo.alloc(2 * sizeof(int32_t), st)) != GMD_OK) return rc;
+    rc = gmd_knn_f64(dq, Nq, (const double*)dC.p, Nc, D, k, metric, GMD_FORM_AUTO, (int32_t*)dI.p, (double*)dD.p,
+                     dW.p, wsb, (int32_t*)dInfo.p, st);
+    if (rc != GMD_OK) return rc;
+    int32_t info[2] = {0, 0};
+    GMD_CUDA_CHECK(cudaMemcpyAsync(info, dInfo.p, sizeof(info), cudaMemcpyDeviceToHost, st));
+    GMD_CUDA_CHECK(cudaMemcpyAsync(out_idx, dI.p, (size_t)Nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (out_dist)
+        GMD_CUDA_CHECK(cudaMemcpyAsync(out_dist, dD.p, (size_t)Nq * k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GMD_CUDA_CHECK(cudaStreamSynchronize(st));
+    GMD_REQUIRE(info[1] == 0, GMD_ERR_NONFINITE, "non-finite value in an input profile");
+    return GMD_OK;
+}
+
+extern "C" int gmd_bmu_host_f64(const double* nodes, int64_t M, const double* X, int64_t N, int D, int32_t* out_loc,
+                                double* out_dist) {
+    return gmd_knn_host_f64(X, N, nodes, M, D, 1, GMD_L2, out_loc, out_dist);
+}

@@ -1,0 +1,155 @@
+// Profile staging: float64 row-major rows -> centred FP32 tiles in HBM.
+//
+// HBM layout of a profile set ("tiles"): tile t holds rows [64t, 64t+64) as
+//   float tile[DP + 1][64]     tile[d][r] = (float)(X[64t + r][d] - center[d])  (d <  D)
+//                              tile[d][r] = 0                                    (D <= d < DP)
+//                              tile[DP][r] = ||row||_2^2 of the FP32 row         (expanded form)
+// so one candidate tile is a single contiguous (DP+1)*256-byte block: exactly one
+// bulk async copy per pipeline stage of the scan, and the scan's shared-memory
+// reads of 8 consecutive rows of one dimension are two conflict-free LDS.128.
+// Padding rows (beyond N) can never be selected: their norm (expanded form) or
+// first coordinate (direct forms) is huge.
+#include "scan_impl.cuh"
+
+namespace {
+
+__global__ void col_mean_kernel(const double* __restrict__ X, long long N, int D, double* __restrict__ center) {
+    // deterministic (fixed summation order) mean over a strided sample of <= 65536 rows;
+    // the centre only conditions the FP32 scan, the float64 re-rank never sees it rounded.
+    __shared__ double part[32];
+    const long long stride = (N + 65535) / 65536;
+    const long long ns = (N + stride - 1) / stride;
+    for (int d = 0; d < D; ++d) {
+        double s = 0.0;
+        for (long long i = threadIdx.x; i < ns; i += blockDim.x) s += X[(size_t)(i * stride) * D + d];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+            center[d] = tot / (double)ns;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(const double* __restrict__ X, long long N, int D, int DP,
+                                                   const double* __restrict__ center, int form,
+                                                   float* __restrict__ tiles, float* __restrict__ stats,
+                                                   int* __restrict__ flags) {
+    extern __shared__ float sm[];  // [D][65]
+    const long long t = blockIdx.x;
+    const long long row0 = t * GMD_TW;
+    const int tile_f = (DP + 1) * GMD_TW;
+    bool bad = false;
+    // coalesced read of 64 consecutive rows (64*D consecutive doubles)
+    for (int e = threadIdx.x; e < GMD_TW * D; e += blockDim.x) {
+        const int r = e / D, d = e - r * D;
+        const long long row = row0 + r;
+        float v;
+        if (row < N) {
+            const double x = X[(size_t)row0 * D + e];
+            bad |= !isfinite(x);
+            v = (float)(x - (center ? center[d] : 0.0));
+        } else {
+            v = (form != GMD_FORM_EXPANDED && d == 0) ? GMD_PAD_COORD : 0.0f;
+        }
+        sm[d * 65 + r] = v;
+    }
+    if (bad) atomicExch(flags, 1);
+    __syncthreads();
+    float* out = tiles + (size_t)t * tile_f;
+    for (int e = threadIdx.x; e < DP * GMD_TW; e += blockDim.x) {
+        const int d = e >> 6, r = e & 63;
+        out[e] = d < D ? sm[d * 65 + r] : 0.0f;
+    }
+    if (threadIdx.x < GMD_TW) {
+        const int r = threadIdx.x;
+        double n2 = 0.0, n1 = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double v = (double)sm[d * 65 + r];
+            n2 += v * v;
+            n1 += fabs(v);
+        }
+        const bool real = (row0 + r) < N;
+        float aux = 0.0f;
+        if (form == GMD_FORM_EXPANDED) aux = real ? (float)n2 : GMD_PAD_AUX;
+        out[DP * GMD_TW + r] = aux;
+        if (real && stats) {
+            // non-negative floats order like their bit patterns; round the maxima up
+            atomicMax(reinterpret_cast<int*>(stats), __float_as_int(__double2float_ru(n2)));
+            atomicMax(reinterpret_cast<int*>(stats) + 1, __float_as_int(__double2float_ru(n1)));
+        }
+    }
+}
+
+// FP32 FFMA peak probe: 16 independent chains per thread, all operands in registers.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float* sink) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+    const float m = 0.999f + (float)blockIdx.x * 1e-9f, c = 1e-4f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 256; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;  // keep the chains alive
+}
+
+}  // namespace
+
+int gmd_scan_pad_dim(int D) {
+#define X(d) \
+    if (D <= d) return d;
+    GMD_SCAN_DIMS(X)
+    GMD_SCAN_DIMS_BIG(X)
+#undef X
+    return -1;
+}
+
+int gmd_scan_block_queries(int DP) { return DP <= 64 ? 256 : 128; }
+
+extern "C" size_t gmd_tiles_bytes(int64_t N, int D) {
+    const int DP = gmd_scan_pad_dim(D);
+    if (DP < 0 || N < 0) return 0;
+    return (size_t)gmd_ntiles(N) * (size_t)(DP + 1) * GMD_TW * sizeof(float);
+}
+
+extern "C" int gmd_col_mean_f64(const double* X, int64_t N, int D, double* center, void* stream) {
+    GMD_REQUIRE(X && center && N > 0 && D > 0, GMD_ERR_BAD_ARG, "col_mean: bad arguments");
+    col_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(X, N, D, center);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+extern "C" int gmd_prep_f64(const double* X, int64_t N, int D, const double* center, int form, float* tiles,
+                            float* stats, int32_t* flags, void* stream) {
+    GMD_REQUIRE(X && tiles && flags && N > 0, GMD_ERR_BAD_ARG, "prep: bad arguments");
+    GMD_REQUIRE(D >= 1 && D <= GMD_MAX_D, GMD_ERR_UNSUPPORTED, "prep: D=%d outside [1, %d]", D, GMD_MAX_D);
+    GMD_REQUIRE(form >= 0 && form <= 2, GMD_ERR_BAD_ARG, "prep: bad form %d", form);
+    const int DP = gmd_scan_pad_dim(D);
+    const size_t smem = (size_t)D * 65 * sizeof(float);
+    prep_kernel<<<(unsigned)gmd_ntiles(N), 256, smem, (cudaStream_t)stream>>>(X, N, D, DP, center, form, tiles, stats,
+                                                                             flags);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+extern "C" int gmd_fp32_peak_probe(int iters, float* sink, double* flops, void* stream) {
+    GMD_REQUIRE(iters > 0 && sink, GMD_ERR_BAD_ARG, "fp32_peak_probe: bad arguments");
+    int dev = 0, sms = 0;
+    GMD_CUDA_CHECK(cudaGetDevice(&dev));
+    GMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8;
+    fp32_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    if (flops) *flops = 2.0 * 16.0 * 256.0 * (double)iters * 256.0 * (double)blocks;
+    return GMD_OK;
+}

@@ -1,0 +1,255 @@
+// float64 re-rank of the scan's candidates + exactness certificate + exact fallback.
+//
+// The FP32 scan only PROPOSES kk >= k candidates per (query, split).  Here every
+// proposed pair is re-measured from the original float64 rows with the reference's
+// own arithmetic -- sqrt(sum((a-b)^2)) / sum(|a-b|), direct differences, no FMA
+// contraction (scipy cdist/pdist, e.g. torusMesh.py:127, cluster.py:495) -- and
+// ranked by (distance, index), the np.argmin / lowest-index tie rule.
+//
+// Certificate.  A candidate the scan did NOT propose sits in some full split list
+// whose kk-th FP32 value is tau_s, so its FP32 value is >= tau = min_s tau_s and its
+// true float64 distance is >= lower(tau) where lower() subtracts a rigorous bound on
+// (a) float64->float32 rounding of the centred rows, |d - d~| <= u(||q|| + ||c||),
+// and (b) the FP32 accumulation error of the scan's form.  If the k-th float64
+// distance is strictly below lower(tau) the top-k is provably the exact one.
+// Otherwise the row goes to exact_rows_kernel, a float64 scan of every candidate.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr double U32 = 5.9604644775390625e-08;  // 2^-24
+
+__device__ __forceinline__ double dist64(const double* __restrict__ a, const double* __restrict__ b, int D,
+                                         int metric) {
+    double s = 0.0;
+    if (metric == GMD_L2) {
+        for (int d = 0; d < D; ++d) {
+            const double t = __dsub_rn(a[d], b[d]);
+            s = __dadd_rn(s, __dmul_rn(t, t));
+        }
+        return sqrt(s);
+    }
+    for (int d = 0; d < D; ++d) s = __dadd_rn(s, fabs(__dsub_rn(a[d], b[d])));
+    return s;
+}
+
+__device__ __forceinline__ bool key_less(double da, uint32_t ia, double db, uint32_t ib) {
+    return da < db || (da == db && ia < ib);
+}
+
+// one warp per query row
+__global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ Q, long long Nq,
+                                                     const double* __restrict__ C, int D,
+                                                     const double* __restrict__ center, int k, int kk, int nsplit,
+                                                     int metric, int form, const uint32_t* __restrict__ cand_idx,
+                                                     const float* __restrict__ cand_val,
+                                                     const float* __restrict__ stats, int32_t* __restrict__ out_idx,
+                                                     double* __restrict__ out_dist, int32_t* fail_count,
+                                                     int32_t* __restrict__ fail_rows) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int m = kk * nsplit;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sd = reinterpret_cast<double*>(sm_raw) + (size_t)warp * m;
+    uint32_t* si = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(sm_raw) + (size_t)(blockDim.x >> 5) * m) +
+                   (size_t)warp * m;
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= Nq) return;
+    const double* qrow = Q + (size_t)q * D;
+    const uint32_t* ci = cand_idx + (size_t)q * m;
+    const float* cv = cand_val + (size_t)q * m;
+
+    for (int x = lane; x < m; x += 32) {
+        const uint32_t idx = ci[x];
+        double d = CUDART_INF;
+        if (idx != GMD_EMPTY_IDX) d = dist64(qrow, C + (size_t)idx * D, D, metric);
+        sd[x] = d;
+        si[x] = idx;
+    }
+    __syncwarp();
+
+    double kth = CUDART_INF;
+    for (int x = lane; x < m; x += 32) {
+        const double d = sd[x];
+        const uint32_t idx = si[x];
+        int r = 0;
+        for (int y = 0; y < m; ++y) r += key_less(sd[y], si[y], d, idx) ? 1 : 0;
+        if (r < k && idx != GMD_EMPTY_IDX) {
+            out_idx[(size_t)q * k + r] = (int32_t)idx;
+            out_dist[(size_t)q * k + r] = d;
+            if (r == k - 1) kth = d;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) kth = fmin(kth, __shfl_xor_sync(0xFFFFFFFFu, kth, o));
+
+    // ---- certificate
+    float tau32 = CUDART_INF_F;
+    for (int s = lane; s < nsplit; s += 32)
+        if (ci[s * kk + kk - 1] != GMD_EMPTY_IDX) tau32 = fminf(tau32, cv[s * kk + kk - 1]);
+    for (int o = 16; o > 0; o >>= 1) tau32 = fminf(tau32, __shfl_xor_sync(0xFFFFFFFFu, tau32, o));
+    bool ok = true;
+    if (tau32 != CUDART_INF_F) {
+        double n2 = 0.0, n1 = 0.0;
+        for (int d = lane; d < D; d += 32) {
+            const double v = qrow[d] - (center ? center[d] : 0.0);
+            n2 += v * v;
+            n1 += fabs(v);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            n2 += __shfl_xor_sync(0xFFFFFFFFu, n2, o);
+            n1 += __shfl_xor_sync(0xFFFFFFFFu, n1, o);
+        }
+        const double tau = (double)tau32;
+        double lower;
+        if (form == GMD_FORM_EXPANDED) {
+            const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
+            const double e2 = (2.0 * D + 8.0) * U32 * nn * nn;
+            lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
+        } else if (form == GMD_FORM_DIRECT_L2) {
+            const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
+            lower = sqrt(tau * (1.0 - (D + 6.0) * U32)) - 1.01 * U32 * nn;
+        } else {
+            const double nn = (n1 + (double)stats[1]) * 1.000001;
+            lower = tau * (1.0 - (D + 4.0) * U32) - 1.01 * U32 * nn;
+        }
+        ok = kth < lower;
+    }
+    if (!ok && lane == 0) {
+        const int slot = atomicAdd(fail_count, 1);
+        fail_rows[slot] = (int32_t)q;
+    }
+}
+
+// exact float64 scan of all candidates for the rows the certificate rejected
+constexpr int EX_CAP = 2048;
+constexpr int EX_THREADS = 256;
+
+struct KeyD {
+    double d;
+    uint32_t i;
+};
+
+__device__ __forceinline__ KeyD block_min_key(KeyD v, KeyD* red) {
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xFFFFFFFFu, v.d, o);
+        const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, v.i, o);
+        if (key_less(od, oi, v.d, v.i)) {
+            v.d = od;
+            v.i = oi;
+        }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    KeyD r = red[0];
+    for (int w = 1; w < EX_THREADS / 32; ++w)
+        if (key_less(red[w].d, red[w].i, r.d, r.i)) r = red[w];
+    return r;
+}
+
+__global__ void __launch_bounds__(EX_THREADS) exact_rows_kernel(const double* __restrict__ Q,
+                                                               const double* __restrict__ C, long long Nc, int D,
+                                                               int k, int metric,
+                                                               const int32_t* __restrict__ fail_count,
+                                                               const int32_t* __restrict__ fail_rows,
+                                                               int32_t* __restrict__ out_idx,
+                                                               double* __restrict__ out_dist) {
+    __shared__ double qs[GMD_MAX_D];
+    __shared__ double bd[EX_CAP];
+    __shared__ uint32_t bi[EX_CAP];
+    __shared__ KeyD red[EX_THREADS / 32];
+    __shared__ int cnt;
+    const int nfail = *fail_count;
+    for (int w = blockIdx.x; w < nfail; w += gridDim.x) {
+        const long long q = fail_rows[w];
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += EX_THREADS) qs[d] = Q[(size_t)q * D + d];
+        if (threadIdx.x == 0) cnt = 0;
+        __syncthreads();
+        // the re-ranked k-th distance is a valid upper bound on the true k-th distance
+        const double ub = out_dist[(size_t)q * k + k - 1];
+        for (long long c = threadIdx.x; c < Nc; c += EX_THREADS) {
+            const double d = dist64(qs, C + (size_t)c * D, D, metric);
+            if (d <= ub) {
+                const int slot = atomicAdd(&cnt, 1);
+                if (slot < EX_CAP) {
+                    bd[slot] = d;
+                    bi[slot] = (uint32_t)c;
+                }
+            }
+        }
+        __syncthreads();
+        const int n = cnt;
+        if (n <= EX_CAP) {
+            for (int x = threadIdx.x; x < n; x += EX_THREADS) {
+                int r = 0;
+                for (int y = 0; y < n; ++y) r += key_less(bd[y], bi[y], bd[x], bi[x]) ? 1 : 0;
+                if (r < k) {
+                    out_idx[(size_t)q * k + r] = (int32_t)bi[x];
+                    out_dist[(size_t)q * k + r] = bd[x];
+                }
+            }
+        } else {
+            // pathological tie mass (> EX_CAP candidates within the bound): k selection passes
+            KeyD prev = {-1.0, 0u};
+            bool first = true;
+            for (int r = 0; r < k; ++r) {
+                KeyD best = {CUDART_INF, GMD_EMPTY_IDX};
+                for (long long c = threadIdx.x; c < Nc; c += EX_THREADS) {
+                    const double d = dist64(qs, C + (size_t)c * D, D, metric);
+                    const bool after = first || key_less(prev.d, prev.i, d, (uint32_t)c);
+                    if (after && key_less(d, (uint32_t)c, best.d, best.i)) {
+                        best.d = d;
+                        best.i = (uint32_t)c;
+                    }
+                }
+                best = block_min_key(best, red);
+                if (threadIdx.x == 0) {
+                    out_idx[(size_t)q * k + r] = (int32_t)best.i;
+                    out_dist[(size_t)q * k + r] = best.d;
+                }
+                prev = best;
+                first = false;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                                   const double* center, int k, int kk, int nsplit, int metric, int form,
+                                   const uint32_t* cand_idx, const float* cand_val, const float* stats,
+                                   int32_t* out_idx, double* out_dist, int32_t* fail_count, int32_t* fail_rows,
+                                   void* stream) {
+    GMD_REQUIRE(Q && C && cand_idx && cand_val && stats && out_idx && out_dist && fail_count && fail_rows,
+                GMD_ERR_BAD_ARG, "refine: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1 && k >= 1 && kk >= k && nsplit >= 1 && k <= Nc, GMD_ERR_BAD_ARG,
+                "refine: bad sizes (Nq=%lld Nc=%lld D=%d k=%d kk=%d nsplit=%d)", (long long)Nq, (long long)Nc, D, k,
+                kk, nsplit);
+    const int wpb = 4;
+    const size_t smem = (size_t)wpb * kk * nsplit * (sizeof(double) + sizeof(uint32_t));
+    GMD_REQUIRE(smem <= 200 * 1024, GMD_ERR_UNSUPPORTED, "refine: kk*nsplit=%d too large", kk * nsplit);
+    GMD_CUDA_CHECK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((Nq + wpb - 1) / wpb);
+    refine_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, Nq, C, D, center, k, kk, nsplit, metric, form,
+                                                                 cand_idx, cand_val, stats, out_idx, out_dist,
+                                                                 fail_count, fail_rows);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+extern "C" int gmd_exact_rows_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
+                                  const int32_t* fail_count, const int32_t* fail_rows, int32_t* out_idx,
+                                  double* out_dist, void* stream) {
+    GMD_REQUIRE(Q && C && fail_count && fail_rows && out_idx && out_dist, GMD_ERR_BAD_ARG, "exact_rows: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1 && D <= GMD_MAX_D && k >= 1 && k <= Nc, GMD_ERR_BAD_ARG,
+                "exact_rows: bad sizes");
+    int dev = 0, sms = 0;
+    GMD_CUDA_CHECK(cudaGetDevice(&dev));
+    GMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    exact_rows_kernel<<<sms * 4, EX_THREADS, 0, (cudaStream_t)stream>>>(Q, C, Nc, D, k, metric, fail_count, fail_rows,
+                                                                       out_idx, out_dist);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}

@@ -1,0 +1,21 @@
+// Instantiations of the fused distance + top-k scan for FP32 form 0 (see scan_impl.cuh).
+#include "scan_impl.cuh"
+
+int gmd_scan_launch_form0(int DP, const gmd_scan::ScanParams& p, cudaStream_t st) {
+    switch (DP) {
+#define X(d) \
+    case d:  \
+        return gmd_scan::scan_launch<d, 0, 8, 4>(p, st);
+        GMD_SCAN_DIMS(X)
+#undef X
+#define X(d) \
+    case d:  \
+        return gmd_scan::scan_launch<d, 0, 4, 2>(p, st);
+        GMD_SCAN_DIMS_BIG(X)
+#undef X
+        default:
+            break;
+    }
+    gmd_set_error("scan: no kernel for padded dimension %d", DP);
+    return GMD_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,246 @@
+"""Host side of the distance / neighbour-search engine.
+
+numpy or torch float64 arrays in, numpy or torch arrays out, in the layouts the
+reference's call sites consume.  PyTorch is used only for
+device memory, streams and (in ``dist.py``) torch.distributed; every kernel is
+reached through the C ABI of ``libgmdist.so`` with raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METRICS = {"euclidean": _lib.L2, "cityblock": _lib.L1, "l2": _lib.L2, "l1": _lib.L1,
+           _lib.L2: _lib.L2, _lib.L1: _lib.L1}
+
+
+def _metric(metric) -> int:
+    try:
+        return METRICS[metric]
+    except KeyError:
+        raise ValueError(f"Unknown Distance Metric: {metric}") from None
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.GmdistError("no CUDA device: the gmdist engine has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _as_rows(x, name: str) -> tuple[torch.Tensor, bool]:
+    """-> (2-D float64 C-contiguous torch tensor on its current device, was_numpy)."""
+    was_numpy = not isinstance(x, torch.Tensor)
+    if was_numpy:
+        a = np.asarray(x, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError(f"{name} must be a 2-dimensional array.")
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    else:
+        t = x
+        if t.ndim != 2:
+            raise ValueError(f"{name} must be a 2-dimensional array.")
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        t = t.contiguous()
+    return t, was_numpy
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class KnnPipeline:
+    """The staged device pipeline for one (Nq, Nc, D, k, metric) shape.
+
+    Owns every device buffer (the library never allocates on this path):
+
+        center [D] f64 | stats [4] f32 | flags [4] i32
+        ctiles / qtiles  FP32 profile tiles  [ntiles][DP+1][64]
+        cand_idx / cand_val                  [Nq][nsplit][kk]   proposals of the FP32 scan
+        out_idx [Nq, k] i32, out_dist [Nq, k] f64
+
+    ``run`` = col_mean -> prep -> scan -> refine -> exact_rows, all stream-ordered.
+    """
+
+    def __init__(self, nq: int, nc: int, d: int, k: int, metric="euclidean", form: Optional[int] = None,
+                 same: bool = False, device=None):
+        self.lib = _lib.lib()
+        self.dev = _device(device)
+        self.nq, self.nc, self.d, self.k = int(nq), int(nc), int(d), int(k)
+        self.metric = _metric(metric)
+        if self.nq <= 0 or self.nc <= 0 or self.d <= 0:
+            raise ValueError("empty profile set")
+        if self.d > _lib.MAX_D:
+            raise ValueError(f"D={self.d} exceeds {_lib.MAX_D}")
+        if not 1 <= self.k <= _lib.MAX_K:
+            raise ValueError(f"k={self.k} outside [1, {_lib.MAX_K}]")
+        if self.k > self.nc:
+            raise ValueError(f"k={self.k} exceeds the {self.nc} candidates")
+        self.form = self.lib.gmd_pick_form(self.metric, self.d) if form is None else int(form)
+        self.same = bool(same)
+        with torch.cuda.device(self.dev):
+            self.kk = self.lib.gmd_pick_kk(self.k)
+            self.nsplit = self.lib.gmd_pick_nsplit(self.nq, self.nc, self.d, self.kk)
+        e = dict(device=self.dev)
+        self.center = torch.zeros(_lib.MAX_D, dtype=torch.float64, **e)
+        self.stats = torch.zeros(4, dtype=torch.float32, **e)
+        self.flags = torch.zeros(4, dtype=torch.int32, **e)
+        self.ctiles = torch.empty(self.lib.gmd_tiles_bytes(self.nc, self.d) // 4, dtype=torch.float32, **e)
+        self.qtiles = self.ctiles if same else torch.empty(
+            self.lib.gmd_tiles_bytes(self.nq, self.d) // 4, dtype=torch.float32, **e)
+        m = self.nq * self.nsplit * self.kk
+        self.cand_idx = torch.empty(m, dtype=torch.int32, **e)
+        self.cand_val = torch.empty(m, dtype=torch.float32, **e)
+        self.fail_rows = torch.empty(self.nq, dtype=torch.int32, **e)
+        self.out_idx = torch.empty((self.nq, self.k), dtype=torch.int32, **e)
+        self.out_dist = torch.empty((self.nq, self.k), dtype=torch.float64, **e)
+
+    # -- stages (each a single C-ABI call on the current stream)
+    def reset(self):
+        self.stats.zero_()
+        self.flags.zero_()
+
+    def col_mean(self, c: torch.Tensor):
+        _lib.check(self.lib.gmd_col_mean_f64(_ptr(c), self.nc, self.d, _ptr(self.center), _stream_ptr()))
+
+    def prep_candidates(self, c: torch.Tensor):
+        _lib.check(self.lib.gmd_prep_f64(_ptr(c), self.nc, self.d, _ptr(self.center), self.form,
+                                         _ptr(self.ctiles), _ptr(self.stats), _ptr(self.flags), _stream_ptr()))
+
+    def prep_queries(self, q: torch.Tensor):
+        if self.same:
+            return
+        _lib.check(self.lib.gmd_prep_f64(_ptr(q), self.nq, self.d, _ptr(self.center), self.form,
+                                         _ptr(self.qtiles), _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))
+
+    def scan(self):
+        _lib.check(self.lib.gmd_scan_topk_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d,
+                                              self.form, self.kk, self.nsplit, 0, _ptr(self.cand_idx),
+                                              _ptr(self.cand_val), _stream_ptr()))
+
+    def refine(self, q: torch.Tensor, c: torch.Tensor):
+        _lib.check(self.lib.gmd_refine_topk_f64(
+            _ptr(q), self.nq, _ptr(c), self.nc, self.d, _ptr(self.center), self.k, self.kk, self.nsplit,
+            self.metric, self.form, _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.stats),
+            _ptr(self.out_idx), _ptr(self.out_dist), _ptr(self.flags) + 4, _ptr(self.fail_rows), _stream_ptr()))
+
+    def exact_rows(self, q: torch.Tensor, c: torch.Tensor):
+        _lib.check(self.lib.gmd_exact_rows_f64(
+            _ptr(q), self.nq, _ptr(c), self.nc, self.d, self.k, self.metric, _ptr(self.flags) + 4,
+            _ptr(self.fail_rows), _ptr(self.out_idx), _ptr(self.out_dist), _stream_ptr()))
+
+    def run(self, q: torch.Tensor, c: torch.Tensor):
+        """q [Nq, D], c [Nc, D] float64 on this pipeline's device -> (out_idx, out_dist) device tensors."""
+        for name, t, n in (("q", q, self.nq), ("c", c, self.nc)):
+            if t.device != self.dev or t.dtype != torch.float64 or not t.is_contiguous() or tuple(t.shape) != (n, self.d):
+                raise ValueError(f"{name}: expected contiguous float64 [{n}, {self.d}] on {self.dev}")
+        with torch.cuda.device(self.dev):
+            self.reset()
+            self.col_mean(c)
+            self.prep_candidates(c)
+            self.prep_queries(q)
+            self.scan()
+            self.refine(q, c)
+            self.exact_rows(q, c)
+        return self.out_idx, self.out_dist
+
+    # -- diagnostics (synchronise)
+    def exact_row_count(self) -> int:
+        return int(self.flags[1].item())
+
+    def saw_nonfinite(self) -> bool:
+        return bool(self.flags[0].item())
+
+    # launches of the engine's own kernels in one run() (col_mean, prep x1/2, scan, refine, exact)
+    @property
+    def launches_per_run(self) -> int:
+        return 5 if self.same else 6
+
+
+def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, device=None,
+        return_info: bool = False):
+    """k nearest rows of ``c`` for every row of ``q``; ascending (distance, index).
+
+    ``c=None`` means all-pairs within ``q`` (self included at rank 0, as in
+    ``sort(squareform(pdist(X)))`` cluster.py:495-496 and ``KDTree.query``
+    refine.py:664-665).  numpy in -> numpy out (int32 indices, float64 distances);
+    CUDA tensors in -> CUDA tensors out.
+    """
+    qt, q_np = _as_rows(q, "XA")
+    same = c is None or c is q
+    ct, _ = (qt, q_np) if same else _as_rows(c, "XB")
+    if qt.shape[1] != ct.shape[1]:
+        raise ValueError("XA and XB must have the same number of columns "
+                         "(i.e. feature dimension.)")
+    if qt.shape[0] == 0 or ct.shape[0] == 0 or qt.shape[1] == 0:
+        raise ValueError("empty profile set")
+    dev = qt.device if qt.is_cuda else _device(device)
+    with torch.cuda.device(dev):
+        qd = qt.to(dev, non_blocking=True)
+        cd = qd if same else ct.to(dev, non_blocking=True)
+        pipe = KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, form, same=same, device=dev)
+        idx, dist = pipe.run(qd, cd)
+        if q_np:
+            idx_h, dist_h = idx.cpu().numpy(), dist.cpu().numpy()  # synchronises
+            if pipe.saw_nonfinite():
+                raise FloatingPointError("non-finite value in an input profile")
+            out = (idx_h, dist_h)
+        else:
+            if pipe.saw_nonfinite():
+                raise FloatingPointError("non-finite value in an input profile")
+            out = (idx, dist)
+        if return_info:
+            return out + ({"exact_rows": pipe.exact_row_count(), "form": pipe.form, "kk": pipe.kk,
+                           "nsplit": pipe.nsplit},)
+        return out
+
+
+def bmu(nodes, x, device=None, return_dist: bool = False):
+    """Flat best-matching-unit index of every row of ``x`` on ``nodes`` [M, D]:
+    ``argmin(cdist(nodes, [x_i]))`` (torusMesh.py:127, som.py:351), first minimum."""
+    idx, dist = knn(x, nodes, k=1, metric="euclidean", device=device)
+    if return_dist:
+        return idx[:, 0], dist[:, 0]
+    return idx[:, 0]
+
+
+def knn_host(q: np.ndarray, c: Optional[np.ndarray], k: int, metric="euclidean"):
+    """Same result through the pure C-ABI host entry point (no torch involved):
+    host float64 pointers in, host arrays out -- what a ctypes-only caller binds."""
+    lib = _lib.lib()
+    qa = np.ascontiguousarray(q, dtype=np.float64)
+    ca = qa if c is None else np.ascontiguousarray(c, dtype=np.float64)
+    if qa.ndim != 2 or ca.ndim != 2 or qa.shape[1] != ca.shape[1]:
+        raise ValueError("XA and XB must be 2-dimensional with the same number of columns")
+    out_i = np.empty((qa.shape[0], k), dtype=np.int32)
+    out_d = np.empty((qa.shape[0], k), dtype=np.float64)
+    _lib.check(lib.gmd_knn_host_f64(qa.ctypes.data, qa.shape[0], ca.ctypes.data, ca.shape[0], qa.shape[1], int(k),
+                                    _metric(metric), out_i.ctypes.data, out_d.ctypes.data))
+    return out_i, out_d
+
+
+def fp32_peak_tflops(iters: int = 64, repeats: int = 5) -> float:
+    """Measured FFMA peak of the current device (TFLOP/s), best of ``repeats``."""
+    lib = _lib.lib()
+    dev = _device()
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    flops = C.c_double(0.0)
+    best = 0.0
+    for r in range(repeats + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.gmd_fp32_peak_probe(iters, sink.data_ptr(), C.byref(flops), _stream_ptr()))
+        e1.record()
+        e1.synchronize()
+        if r:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

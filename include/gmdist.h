@@ -1,0 +1,151 @@
+/*
+ * gmdist.h -- C ABI of libgmdist.so, the B200 (sm_100a) contig-profile distance
+ * and neighbour-search engine.
+ *
+ * The reference (GroopM, /root/reference/groopm) has no FFI of its own: its hot
+ * path is ~20 inline scipy/numpy calls.  Each entry point below names the
+ * reference call site (file:line) whose arithmetic it replaces; INTEGRATION.md
+ * shows the ctypes binding a GroopM maintainer would add at that site.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns a gmd_status (0 == OK, < 0 == error);
+ *     gmd_last_error() returns a per-thread message for the last failure.
+ *   - "*_host_*" functions take HOST pointers in the reference's own dtype
+ *     (float64, C-contiguous, row-major [rows, D]) and do allocation, H2D, the
+ *     kernels and D2H themselves on the current device -- the drop-in layer.
+ *   - all other functions take DEVICE pointers, never allocate or free device
+ *     memory, are stream-ordered and asynchronous (stream is a cudaStream_t
+ *     passed as void*; NULL == the legacy default stream).
+ *   - metric: 0 = Euclidean (scipy 'euclidean'), 1 = cityblock (scipy 'cityblock').
+ *   - results are exact in the reference's float64 sense: the FP32 scan only
+ *     proposes candidates; a float64 re-rank from the original float64 rows
+ *     emits the distances and a per-row certificate sends any row whose FP32
+ *     candidate set could be incomplete to an exact float64 scan.  Ties are
+ *     broken by lowest candidate index (np.argmin / first-occurrence rule,
+ *     torusMesh.py:127).
+ */
+#ifndef GMDIST_H
+#define GMDIST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GMD_API __attribute__((visibility("default")))
+#else
+#define GMD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GMD_OK = 0,
+    GMD_ERR_BAD_ARG = -1,      /* shapes / k / metric out of range  -> ValueError      */
+    GMD_ERR_NONFINITE = -2,    /* NaN/Inf in an input (np.seterr(all='raise'),
+                                  torusMesh.py:57)                  -> FloatingPointError */
+    GMD_ERR_CUDA = -3,         /* CUDA runtime error                 -> RuntimeError    */
+    GMD_ERR_WORKSPACE = -4,    /* caller workspace too small         -> ValueError      */
+    GMD_ERR_UNSUPPORTED = -5   /* D or k beyond what the kernels are built for          */
+} gmd_status;
+
+enum { GMD_L2 = 0, GMD_L1 = 1 };
+
+/* FP32 scan forms (chosen by gmd_pick_form unless forced):
+ *   0 expanded  ||c||^2 - 2 q.c   (L2 only; D FFMA per pair)
+ *   1 direct L2 sum (q-c)^2       (2D instr per pair; for ill-conditioned / tiny D)
+ *   2 direct L1 sum |q-c|         (2D instr per pair)                              */
+enum { GMD_FORM_EXPANDED = 0, GMD_FORM_DIRECT_L2 = 1, GMD_FORM_DIRECT_L1 = 2, GMD_FORM_AUTO = -1 };
+
+#define GMD_TILE_ROWS 64        /* profile rows per HBM tile                        */
+#define GMD_MAX_K 64            /* largest k of the fused top-k                     */
+#define GMD_MAX_D 136           /* largest profile dimension (raw tetranucleotides) */
+
+GMD_API const char* gmd_last_error(void);
+GMD_API int gmd_version(void);
+
+/* ------------------------------------------------------------------ host-level drop-ins
+ * (inputs/outputs are HOST float64/int32 arrays; each call is synchronous)            */
+
+/* Best-matching unit of every row of X on a flattened torus mesh.
+ * Replaces the per-contig  argmin(cdist(flatNodes, [v]))  of TorusMesh.bestMatch
+ * (torusMesh.py:123-130), the classify loops refine.py:1219-1222 / 2137-2138 and the
+ * inner BMU of SOM.train (som.py:348-353).  out_loc[i] is the flat node index
+ * (first minimum); out_dist (nullable) the float64 Euclidean distance.               */
+GMD_API int gmd_bmu_host_f64(const double* nodes, int64_t M, const double* X, int64_t N, int D,
+                     int32_t* out_loc, double* out_dist);
+
+/* k nearest candidates of every query row, ascending (distance, index), self included
+ * when Q and C are the same rows.  Replaces KDTree(data).query(x, k)
+ * (refine.py:653-665, metric 0) and sort(squareform(pdist(X,'cityblock')))[:, :k]
+ * (cluster.py:495-498, metric 1) without materialising the n x n matrix.
+ * out_idx [Nq,k] int32, out_dist [Nq,k] float64.                                      */
+GMD_API int gmd_knn_host_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                     int k, int metric, int32_t* out_idx, double* out_dist);
+
+/* ------------------------------------------------------------------ device-level stages
+ * (device pointers; stream-ordered; caller owns all memory)                           */
+
+/* bytes of the FP32 tile array for N rows of dimension D */
+GMD_API size_t gmd_tiles_bytes(int64_t N, int D);
+
+/* column means of X[N,D] (float64) -> center[D]; the centring that keeps FP32
+ * norm expansion well conditioned (SURVEY.md section 7 "hard parts").                 */
+GMD_API int gmd_col_mean_f64(const double* X, int64_t N, int D, double* center, void* stream);
+
+/* float64 row-major rows -> centred FP32 tiles [tile][D+1][64] (row D: ||x||^2 for
+ * form 0).  stats[0] = max ||x||_2^2, stats[1] = max ||x||_1 over the rows (FP32 bit
+ * patterns, updated with atomicMax: zero it once per candidate set);
+ * flags[0] is set to 1 if any input is NaN/Inf.                                       */
+GMD_API int gmd_prep_f64(const double* X, int64_t N, int D, const double* center, int form,
+                 float* tiles, float* stats, int32_t* flags, void* stream);
+
+/* The hot kernel: FP32 distance tiles + fused warp-level top-kk selection; the
+ * Nq x Nc matrix is never materialised.  Candidates are cut into nsplit contiguous
+ * ranges; for each (query, split) the kk best (value, index) pairs are written to
+ * cand_idx / cand_val [Nq][nsplit][kk] (index 0xFFFFFFFF == empty slot).
+ * c_index_offset is added to every candidate index (row-sharded candidates).          */
+GMD_API int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc,
+                      int D, int form, int kk, int nsplit, int64_t c_index_offset,
+                      uint32_t* cand_idx, float* cand_val, void* stream);
+
+/* float64 re-rank of the proposed candidates from the ORIGINAL rows, lowest-index tie
+ * rule, plus the per-row certificate; uncertified rows are appended to fail_rows
+ * (count in fail_count[0]) and finished by gmd_exact_rows_f64.                        */
+GMD_API int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                        const double* center, int k, int kk, int nsplit, int metric,
+                        int form, const uint32_t* cand_idx, const float* cand_val,
+                        const float* stats, int32_t* out_idx, double* out_dist,
+                        int32_t* fail_count, int32_t* fail_rows, void* stream);
+
+/* exact float64 scan of all candidates for the listed rows (reads the count on device) */
+GMD_API int gmd_exact_rows_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                       int k, int metric, const int32_t* fail_count,
+                       const int32_t* fail_rows, int32_t* out_idx, double* out_dist,
+                       void* stream);
+
+/* whole pipeline on device pointers with a caller workspace (see
+ * gmd_knn_workspace_bytes); form = GMD_FORM_AUTO picks by metric and D.
+ * info[0] (nullable, device int32) receives the number of rows that needed the exact
+ * float64 scan.                                                                       */
+GMD_API size_t gmd_knn_workspace_bytes(int64_t Nq, int64_t Nc, int D, int k);
+GMD_API int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k,
+                int metric, int form, int32_t* out_idx, double* out_dist,
+                void* workspace, size_t workspace_bytes, int32_t* info, void* stream);
+
+/* split / slack policy shared with the host layer */
+GMD_API int gmd_pick_form(int metric, int D);
+GMD_API int gmd_pick_kk(int k);
+GMD_API int gmd_pick_nsplit(int64_t Nq, int64_t Nc, int D, int kk);
+
+/* FP32 FFMA peak probe (roofline denominator): runs
+ * iters x 4096 dependent-free FFMAs per thread on every SM and returns the flop
+ * count in *flops; time it with events around the call.                               */
+GMD_API int gmd_fp32_peak_probe(int iters, float* sink, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMDIST_H */

@@ -1,0 +1,223 @@
+"""Literal float64 restatement of the reference's hot-path call sites.
+
+Each function cites the ``/root/reference/groopm`` file:line it follows and
+uses the same scipy/numpy calls on float64 inputs.  Test infrastructure only
+(see ``oracle/__init__.py``).
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.spatial import KDTree
+from scipy.spatial.distance import cdist, pdist, squareform
+
+__all__ = [
+    "best_match", "bmu_batch", "classify_contigs", "som_train_bmus",
+    "whiten", "allpairs_cityblock", "kth_neighbour_radius", "radius_neighbours",
+    "contraction_weights", "two_way_contraction_step", "kdtree_knn", "knn",
+    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal",
+]
+
+
+# ---------------------------------------------------------------- a1 / a2 / a3
+
+def best_match(flat_nodes: np.ndarray, target: np.ndarray, rows: int, columns: int):
+    """TorusMesh.bestMatch, torusMesh.py:123-130 (including ``col = loc - row*rows``)."""
+    loc = int(np.argmin(cdist(flat_nodes, [target])))
+    row = int(loc / columns)
+    col = loc - (row * rows)
+    return [row, col]
+
+
+def bmu_batch(flat_nodes: np.ndarray, x: np.ndarray, chunk: int = 8192) -> np.ndarray:
+    """``argmin(cdist(flat_nodes, [x_i]))`` for every row of ``x`` (torusMesh.py:127,
+    som.py:351), batched: cdist(X_chunk, nodes) is the same float64 direct-difference
+    arithmetic per pair, argmin keeps the first (lowest-index) minimum."""
+    out = np.empty(x.shape[0], dtype=np.int64)
+    for s in range(0, x.shape[0], chunk):
+        out[s:s + chunk] = np.argmin(cdist(x[s:s + chunk], flat_nodes), axis=1)
+    return out
+
+
+def classify_contigs(flat_nodes, block, bin_assignments, rows, columns, chunk: int = 8192):
+    """The per-contig loop refine.py:1219-1222 / 2137-2138 over SOM.classifyContig
+    (som.py:572-575): ``int(binAssignments[r, c])`` with [r, c] from bestMatch."""
+    loc = bmu_batch(flat_nodes, block, chunk)
+    row = (loc / columns).astype(np.int64)
+    col = loc - row * rows
+    return np.asarray(bin_assignments)[row, col].astype(np.int64)
+
+
+def som_train_bmus(flat_nodes: np.ndarray, train_vectors: np.ndarray, index_array) -> np.ndarray:
+    """Inner BMU of SOM.train (som.py:348-353): nodes are frozen for the whole
+    ``for j in index_array`` loop, so the T searches are one batch."""
+    tv = np.asarray(train_vectors)[np.asarray(index_array)]
+    return bmu_batch(flat_nodes, tv)
+
+
+# ---------------------------------------------------------------- a4 / a5 / a6
+
+def whiten(dat: np.ndarray) -> np.ndarray:
+    """cluster.py:488-491 (same at refine.py:647-651)."""
+    mean = np.mean(dat, axis=0)
+    std = np.std(dat, axis=0)
+    std += np.where(std == 0, 1, 0)
+    return (dat - mean) / std
+
+
+def allpairs_cityblock(x: np.ndarray) -> np.ndarray:
+    """cluster.py:495 / :497 -- ``squareform(pdist(X, 'cityblock'))``."""
+    return squareform(pdist(x, 'cityblock'))
+
+
+def kth_neighbour_radius(dist_matrix: np.ndarray, eps_neighbours: int):
+    """cluster.py:496 / :498 -- ``median(sort(D)[:, eps])``; column 0 is self.
+    Returns (radius, per-row k-th distances)."""
+    kth = np.sort(dist_matrix)[:, eps_neighbours]
+    return float(np.median(kth)), kth
+
+
+def radius_neighbours(dist_row: np.ndarray, radius: float, eps_neighbours: int):
+    """cluster.py:534-541 / 571-578: ascending ``where(row <= r)[0]``; when there
+    are more than max(1, 0.1*eps) of them the FIRST (lowest-index) one is dropped
+    as the presumed self match; otherwise the row is putative noise (None)."""
+    nb = np.where(dist_row <= radius)[0]
+    if len(nb) > np.max([1, 0.1 * eps_neighbours]):
+        return nb[1:]
+    return None
+
+
+def contraction_weights(other_dist_row: np.ndarray, neighbours: np.ndarray, other_radius: float):
+    """cluster.py:547-557 / 583-588: inverse-distance weights from the OTHER
+    metric's matrix, floor of 0.1 * other radius."""
+    nd = other_dist_row[neighbours] + 0.1 * other_radius
+    inv = 1.0 / nd
+    return inv / np.sum(inv)
+
+
+def two_way_contraction_step(c_dat: np.ndarray, k_dat: np.ndarray, move: float = 0.1):
+    """One iteration of twoWayContraction's distance-driven part, cluster.py:430,
+    488-498, 530-590 (max_iterations = 1, :437).  Returns the new k_dat, c_dat,
+    both radii and the putative-noise index sets."""
+    n = len(c_dat)
+    eps = int(np.min([10, int(n / 2)]))
+    c_w = whiten(c_dat)
+    c_dm = allpairs_cityblock(c_w)
+    c_radius, _ = kth_neighbour_radius(c_dm, eps)
+    k_dm = allpairs_cityblock(k_dat)
+    k_radius, _ = kth_neighbour_radius(k_dm, eps)
+
+    new_k = np.zeros(k_dat.shape)
+    k_noise = set()
+    for i, row in enumerate(c_dm):
+        nb = radius_neighbours(row, c_radius, eps)
+        if nb is None:
+            k_noise.add(i)
+            new_k[i] = k_dat[i]
+            continue
+        w = contraction_weights(k_dm[i], nb, k_radius)
+        new_k[i] = (1 - move) * k_dat[i] + move * np.sum((k_dat[nb].T * w).T, axis=0)
+
+    # NB the reference has already replaced k_dat by new_k_dat here (cluster.py:563)
+    # but k_dist_matrix is the one computed before the move.
+    new_c = np.zeros(c_dat.shape)
+    c_noise = set()
+    for i, row in enumerate(k_dm):
+        nb = radius_neighbours(row, k_radius, eps)
+        if nb is None:
+            c_noise.add(i)
+            new_c[i] = c_dat[i]
+            continue
+        w = contraction_weights(c_dm[i], nb, c_radius)
+        new_c[i] = (1 - move) * c_dat[i] + move * np.sum((c_dat[nb].T * w).T, axis=0)
+    return {"k_dat": new_k, "c_dat": new_c, "c_radius": c_radius, "k_radius": k_radius,
+            "k_noise": k_noise, "c_noise": c_noise, "eps": eps}
+
+
+# ---------------------------------------------------------------- a7
+
+def kdtree_knn(data: np.ndarray, k: int):
+    """findMergeGroups, refine.py:653-665: ``KDTree(data).query(data[i], k=K)``
+    for every row, Euclidean, self included, ascending distance.  K is capped at
+    the number of rows (refine.py:590-594)."""
+    k = min(k, len(data))
+    tree = KDTree(data)
+    d, i = tree.query(data, k=k)
+    if k == 1:
+        d = d[:, None]
+        i = i[:, None]
+    return d, i
+
+
+def knn(q: np.ndarray, c: np.ndarray, k: int, metric: str = "euclidean", chunk: int = 1024):
+    """Generalised a4+a5+a7 (BASELINE configs 2 and 5): the k smallest entries of
+    each row of ``cdist(Q, C, metric)`` ascending, ties broken by lowest index.
+    Same float64 per-pair arithmetic as the reference's cdist/pdist calls; the
+    full-row ``sort`` of cluster.py:496 is replaced by argpartition + sort of the
+    survivors, which returns the same k values."""
+    nq = q.shape[0]
+    k = min(k, c.shape[0])
+    out_i = np.empty((nq, k), dtype=np.int64)
+    out_d = np.empty((nq, k), dtype=np.float64)
+    for s in range(0, nq, chunk):
+        dm = cdist(q[s:s + chunk], c, metric)
+        if k < c.shape[0]:
+            part = np.argpartition(dm, k - 1, axis=1)[:, :k]
+            kth = np.take_along_axis(dm, part, axis=1).max(axis=1)
+        else:
+            kth = dm.max(axis=1)
+        for r in range(dm.shape[0]):
+            row = dm[r]
+            cand = np.flatnonzero(row <= kth[r])
+            order = np.lexsort((cand, row[cand]))[:k]
+            out_i[s + r] = cand[order]
+            out_d[s + r] = row[cand[order]]
+    return out_d, out_i
+
+
+# ---------------------------------------------------------------- a8 / a9
+
+def k_dist(bin_k_vals: np.ndarray):
+    """RefineEngine.kDist, refine.py:1490-1496."""
+    kd = pdist(bin_k_vals, 'cityblock')
+    if len(kd) > 0:
+        return float(np.median(kd))
+    return None
+
+
+def k_dist_between(k1: np.ndarray, k2: np.ndarray) -> float:
+    """RefineEngine.kDistBetweenBins, refine.py:1502-1503."""
+    return float(np.median(cdist(k1, k2, 'cityblock')))
+
+
+def small2indices(index: int, side: int):
+    """mstore.py:1880-1888: condensed pdist index -> (i, j)."""
+    step = 0
+    while index >= (side - step):
+        index = index - side + step
+        step += 1
+    return (step, step + index + 1)
+
+
+# ---------------------------------------------------------------- parity helper
+
+def knn_tie_aware_equal(q, c, idx_engine, idx_oracle, dist_oracle, metric="euclidean",
+                        tie: float = 1e-6):
+    """Index parity rule of BASELINE.json's north_star: indices are identical to
+    the oracle's except where the competing oracle distances are within ``tie``.
+
+    A rank where the engine's index differs is excused only if the float64
+    distance from the query to the index the engine chose equals the oracle's
+    distance at that rank within ``tie`` (i.e. it is a genuine tie), and no row
+    may repeat an index.  Returns the number of violating rows (0 == parity)."""
+    idx_engine = np.asarray(idx_engine)
+    idx_oracle = np.asarray(idx_oracle)
+    bad = 0
+    for r in np.flatnonzero((idx_engine != idx_oracle).any(axis=1)):
+        cols = np.flatnonzero(idx_engine[r] != idx_oracle[r])
+        if len(set(idx_engine[r].tolist())) != idx_engine.shape[1]:
+            bad += 1
+            continue
+        d = cdist(q[r:r + 1], c[idx_engine[r, cols]], metric)[0]
+        if np.any(np.abs(d - dist_oracle[r, cols]) > tie):
+            bad += 1
+    return bad
