@@ -27,9 +27,9 @@ SIGNATURES = {
     "gmd_tiles_bytes": (_sz, [_i64, _int]),
     "gmd_col_mean_f64": (_int, [_vp, _i64, _int, _vp, _vp]),
     "gmd_prep_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp]),
-    "gmd_scan_topk_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _i64, _vp, _vp, _vp]),
+    "gmd_scan_topk_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _i64, _vp, _vp, _vp, _vp]),
     "gmd_refine_topk_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
-                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_exact_rows_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "gmd_knn_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "gmd_knn_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),

@@ -55,8 +55,8 @@ extern "C" int gmd_pick_nsplit(int64_t Nq, int64_t Nc, int D, int kk) {
 
 extern "C" int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc, int D, int form,
                                  int kk, int nsplit, int64_t c_index_offset, uint32_t* cand_idx, float* cand_val,
-                                 void* stream) {
-    GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val, GMD_ERR_BAD_ARG, "scan: null pointer");
+                                 float* cand_tau, void* stream) {
+    GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG, "scan: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan: bad sizes");
     GMD_REQUIRE(kk >= 1 && kk <= 96 && nsplit >= 1, GMD_ERR_BAD_ARG, "scan: kk=%d nsplit=%d out of range", kk, nsplit);
     const int DP = gmd_scan_pad_dim(D);
@@ -73,6 +73,7 @@ extern "C" int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* c
     p.c_index_offset = c_index_offset;
     p.cand_idx = cand_idx;
     p.cand_val = cand_val;
+    p.cand_tau = cand_tau;
     cudaStream_t st = (cudaStream_t)stream;
     switch (form) {
         case GMD_FORM_EXPANDED:
@@ -98,6 +99,7 @@ struct Workspace {
     float* qtiles;
     uint32_t* cand_idx;
     float* cand_val;
+    float* cand_tau;
     int32_t* fail_rows;
     size_t bytes;
 };
@@ -120,6 +122,7 @@ Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, b
     w.qtiles = same ? w.ctiles : (float*)take(gmd_tiles_bytes(Nq, D));
     w.cand_idx = (uint32_t*)take((size_t)Nq * nsplit * kk * sizeof(uint32_t));
     w.cand_val = (float*)take((size_t)Nq * nsplit * kk * sizeof(float));
+    w.cand_tau = (float*)take((size_t)Nq * nsplit * sizeof(float));
     w.fail_rows = (int32_t*)take((size_t)Nq * sizeof(int32_t));
     w.bytes = off;
     return w;
@@ -159,10 +162,10 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     if (!same && (rc = gmd_prep_f64(Q, Nq, D, w.center, form, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK)
         return rc;
     if ((rc = gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,
-                                stream)) != GMD_OK)
+                                w.cand_tau, stream)) != GMD_OK)
         return rc;
     if ((rc = gmd_refine_topk_f64(Q, Nq, C, Nc, D, w.center, k, kk, nsplit, metric, form, w.cand_idx, w.cand_val,
-                                  w.stats, out_idx, out_dist, w.flags + 1, w.fail_rows, stream)) != GMD_OK)
+                                  w.cand_tau, w.stats, out_idx, out_dist, w.flags + 1, w.fail_rows, stream)) != GMD_OK)
         return rc;
     if ((rc = gmd_exact_rows_f64(Q, Nq, C, Nc, D, k, metric, w.flags + 1, w.fail_rows, out_idx, out_dist, stream)) !=
         GMD_OK)

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
                                                      const double* __restrict__ center, int k, int kk, int nsplit,
                                                      int metric, int form, const uint32_t* __restrict__ cand_idx,
                                                      const float* __restrict__ cand_val,
+                                                     const float* __restrict__ cand_tau,
                                                      const float* __restrict__ stats, int32_t* __restrict__ out_idx,
                                                      double* __restrict__ out_dist, int32_t* fail_count,
                                                      int32_t* __restrict__ fail_rows) {
@@ -57,7 +58,6 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
     if (q >= Nq) return;
     const double* qrow = Q + (size_t)q * D;
     const uint32_t* ci = cand_idx + (size_t)q * m;
-    const float* cv = cand_val + (size_t)q * m;
 
     for (int x = lane; x < m; x += 32) {
         const uint32_t idx = ci[x];
@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
 
     // ---- certificate
     float tau32 = CUDART_INF_F;
-    for (int s = lane; s < nsplit; s += 32)
-        if (ci[s * kk + kk - 1] != GMD_EMPTY_IDX) tau32 = fminf(tau32, cv[s * kk + kk - 1]);
+    for (int s = lane; s < nsplit; s += 32) tau32 = fminf(tau32, cand_tau[(size_t)q * nsplit + s]);
     for (int o = 16; o > 0; o >>= 1) tau32 = fminf(tau32, __shfl_xor_sync(0xFFFFFFFFu, tau32, o));
     bool ok = true;
     if (tau32 != CUDART_INF_F) {
@@ -219,10 +218,10 @@ __global__ void __launch_bounds__(EX_THREADS) exact_rows_kernel(const double* __
 
 extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
                                    const double* center, int k, int kk, int nsplit, int metric, int form,
-                                   const uint32_t* cand_idx, const float* cand_val, const float* stats,
-                                   int32_t* out_idx, double* out_dist, int32_t* fail_count, int32_t* fail_rows,
+                                   const uint32_t* cand_idx, const float* cand_val, const float* cand_tau,
+                                   const float* stats, int32_t* out_idx, double* out_dist, int32_t* fail_count, int32_t* fail_rows,
                                    void* stream) {
-    GMD_REQUIRE(Q && C && cand_idx && cand_val && stats && out_idx && out_dist && fail_count && fail_rows,
+    GMD_REQUIRE(Q && C && cand_idx && cand_val && cand_tau && stats && out_idx && out_dist && fail_count && fail_rows,
                 GMD_ERR_BAD_ARG, "refine: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1 && k >= 1 && kk >= k && nsplit >= 1 && k <= Nc, GMD_ERR_BAD_ARG,
                 "refine: bad sizes (Nq=%lld Nc=%lld D=%d k=%d kk=%d nsplit=%d)", (long long)Nq, (long long)Nc, D, k,
@@ -233,7 +232,7 @@ extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C,
     GMD_CUDA_CHECK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((Nq + wpb - 1) / wpb);
     refine_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, Nq, C, D, center, k, kk, nsplit, metric, form,
-                                                                 cand_idx, cand_val, stats, out_idx, out_dist,
+                                                                 cand_idx, cand_val, cand_tau, stats, out_idx, out_dist,
                                                                  fail_count, fail_rows);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;

@@ -5,11 +5,12 @@
 // shared-memory ring filled by a dedicated producer warp with bulk async copies
 // (cp.async.bulk -> SASS UBLKCP) that complete on mbarriers.  Each compute warp
 // owns 32 of the CTA's queries outright -- its 32q x 64c warp tile is an 8x8
-// register tile per lane -- so the running top-kk lists (shared memory, sorted
+// register tile per lane -- so the running top-kk sets (shared-memory max-heaps of
 // u64 keys = order-preserving(value) << 32 | index) are warp-private and the
 // warps never synchronise with one another.  The fast path per candidate tile is
 // D x 64 FFMA + a min-tree against the per-query threshold; only when some
-// value beats a threshold does the warp take the cooperative insert path.
+// value beats a threshold does the warp take the insert path (hits are queued per
+// query, then lane L updates the heap of the warp's query L).
 //
 // Candidate tiles are visited in ascending index order and the threshold test is
 // strict, so equal values keep the lowest index (np.argmin's first-occurrence
@@ -63,6 +64,7 @@ struct ScanParams {
     long long c_index_offset;
     uint32_t* cand_idx;
     float* cand_val;
+    float* cand_tau;
 };
 
 __device__ __forceinline__ float sel8(const float (&a)[8], int j) {
@@ -72,28 +74,68 @@ __device__ __forceinline__ float sel8(const float (&a)[8], int j) {
     return v;
 }
 
-// Insert (v, idx) into one query's sorted list, all 32 lanes cooperating.
-__device__ __forceinline__ void warp_insert(uint64_t* lst, int kk, float v, uint32_t idx, int lane,
-                                            float* thr_slot) {
-    const unsigned FULL = 0xFFFFFFFFu;
-    const uint64_t key = gmd_key(v, idx);
-    const int x0 = lane, x1 = lane + 32, x2 = lane + 64;
-    const uint64_t e0 = x0 < kk ? lst[x0] : GMD_EMPTY_KEY;
-    const uint64_t e1 = x1 < kk ? lst[x1] : GMD_EMPTY_KEY;
-    const uint64_t e2 = x2 < kk ? lst[x2] : GMD_EMPTY_KEY;
-    const int pos = __popc(__ballot_sync(FULL, e0 < key)) + __popc(__ballot_sync(FULL, e1 < key)) +
-                    __popc(__ballot_sync(FULL, e2 < key));
-    if (pos >= kk) return;  // warp-uniform
-    __syncwarp();
-    if (x0 >= pos && x0 + 1 < kk) lst[x0 + 1] = e0;
-    if (x1 >= pos && x1 + 1 < kk) lst[x1 + 1] = e1;
-    if (x2 >= pos && x2 + 1 < kk) lst[x2 + 1] = e2;
-    if (lane == 0) lst[pos] = key;
-    __syncwarp();
-    if (lane == 0) {
-        const uint64_t last = lst[kk - 1];
-        *thr_slot = (last == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(last >> 32));
+// Per-query running top-kk set: a binary MAX-heap of u64 keys in shared memory
+// (root = current kk-th best = the threshold).  Each compute warp owns 32 queries
+// and, on the rare path, lane L maintains the heap of the warp's query L by itself,
+// so up to 32 inserts proceed in parallel with no shuffles; the float64 re-rank
+// orders the survivors anyway.  Empty slots hold GMD_EMPTY_KEY (largest key), so a
+// freshly initialised array is already a valid heap.
+__device__ __forceinline__ void heap_replace_root(uint64_t* h, int kk, uint64_t key) {
+    int pos = 0;
+    while (true) {
+        const int l = 2 * pos + 1;
+        if (l >= kk) break;
+        const uint64_t kl = h[l];
+        const uint64_t kr = (l + 1 < kk) ? h[l + 1] : 0ull;
+        const bool right = kr > kl;
+        const uint64_t kc = right ? kr : kl;
+        if (kc <= key) break;
+        h[pos] = kc;
+        pos = right ? l + 1 : l;
     }
+    h[pos] = key;
+}
+
+constexpr int QCAP = 8;  // pending-hit queue slots per query and round
+
+// d-loop shape: a straight-line prefix of PRE steps (d = 0 initialises the accumulators)
+// then a rolled loop whose body is U steps, so the hot loop stays inside the
+// instruction cache (a fully unrolled D=30 body is 34 KB of SASS and starves issue).
+__host__ __device__ constexpr int pick_unroll(int D) {
+    if (D <= 9) return D;  // whole thing straight-line
+    int best_u = 8, best_rem = (D - 1) % 8;
+    for (int u = 9; u >= 4; --u) {
+        const int rem = (D - 1) % u;
+        if (rem < best_rem) {
+            best_rem = rem;
+            best_u = u;
+        }
+    }
+    return best_u;
+}
+
+struct Frag {
+    float4 qa, qb, ca, cb;
+};
+
+template <int FORM, bool FIRST>
+__device__ __forceinline__ void tile_step(float (&acc)[8][8], const Frag& f, const float (&cn)[8]) {
+    const float q[8] = {f.qa.x, f.qa.y, f.qa.z, f.qa.w, f.qb.x, f.qb.y, f.qb.z, f.qb.w};
+    const float c[8] = {f.ca.x, f.ca.y, f.ca.z, f.ca.w, f.cb.x, f.cb.y, f.cb.z, f.cb.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (FORM == GMD_FORM_EXPANDED) {
+                acc[i][j] = fmaf(q[i], c[j], FIRST ? cn[j] : acc[i][j]);
+            } else if (FORM == GMD_FORM_DIRECT_L2) {
+                const float df = q[i] - c[j];
+                acc[i][j] = FIRST ? df * df : fmaf(df, df, acc[i][j]);
+            } else {
+                const float df = fabsf(q[i] - c[j]);
+                acc[i][j] = FIRST ? df : acc[i][j] + df;
+            }
+        }
 }
 
 template <int D, int FORM, int NW, int NST>
@@ -101,18 +143,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
     constexpr int BQ = NW * 32;
     constexpr int TILE_F = (D + 1) * GMD_TW;
     constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr int U = pick_unroll(D);
+    constexpr int PRE = (D <= 9) ? D : 1 + (D - 1) % U;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* Cs = reinterpret_cast<float*>(smem_raw);          // NST x [D+1][64]
-    float* Qs = Cs + NST * TILE_F;                           // [D][BQ]
-    float* qn = Qs + D * BQ;                                 // [BQ]  ||q||^2 (form 0)
-    float* thr_s = qn + BQ;                                  // [BQ]  current kk-th value
-    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + BQ);  // full[NST], empty[NST]
-    uint64_t* lists = bars + 2 * NST;                        // [BQ][kk]
+    float* Cs = reinterpret_cast<float*>(smem_raw);                // NST x [D+1][64]
+    float* Qs = Cs + NST * TILE_F;                                 // [D][BQ]
+    float* qn = Qs + D * BQ;                                       // [BQ]  ||q||^2 (form 0)
+    float* thr_s = qn + BQ;                                        // [BQ]  heap-root value (+inf until full)
+    int* qcnt = reinterpret_cast<int*>(thr_s + BQ);                // [BQ]  pending hits this round
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + BQ);       // full[NST], empty[NST]
+    uint64_t* queue = bars + 2 * NST;                              // [BQ][QCAP] pending (value, index)
+    uint64_t* lists = queue + BQ * QCAP;                           // [BQ][kkp]  max-heaps
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int kk = p.kk;
+    const int kkp = kk | 1;  // odd stride: lanes walking their own heaps hit distinct banks
     const long long q0 = (long long)blockIdx.x * BQ;
     const int split = blockIdx.y;
     const int tps = (p.ntiles_c + p.nsplit - 1) / p.nsplit;
@@ -133,8 +180,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
             else
                 qn[r] = v;
         }
-        for (int e = tid; e < BQ * kk; e += (NW + 1) * 32) lists[e] = GMD_EMPTY_KEY;
-        for (int e = tid; e < BQ; e += (NW + 1) * 32) thr_s[e] = __int_as_float(0x7f800000);
+        for (int e = tid; e < BQ * kkp; e += (NW + 1) * 32) lists[e] = GMD_EMPTY_KEY;
+        for (int e = tid; e < BQ; e += (NW + 1) * 32) {
+            thr_s[e] = __int_as_float(0x7f800000);
+            qcnt[e] = 0;
+        }
         if (tid == 0) {
             for (int s = 0; s < NST; ++s) {
                 mbar_init(&bars[s], 1);
@@ -145,7 +195,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
         }
     }
     __syncthreads();
-    // no CTA-wide barrier below this line: the producer warp may retire early
+    // no CTA-wide barrier below this line: the producer warp retires early
 
     if (warp == NW) {
         // ---- producer: keep the ring full
@@ -163,6 +213,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
     // ---- compute warps
     const int lq = lane >> 3, lc = lane & 7;
     const float* Qw = Qs + warp * 32 + lq * 4;
+    float* wthr = thr_s + warp * 32;
+    int* wcnt = qcnt + warp * 32;
+    uint64_t* wqueue = queue + warp * 32 * QCAP;
+    uint64_t* wheap = lists + (size_t)warp * 32 * kkp;
     float thr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) thr[i] = __int_as_float(0x7f800000);
@@ -171,114 +225,138 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
         const int it = t - tb, s = it % NST;
         mbar_wait(&bars[s], (it / NST) & 1);
         const float* Ct = Cs + s * TILE_F + lc * 4;
+        auto load = [&](int d) {
+            Frag f;
+            f.qa = *reinterpret_cast<const float4*>(Qw + d * BQ);
+            f.qb = *reinterpret_cast<const float4*>(Qw + d * BQ + 16);
+            f.ca = *reinterpret_cast<const float4*>(Ct + d * GMD_TW);
+            f.cb = *reinterpret_cast<const float4*>(Ct + d * GMD_TW + 32);
+            return f;
+        };
 
         float acc[8][8];
-        {
-            // d = 0 peeled: initialises the accumulators
-            const float4 qa = *reinterpret_cast<const float4*>(Qw);
-            const float4 qb = *reinterpret_cast<const float4*>(Qw + 16);
-            const float4 ca = *reinterpret_cast<const float4*>(Ct);
-            const float4 cb = *reinterpret_cast<const float4*>(Ct + 32);
-            const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-            const float c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-            if (FORM == GMD_FORM_EXPANDED) {
-                const float4 na = *reinterpret_cast<const float4*>(Ct + D * GMD_TW);
-                const float4 nb = *reinterpret_cast<const float4*>(Ct + D * GMD_TW + 32);
-                const float cn[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(q[i], c[j], cn[j]);
-            } else if (FORM == GMD_FORM_DIRECT_L2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float df = q[i] - c[j];
-                        acc[i][j] = df * df;
-                    }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fabsf(q[i] - c[j]);
-            }
+        float cn[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (FORM == GMD_FORM_EXPANDED) {
+            const float4 na = *reinterpret_cast<const float4*>(Ct + D * GMD_TW);
+            const float4 nb = *reinterpret_cast<const float4*>(Ct + D * GMD_TW + 32);
+            cn[0] = na.x, cn[1] = na.y, cn[2] = na.z, cn[3] = na.w;
+            cn[4] = nb.x, cn[5] = nb.y, cn[6] = nb.z, cn[7] = nb.w;
         }
-#pragma unroll(D <= 32 ? D : 8)
-        for (int d = 1; d < D; ++d) {
-            const float4 qa = *reinterpret_cast<const float4*>(Qw + d * BQ);
-            const float4 qb = *reinterpret_cast<const float4*>(Qw + d * BQ + 16);
-            const float4 ca = *reinterpret_cast<const float4*>(Ct + d * GMD_TW);
-            const float4 cb = *reinterpret_cast<const float4*>(Ct + d * GMD_TW + 32);
-            const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-            const float c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        // one step ahead in registers; reading "row D" at the very end is harmless
+        // (the norm row of the tile / the qn array follow the last coordinate row)
+        Frag cur = load(0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+        for (int d = 0; d < PRE; ++d) {
+            const Frag nxt = load(d + 1);
+            if (d == 0)
+                tile_step<FORM, true>(acc, cur, cn);
+            else
+                tile_step<FORM, false>(acc, cur, cn);
+            cur = nxt;
+        }
+        if (PRE < D) {
+#pragma unroll 1
+            for (int d0 = PRE; d0 < D; d0 += U) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (FORM == GMD_FORM_EXPANDED) {
-                        acc[i][j] = fmaf(q[i], c[j], acc[i][j]);
-                    } else if (FORM == GMD_FORM_DIRECT_L2) {
-                        const float df = q[i] - c[j];
-                        acc[i][j] = fmaf(df, df, acc[i][j]);
-                    } else {
-                        acc[i][j] += fabsf(q[i] - c[j]);
-                    }
+                for (int u = 0; u < U; ++u) {
+                    const Frag nxt = load(d0 + u + 1);
+                    tile_step<FORM, false>(acc, cur, cn);
+                    cur = nxt;
                 }
+            }
         }
         // this stage's shared memory is no longer needed by this warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[NST + s]);
 
         // ---- selection fast path: one min-tree per query row against its threshold
-        bool hit = false;
+        unsigned rf = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float m01 = fminf(acc[i][0], acc[i][1]), m23 = fminf(acc[i][2], acc[i][3]);
             const float m45 = fminf(acc[i][4], acc[i][5]), m67 = fminf(acc[i][6], acc[i][7]);
             const float m = fminf(fminf(m01, m23), fminf(m45, m67));
-            hit |= (m < thr[i]);
+            rf |= (m < thr[i]) ? (1u << i) : 0u;
         }
-        if (__any_sync(FULL, hit)) {
-            // ---- rare path: cooperative inserts, candidate by candidate
-            const uint32_t cbase = (uint32_t)t * GMD_TW;
+        if (__any_sync(FULL, rf != 0)) {
+            // ---- rare path.  Phase 1: every lane queues its hits on the owning query;
+            // phase 2: lane L drains query L's queue into its heap.  Rounds repeat while a
+            // queue overflowed (only during list warm-up).
+            const unsigned rows = __reduce_or_sync(FULL, rf);
+            const uint32_t cbase = (uint32_t)t * GMD_TW + (lc << 2);
+            unsigned pend[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                unsigned hm = 0;
+                pend[i] = 0;
+                if (rows & (1u << i)) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) hm |= (acc[i][j] < thr[i]) ? (1u << j) : 0u;
-                unsigned bal = __ballot_sync(FULL, hm != 0);
-                while (bal) {
-                    const int src = __ffs(bal) - 1;
-                    bal &= bal - 1;
-                    unsigned shm = __shfl_sync(FULL, hm, src);
-                    const int ql = ((i >> 2) << 4) + ((src >> 3) << 2) + (i & 3);
-                    uint64_t* lst = lists + (size_t)(warp * 32 + ql) * kk;
-                    while (shm) {
-                        const int j = __ffs(shm) - 1;
-                        shm &= shm - 1;
-                        const float v = __shfl_sync(FULL, sel8(acc[i], j), src);
-                        const uint32_t cidx = cbase + ((j >> 2) << 5) + ((src & 7) << 2) + (j & 3);
-                        warp_insert(lst, kk, v, cidx, lane, &thr_s[warp * 32 + ql]);
-                    }
+                    for (int j = 0; j < 8; ++j) pend[i] |= (acc[i][j] < thr[i]) ? (1u << j) : 0u;
                 }
             }
-            __syncwarp();
+            bool more;
+            do {
+                bool left = false;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) thr[i] = thr_s[warp * 32 + ((i >> 2) << 4) + (lq << 2) + (i & 3)];
+                for (int i = 0; i < 8; ++i) {
+                    if (!(rows & (1u << i))) continue;  // warp-uniform
+                    const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (pend[i] & (1u << j)) {
+                            const int slot = atomicAdd(&wcnt[ql], 1);
+                            if (slot < QCAP) {
+                                wqueue[ql * QCAP + slot] = gmd_key(acc[i][j], cbase + ((j >> 2) << 5) + (j & 3));
+                                pend[i] &= ~(1u << j);
+                            } else {
+                                left = true;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                {
+                    const int n = min(wcnt[lane], QCAP);
+                    if (n > 0) {
+                        uint64_t* h = wheap + (size_t)lane * kkp;
+                        for (int r = 0; r < n; ++r) {
+                            const uint64_t key = wqueue[lane * QCAP + r];
+                            if (key < h[0]) heap_replace_root(h, kk, key);
+                        }
+                        const uint64_t root = h[0];
+                        wthr[lane] = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000)
+                                                             : gmd_unflip((uint32_t)(root >> 32));
+                        wcnt[lane] = 0;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) thr[i] = wthr[((i >> 2) << 4) + (lq << 2) + (i & 3)];
+                more = __any_sync(FULL, left);
+                if (more) {
+                    // drop queued-out hits that no longer beat the refreshed thresholds
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (pend[i]) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (!(acc[i][j] < thr[i])) pend[i] &= ~(1u << j);
+                        }
+                    }
+                }
+            } while (more);
         }
     }
 
-    // ---- write this warp's lists: cand_*[q][split][kk]
+    // ---- write this warp's proposals: cand_*[q][split][kk], cand_tau[q][split]
     __syncwarp();
     for (int ql = 0; ql < 32; ++ql) {
         const long long q = q0 + warp * 32 + ql;
         if (q >= p.Nq) break;
-        const uint64_t* lst = lists + (size_t)(warp * 32 + ql) * kk;
+        const uint64_t* h = wheap + (size_t)ql * kkp;
         const float qnv = qn[warp * 32 + ql];
         const size_t ob = ((size_t)q * p.nsplit + split) * kk;
         for (int x = lane; x < kk; x += 32) {
-            const uint64_t key = lst[x];
+            const uint64_t key = h[x];
             const uint32_t li = (uint32_t)key;
             float v = gmd_unflip((uint32_t)(key >> 32));
             uint32_t oi = GMD_EMPTY_IDX;
@@ -291,6 +369,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
             p.cand_idx[ob + x] = oi;
             p.cand_val[ob + x] = v;
         }
+        if (lane == 0) {
+            // every candidate of this split that is NOT in the heap has an FP32 value >= tau
+            float tau = wthr[ql];
+            if (FORM == GMD_FORM_EXPANDED && h[0] != GMD_EMPTY_KEY) tau = fmaxf(tau + qnv, 0.0f);
+            p.cand_tau[(size_t)q * p.nsplit + split] = tau;
+        }
     }
 }
 
@@ -298,7 +382,7 @@ template <int D, int FORM, int NW, int NST>
 static size_t scan_smem_bytes(int kk) {
     constexpr int BQ = NW * 32;
     constexpr int TILE_F = (D + 1) * GMD_TW;
-    return (size_t)(NST * TILE_F + D * BQ + 2 * BQ) * 4 + 2 * NST * 8 + (size_t)BQ * kk * 8;
+    return (size_t)(NST * TILE_F + D * BQ + 3 * BQ) * 4 + 2 * NST * 8 + (size_t)BQ * QCAP * 8 + (size_t)BQ * (kk | 1) * 8;
 }
 
 template <int D, int FORM, int NW, int NST>

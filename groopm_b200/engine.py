@@ -66,6 +66,7 @@ class KnnPipeline:
         center [D] f64 | stats [4] f32 | flags [4] i32
         ctiles / qtiles  FP32 profile tiles  [ntiles][DP+1][64]
         cand_idx / cand_val                  [Nq][nsplit][kk]   proposals of the FP32 scan
+        cand_tau                             [Nq][nsplit]       bound on everything not proposed
         out_idx [Nq, k] i32, out_dist [Nq, k] f64
 
     ``run`` = col_mean -> prep -> scan -> refine -> exact_rows, all stream-ordered.
@@ -100,6 +101,7 @@ class KnnPipeline:
         m = self.nq * self.nsplit * self.kk
         self.cand_idx = torch.empty(m, dtype=torch.int32, **e)
         self.cand_val = torch.empty(m, dtype=torch.float32, **e)
+        self.cand_tau = torch.empty(self.nq * self.nsplit, dtype=torch.float32, **e)
         self.fail_rows = torch.empty(self.nq, dtype=torch.int32, **e)
         self.out_idx = torch.empty((self.nq, self.k), dtype=torch.int32, **e)
         self.out_dist = torch.empty((self.nq, self.k), dtype=torch.float64, **e)
@@ -125,12 +127,12 @@ class KnnPipeline:
     def scan(self):
         _lib.check(self.lib.gmd_scan_topk_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d,
                                               self.form, self.kk, self.nsplit, 0, _ptr(self.cand_idx),
-                                              _ptr(self.cand_val), _stream_ptr()))
+                                              _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))
 
     def refine(self, q: torch.Tensor, c: torch.Tensor):
         _lib.check(self.lib.gmd_refine_topk_f64(
             _ptr(q), self.nq, _ptr(c), self.nc, self.d, _ptr(self.center), self.k, self.kk, self.nsplit,
-            self.metric, self.form, _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.stats),
+            self.metric, self.form, _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau), _ptr(self.stats),
             _ptr(self.out_idx), _ptr(self.out_dist), _ptr(self.flags) + 4, _ptr(self.fail_rows), _stream_ptr()))
 
     def exact_rows(self, q: torch.Tensor, c: torch.Tensor):

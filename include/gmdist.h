@@ -104,12 +104,14 @@ GMD_API int gmd_prep_f64(const double* X, int64_t N, int D, const double* center
 
 /* The hot kernel: FP32 distance tiles + fused warp-level top-kk selection; the
  * Nq x Nc matrix is never materialised.  Candidates are cut into nsplit contiguous
- * ranges; for each (query, split) the kk best (value, index) pairs are written to
- * cand_idx / cand_val [Nq][nsplit][kk] (index 0xFFFFFFFF == empty slot).
+ * ranges; for each (query, split) the kk best (value, index) pairs are written, in no
+ * particular order, to cand_idx / cand_val [Nq][nsplit][kk] (index 0xFFFFFFFF == empty
+ * slot) and cand_tau [Nq][nsplit] receives the FP32 value that every candidate of the
+ * split NOT in the list is known to reach or exceed (+inf if all were listed).
  * c_index_offset is added to every candidate index (row-sharded candidates).          */
 GMD_API int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc,
                       int D, int form, int kk, int nsplit, int64_t c_index_offset,
-                      uint32_t* cand_idx, float* cand_val, void* stream);
+                      uint32_t* cand_idx, float* cand_val, float* cand_tau, void* stream);
 
 /* float64 re-rank of the proposed candidates from the ORIGINAL rows, lowest-index tie
  * rule, plus the per-row certificate; uncertified rows are appended to fail_rows
@@ -117,7 +119,8 @@ GMD_API int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* ctil
 GMD_API int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
                         const double* center, int k, int kk, int nsplit, int metric,
                         int form, const uint32_t* cand_idx, const float* cand_val,
-                        const float* stats, int32_t* out_idx, double* out_dist,
+                        const float* cand_tau, const float* stats, int32_t* out_idx,
+                        double* out_dist,
                         int32_t* fail_count, int32_t* fail_rows, void* stream);
 
 /* exact float64 scan of all candidates for the listed rows (reads the count on device) */
