@@ -1,6 +1,7 @@
 // C ABI glue: error state, policy helpers, the device-level pipeline and the
 // host-level drop-ins (see include/gmdist.h for the reference call sites).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,6 +32,10 @@ extern "C" int gmd_pick_kk(int k) { return k + std::min(8, std::max(3, k / 4)); 
 
 extern "C" int gmd_pick_nsplit(int64_t Nq, int64_t Nc, int D, int kk) {
     (void)kk;
+    if (const char* env = getenv("GMD_NSPLIT")) {  // tuning / profiling override
+        const int v = atoi(env);
+        if (v >= 1) return (int)std::min<int64_t>(v, std::max<int64_t>(1, gmd_ntiles(Nc)));
+    }
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int DP = gmd_scan_pad_dim(D);

@@ -84,22 +84,36 @@ __global__ void __launch_bounds__(256) prep_kernel(const double* __restrict__ X,
     }
 }
 
-// FP32 FFMA peak probe: 16 independent chains per thread, all operands in registers.
+// FP32 FFMA peak probe: the same 8x8 register-tile outer product as the scan's inner loop
+// (64 independent chains, operands already in registers, no memory traffic).
 __global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float* sink) {
-    float a[16];
+    float acc[8][8], a[8], b[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
-    const float m = 0.999f + (float)blockIdx.x * 1e-9f, c = 1e-4f;
+    for (int i = 0; i < 8; ++i) {
+        a[i] = 1.0f + (float)((threadIdx.x + i) & 7) * 1e-7f;
+        b[i] = 1e-3f * (float)(i + 1) + (float)blockIdx.x * 1e-9f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = (float)(i * 8 + j);
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int u = 0; u < 256; ++u) {
+        for (int u = 0; u < 16; ++u) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+        // rotate the operands so the loop body cannot be collapsed
+        const float t = a[0];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) a[i] = a[i + 1];
+        a[7] = t;
     }
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += a[i];
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
     if (s == 123.456f) sink[0] = s;  // keep the chains alive
 }
 
@@ -147,9 +161,9 @@ extern "C" int gmd_fp32_peak_probe(int iters, float* sink, double* flops, void* 
     int dev = 0, sms = 0;
     GMD_CUDA_CHECK(cudaGetDevice(&dev));
     GMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int blocks = sms * 8;
+    const int blocks = sms * 4;
     fp32_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
     GMD_CUDA_CHECK(cudaGetLastError());
-    if (flops) *flops = 2.0 * 16.0 * 256.0 * (double)iters * 256.0 * (double)blocks;
+    if (flops) *flops = 2.0 * 64.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
     return GMD_OK;
 }

@@ -1,0 +1,154 @@
+"""Drop-in mirrors of the reference's call sites on the distance path.
+
+Same names, argument meaning, return layouts and error behaviour as the scipy /
+numpy / GroopM calls they replace; every distance,
+argmin, top-k and radius selection runs in ``libgmdist.so``.  Host-side glue that
+is not distance work (whitening, the inverse-distance weighted moves) stays
+numpy, as in the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine
+from .engine import cdist, pdist, squareform  # noqa: F401  (scipy.spatial.distance names)
+
+
+# ------------------------------------------------------------------ torusMesh.py / som.py
+
+def best_match(flat_nodes, target_vector, rows: int, columns: int):
+    """TorusMesh.bestMatch (torusMesh.py:123-130) -> [row, col] Python ints,
+    including the reference's ``col = loc - row*rows`` arithmetic."""
+    loc = int(engine.bmu(flat_nodes, np.asarray(target_vector, dtype=np.float64)[None, :])[0])
+    row = int(loc / columns)
+    col = loc - (row * rows)
+    return [row, col]
+
+
+def best_match_many(flat_nodes, vectors, rows: int, columns: int):
+    """bestMatch for every row of ``vectors`` in one launch -> (row[], col[]) int64."""
+    loc = np.asarray(engine.bmu(flat_nodes, vectors)).astype(np.int64)
+    row = (loc / columns).astype(np.int64)
+    col = loc - row * rows
+    return row, col
+
+
+def classify_contigs(flat_nodes, block, bin_assignments, rows: int, columns: int):
+    """The per-contig ``SS.classifyContig(block[i])`` loops (refine.py:1219-1222,
+    2137-2138; som.py:572-575) as one call -> int64 bin id per contig."""
+    row, col = best_match_many(flat_nodes, block, rows, columns)
+    return np.asarray(bin_assignments)[row, col].astype(np.int64)
+
+
+def som_train_bmus(flat_nodes, train_vectors, index_array):
+    """The inner ``argmin(cdist(flat_nodes, [trainVector[j]]))`` of SOM.train
+    (som.py:348-353) for all j of one iteration (nodes are frozen inside it)
+    -> (row[], col[]) with ``col = loc - row*cols`` as at som.py:352-353."""
+    tv = np.asarray(train_vectors, dtype=np.float64)[np.asarray(index_array)]
+    return np.asarray(engine.bmu(flat_nodes, tv)).astype(np.int64)
+
+
+# ------------------------------------------------------------------ refine.py
+
+class KDTree:
+    """``scipy.spatial.KDTree(data).query(x, k)`` as used by findMergeGroups
+    (refine.py:653-665): Euclidean, ascending distance, returns (d, i)."""
+
+    def __init__(self, data):
+        self.data = np.ascontiguousarray(data, dtype=np.float64)
+        if self.data.ndim != 2:
+            raise ValueError("data must be 2 dimensions")
+        self.n, self.m = self.data.shape
+
+    def query(self, x, k=1, p=2):
+        if p != 2:
+            raise ValueError("only the Euclidean norm (p=2) is used by the reference")
+        xa = np.asarray(x, dtype=np.float64)
+        single = xa.ndim == 1
+        xq = xa[None, :] if single else xa
+        if xq.shape[-1] != self.m:
+            raise ValueError(f"x must consist of vectors of length {self.m} but has shape {xa.shape}")
+        kk = min(int(k), self.n)
+        idx, dist = engine.knn(xq, self.data, k=kk, metric="euclidean")
+        idx = idx.astype(np.intp)
+        if kk < k:  # scipy pads missing neighbours with (inf, n)
+            pad = k - kk
+            dist = np.concatenate([dist, np.full((len(xq), pad), np.inf)], axis=1)
+            idx = np.concatenate([idx, np.full((len(xq), pad), self.n, dtype=np.intp)], axis=1)
+        if k == 1:
+            dist, idx = dist[:, 0], idx[:, 0]
+        if single:
+            return dist[0], idx[0]
+        return dist, idx
+
+
+def k_dist(bin_k_vals):
+    """RefineEngine.kDist (refine.py:1490-1496): median cityblock pdist of a bin, or None."""
+    return engine.median_dist(bin_k_vals, None, "cityblock")
+
+
+def k_dist_between(k1, k2):
+    """RefineEngine.kDistBetweenBins (refine.py:1502-1503)."""
+    return engine.median_dist(k1, k2, "cityblock")
+
+
+# ------------------------------------------------------------------ cluster.py
+
+def whiten(dat):
+    """cluster.py:488-491 / refine.py:647-651 (host numpy, as in the reference)."""
+    dat = np.asarray(dat, dtype=np.float64)
+    mean = np.mean(dat, axis=0)
+    std = np.std(dat, axis=0)
+    std += np.where(std == 0, 1, 0)
+    return (dat - mean) / std
+
+
+def kth_neighbour_radius(x, eps_neighbours: int, metric="cityblock"):
+    """``np.median(np.sort(squareform(pdist(X, metric)))[:, eps])`` (cluster.py:495-498)
+    without the n x n matrix -> (radius, per-row k-th distances)."""
+    kth = engine.kth_neighbour_dist(x, eps_neighbours, metric)
+    return float(np.median(kth)), kth
+
+
+def two_way_contraction_step(c_dat, k_dat, move: float = 0.1):
+    """The distance-driven part of one twoWayContraction iteration (cluster.py:430,
+    488-498, 530-590): both radii, the radius-neighbour lists with the reference's
+    drop-the-first-neighbour quirk, cross-metric inverse-distance weights and the
+    contraction moves.  The n x n matrices are never built."""
+    c_dat = np.ascontiguousarray(c_dat, dtype=np.float64)
+    k_dat = np.ascontiguousarray(k_dat, dtype=np.float64)
+    n = len(c_dat)
+    eps = int(np.min([10, int(n / 2)]))
+    c_w = whiten(c_dat)
+    c_radius, _ = kth_neighbour_radius(c_w, eps, "cityblock")
+    k_radius, _ = kth_neighbour_radius(k_dat, eps, "cityblock")
+    min_nb = np.max([1, 0.1 * eps])
+
+    def contract(space_x, radius, other_x, other_radius, moved):
+        indptr, indices = engine.radius_neighbours(space_x, radius, "cityblock")
+        counts = np.diff(indptr)
+        keep_row = counts > min_nb
+        # drop the first (lowest-index) neighbour of every kept row: cluster.py:535-536
+        drop = np.zeros(len(indices), dtype=bool)
+        drop[indptr[:-1][counts > 0]] = True
+        row_of = np.repeat(np.arange(n), counts)
+        sel = (~drop) & keep_row[row_of]
+        other = engine.gather_dist(other_x, indptr, indices, "cityblock")
+        inv = 1.0 / (other[sel] + 0.1 * other_radius)
+        rows = row_of[sel]
+        nb = indices[sel].astype(np.int64)
+        sums = np.zeros(n)
+        np.add.at(sums, rows, inv)
+        outs = []
+        for dat in moved:
+            acc = np.zeros_like(dat)
+            np.add.at(acc, rows, dat[nb] * (inv / sums[rows])[:, None])
+            out = np.where(keep_row[:, None], (1 - move) * dat + move * acc, dat)
+            outs.append(out)
+        noise = set(np.flatnonzero(~keep_row).tolist())
+        return outs, noise
+
+    (new_k,), k_noise = contract(c_w, c_radius, k_dat, k_radius, (k_dat,))
+    (new_c,), c_noise = contract(k_dat, k_radius, c_w, c_radius, (c_dat,))
+    return {"k_dat": new_k, "c_dat": new_c, "c_radius": c_radius, "k_radius": k_radius,
+            "k_noise": k_noise, "c_noise": c_noise, "eps": eps}

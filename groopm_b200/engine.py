@@ -246,3 +246,167 @@ def fp32_peak_tflops(iters: int = 64, repeats: int = 5) -> float:
         if r:
             best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
+
+
+# ---------------------------------------------------------------------------
+# float64 pairwise stages (small / medium call sites of the reference)
+
+def _to_dev(t: torch.Tensor, dev) -> torch.Tensor:
+    return t if t.is_cuda else t.to(dev, non_blocking=True)
+
+
+def _out(t: torch.Tensor, as_numpy: bool):
+    return t.cpu().numpy() if as_numpy else t
+
+
+def _check_finite(*tensors):
+    for t in tensors:
+        if not bool(torch.isfinite(t).all().item()):
+            raise FloatingPointError("non-finite value in an input profile")
+
+
+def cdist(xa, xb, metric="euclidean", device=None):
+    """scipy.spatial.distance.cdist(XA, XB, metric) -> [mA, mB] float64, bit-identical
+    values (torusMesh.py:127; som.py:351; refine.py:927, 945, 1006, 1503)."""
+    at, a_np = _as_rows(xa, "XA")
+    bt, _ = _as_rows(xb, "XB")
+    if at.shape[1] != bt.shape[1]:
+        raise ValueError("XA and XB must have the same number of columns "
+                         "(i.e. feature dimension.)")
+    m = _metric(metric)
+    dev = at.device if at.is_cuda else _device(device)
+    with torch.cuda.device(dev):
+        if at.shape[0] == 0 or bt.shape[0] == 0:
+            return _out(torch.empty((at.shape[0], bt.shape[0]), dtype=torch.float64, device=dev), a_np)
+        ad, bd = _to_dev(at, dev), _to_dev(bt, dev)
+        _check_finite(ad, bd)
+        out = torch.empty((ad.shape[0], bd.shape[0]), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().gmd_cdist_f64(_ptr(ad), ad.shape[0], _ptr(bd), bd.shape[0], ad.shape[1], m,
+                                            _ptr(out), _stream_ptr()))
+        return _out(out, a_np)
+
+
+def pdist(x, metric="euclidean", device=None):
+    """scipy.spatial.distance.pdist(X, metric) -> condensed [n(n-1)/2] float64
+    (cluster.py:495, 497; refine.py:1492)."""
+    xt, x_np = _as_rows(x, "X")
+    m = _metric(metric)
+    dev = xt.device if xt.is_cuda else _device(device)
+    n = xt.shape[0]
+    with torch.cuda.device(dev):
+        if n < 2:
+            return _out(torch.empty(0, dtype=torch.float64, device=dev), x_np)
+        xd = _to_dev(xt, dev)
+        _check_finite(xd)
+        out = torch.empty(n * (n - 1) // 2, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().gmd_pdist_f64(_ptr(xd), n, xd.shape[1], m, _ptr(out), _stream_ptr()))
+        return _out(out, x_np)
+
+
+def squareform(v):
+    """scipy.spatial.distance.squareform for the two directions the reference uses
+    (condensed -> square at cluster.py:495; square -> condensed in small2indices math,
+    mstore.py:1880-1888).  Pure index movement, done with numpy/torch indexing."""
+    is_np = not isinstance(v, torch.Tensor)
+    t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)) if is_np else v
+    if t.ndim == 1:
+        m = t.shape[0]
+        n = int(round((1 + (1 + 8 * m) ** 0.5) / 2))
+        if n * (n - 1) // 2 != m:
+            raise ValueError("Incompatible vector size. It must be a binomial coefficient n choose 2 "
+                             "for some integer n >= 2.")
+        out = torch.zeros((n, n), dtype=t.dtype, device=t.device)
+        iu = torch.triu_indices(n, n, 1, device=t.device)
+        out[iu[0], iu[1]] = t
+        out[iu[1], iu[0]] = t
+    elif t.ndim == 2 and t.shape[0] == t.shape[1]:
+        n = t.shape[0]
+        iu = torch.triu_indices(n, n, 1, device=t.device)
+        out = t[iu[0], iu[1]].contiguous()
+    else:
+        raise ValueError("The matrix argument must be square.")
+    return out.numpy() if is_np else out
+
+
+def radius_neighbours(x, radius: float, metric="cityblock", return_dist: bool = False, device=None):
+    """CSR of ``where(D[i, :] <= radius)[0]`` for every row i (ascending indices) without
+    the n x n matrix (cluster.py:533-536, 570-573).  -> (indptr int64 [n+1], indices int32
+    [, dists float64])."""
+    xt, x_np = _as_rows(x, "X")
+    m = _metric(metric)
+    dev = xt.device if xt.is_cuda else _device(device)
+    n, d = xt.shape
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+        xd = _to_dev(xt, dev)
+        _check_finite(xd)
+        if radius != radius:
+            raise FloatingPointError("radius is NaN")
+        counts = torch.empty(n, dtype=torch.int64, device=dev)
+        _lib.check(lib.gmd_radius_count_f64(_ptr(xd), n, d, m, float(radius), _ptr(counts), _stream_ptr()))
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        nnz = int(indptr[-1].item())
+        indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        dists = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev) if return_dist else None
+        _lib.check(lib.gmd_radius_fill_f64(_ptr(xd), n, d, m, float(radius), _ptr(indptr), _ptr(indices),
+                                           _ptr(dists), _stream_ptr()))
+        res = (_out(indptr, x_np), _out(indices[:nnz], x_np))
+        if return_dist:
+            res += (_out(dists[:nnz], x_np),)
+        return res
+
+
+def gather_dist(x, indptr, indices, metric="cityblock", device=None):
+    """Distances of the CSR pairs (i, indices[p]) in the profile space ``x`` -- the
+    ``other_dist_matrix[index][neighbours]`` gathers of cluster.py:547, 583."""
+    xt, x_np = _as_rows(x, "X")
+    m = _metric(metric)
+    dev = xt.device if xt.is_cuda else _device(device)
+    with torch.cuda.device(dev):
+        xd = _to_dev(xt, dev)
+        ip = torch.as_tensor(indptr, dtype=torch.int64).to(dev)
+        ix = torch.as_tensor(indices, dtype=torch.int32).to(dev)
+        out = torch.empty(max(ix.shape[0], 1), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().gmd_gather_dist_f64(_ptr(xd), xd.shape[0], xd.shape[1], m, _ptr(ip), _ptr(ix),
+                                                  _ptr(out), _stream_ptr()))
+        return _out(out[:ix.shape[0]], x_np)
+
+
+def median_dist(a, b=None, metric="cityblock", device=None):
+    """``np.median(cdist(a, b, metric))`` (b given; kDistBetweenBins refine.py:1502-1503)
+    or ``np.median(pdist(a, metric))`` (b None; kDist refine.py:1490-1496) without
+    materialising the block.  Returns a Python float, or None when there are no pairs
+    (refine.py:1493-1496)."""
+    at, _ = _as_rows(a, "XA")
+    m = _metric(metric)
+    dev = at.device if at.is_cuda else _device(device)
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+        ad = _to_dev(at, dev)
+        bd = None
+        if b is not None:
+            bt, _ = _as_rows(b, "XB")
+            if bt.shape[1] != at.shape[1]:
+                raise ValueError("XA and XB must have the same number of columns "
+                                 "(i.e. feature dimension.)")
+            bd = _to_dev(bt, dev)
+            if ad.shape[0] == 0 or bd.shape[0] == 0:
+                return float("nan")  # np.median of an empty block
+            _check_finite(ad, bd)
+        else:
+            if ad.shape[0] < 2:
+                return None
+            _check_finite(ad)
+        ws = torch.empty(lib.gmd_median_workspace_bytes(), dtype=torch.uint8, device=dev)
+        out = torch.empty(1, dtype=torch.float64, device=dev)
+        _lib.check(lib.gmd_median_dist_f64(_ptr(ad), ad.shape[0], _ptr(bd), 0 if bd is None else bd.shape[0],
+                                           ad.shape[1], m, _ptr(out), _ptr(ws), _stream_ptr()))
+        return float(out.item())
+
+
+def kth_neighbour_dist(x, k: int, metric="cityblock", device=None):
+    """``np.sort(squareform(pdist(X, metric)))[:, k]`` -- the k-th smallest entry of every
+    row of the all-pairs matrix, self (0.0) at column 0 (cluster.py:496, 498)."""
+    idx, dist = knn(x, None, k=k + 1, metric=metric, device=device)
+    return dist[:, k]

@@ -22,6 +22,14 @@ import numpy as np
 KMER_DIM = 136  # canonical tetranucleotides (mstore.py:1640-1666)
 
 
+def quantise(x: np.ndarray, bits: int) -> np.ndarray:
+    """Snap to a 2^-bits grid.  The generators go through exp/log/SVD whose last bits vary
+    between CPUs and BLAS builds; on a grid the arrays reproduce bit for bit (the golden
+    fixtures record a SHA-256 of every input they were made from)."""
+    s = float(2 ** bits)
+    return np.round(x * s) / s
+
+
 def _labels(n: int, rng: np.random.Generator) -> tuple[np.ndarray, int]:
     g = max(8, n // 2000)
     return rng.integers(0, g, size=n), g
@@ -143,7 +151,7 @@ def som_nodes(side: int, dim: int, seed: int) -> np.ndarray:
 
 def cfg_knn_rows(n: int, d: int, seed: int, dups: bool = True) -> np.ndarray:
     """Whitened log-coverage rows N x D (cfg2: D=10 seed 2, cfg5: D=30 seed 5)."""
-    x = whitened_log_coverage(coverage_profiles(n, d, seed))
+    x = quantise(whitened_log_coverage(coverage_profiles(n, d, seed)), 20)
     if dups:
         add_duplicates(x, np.random.default_rng(seed + 1000))
     return x
@@ -159,17 +167,17 @@ def cfg_bmu(n: int, side: int, seed: int = 3) -> tuple[np.ndarray, np.ndarray]:
     kpc1 = np.clip(centre[lab] + 0.03 * rng.standard_normal(n), 0.0, None)
     kpc1 -= kpc1.min()
     kpc1 /= kpc1.max()
-    block = som_block(tcp, kpc1)
+    block = quantise(som_block(tcp, kpc1), 24)
     add_duplicates(block, np.random.default_rng(seed + 1000))
-    return block, som_nodes(side, 4, seed + 2)
+    return block, quantise(som_nodes(side, 4, seed + 2), 24)
 
 
 def cfg_core(n: int = 10000, s: int = 3, seed: int = 1) -> dict:
     """cfg1: transformedCP (D=3) and kmerPCs (D=P) for the core-clustering calls."""
     cov = coverage_profiles(n, s, seed)
-    tcp = transform_cp(cov)
-    sigs = kmer_sigs(n, seed)
-    kpcs = kmer_pcs(sigs)
+    tcp = quantise(transform_cp(cov), 16)
+    sigs = quantise(kmer_sigs(n, seed), 34)
+    kpcs = quantise(kmer_pcs(sigs), 20)
     add_duplicates(tcp, np.random.default_rng(seed + 1000))
     return {"cov": cov, "transformedCP": tcp, "kmerSigs": sigs, "kmerPCs": kpcs,
             "kmerNormPC1": kmer_norm_pc1(kpcs)}

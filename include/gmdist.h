@@ -138,6 +138,41 @@ GMD_API int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc
                 int metric, int form, int32_t* out_idx, double* out_dist,
                 void* workspace, size_t workspace_bytes, int32_t* info, void* stream);
 
+/* ------------------------------------------------------------------ float64 pairwise stages
+ * (device pointers; values bit-identical to scipy's cdist/pdist: direct differences,
+ * sequential float64 accumulation)                                                    */
+
+/* cdist(XA, XB, metric) -> out [mA, mB] row-major (torusMesh.py:127, som.py:351,
+ * refine.py:927, 945, 1006, 1503; mstore.py:1915).                                    */
+GMD_API int gmd_cdist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,
+                  double* out, void* stream);
+
+/* pdist(X, metric) -> condensed out [n(n-1)/2], scipy order (cluster.py:495, 497;
+ * refine.py:1492; index map of mstore.py:1880-1888).                                  */
+GMD_API int gmd_pdist_f64(const double* X, int64_t n, int D, int metric, double* out, void* stream);
+
+/* where(D[i, :] <= radius)[0] for every row i without the n x n matrix
+ * (cluster.py:533-536, 570-573): count pass -> caller prefix-sums into indptr [n+1] ->
+ * fill pass writes ascending candidate indices (and, if dists != NULL, distances).    */
+GMD_API int gmd_radius_count_f64(const double* X, int64_t n, int D, int metric, double radius,
+                         int64_t* counts, void* stream);
+GMD_API int gmd_radius_fill_f64(const double* X, int64_t n, int D, int metric, double radius,
+                        const int64_t* indptr, int32_t* indices, double* dists, void* stream);
+
+/* distances of the CSR pairs (i, indices[p]) in ANOTHER profile space: the
+ * k_dist_matrix[index][neighbours] / c_dist_matrix[index][neighbours] gathers of
+ * cluster.py:547, 583.                                                                */
+GMD_API int gmd_gather_dist_f64(const double* X, int64_t n, int D, int metric, const int64_t* indptr,
+                        const int32_t* indices, double* out, void* stream);
+
+/* np.median of a never-materialised distance block by radix select:
+ * B != NULL: median(cdist(A, B, metric))  (kDistBetweenBins, refine.py:1502-1503);
+ * B == NULL: median(pdist(A, metric))     (kDist, refine.py:1490-1496).
+ * out_median: device double[1]; workspace: gmd_median_workspace_bytes() device bytes. */
+GMD_API size_t gmd_median_workspace_bytes(void);
+GMD_API int gmd_median_dist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,
+                        double* out_median, void* workspace, void* stream);
+
 /* split / slack policy shared with the host layer */
 GMD_API int gmd_pick_form(int metric, int D);
 GMD_API int gmd_pick_kk(int k);
