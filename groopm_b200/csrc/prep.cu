@@ -9,6 +9,8 @@
 // reads of 8 consecutive rows of one dimension are two conflict-free LDS.128.
 // Padding rows (beyond N) can never be selected: their norm (expanded form) or
 // first coordinate (direct forms) is huge.
+#include <stdlib.h>
+
 #include "scan_impl.cuh"
 
 namespace {
@@ -117,13 +119,46 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float* sink) 
     if (s == 123.456f) sink[0] = s;  // keep the chains alive
 }
 
+// Same probe with Blackwell's packed FP32 FMA (fma.rn.f32x2 -> SASS FFMA2): two FMAs per
+// issue slot on 64-bit register pairs.
+__global__ void __launch_bounds__(256) fp32x2_peak_kernel(int iters, float* sink) {
+    float2 acc[8][4], a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float av = 1.0f + (float)((threadIdx.x + i) & 7) * 1e-7f;
+        a[i] = make_float2(av, av);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2((float)(i * 8 + j), (float)(i + j));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = make_float2(1e-3f * (float)(j + 1) + (float)blockIdx.x * 1e-9f, 2e-3f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(a[i], b[j], acc[i][j]);
+        }
+        const float2 t = a[0];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) a[i] = a[i + 1];
+        a[7] = t;
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j].x + acc[i][j].y;
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace
 
 int gmd_scan_pad_dim(int D) {
 #define X(d) \
     if (D <= d) return d;
     GMD_SCAN_DIMS(X)
-    GMD_SCAN_DIMS_BIG(X)
 #undef X
     return -1;
 }
@@ -162,7 +197,10 @@ extern "C" int gmd_fp32_peak_probe(int iters, float* sink, double* flops, void* 
     GMD_CUDA_CHECK(cudaGetDevice(&dev));
     GMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int blocks = sms * 4;
-    fp32_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (getenv("GMD_PROBE_SCALAR"))
+        fp32_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    else
+        fp32x2_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
     GMD_CUDA_CHECK(cudaGetLastError());
     if (flops) *flops = 2.0 * 64.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
     return GMD_OK;

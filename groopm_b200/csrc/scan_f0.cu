@@ -5,13 +5,8 @@ int gmd_scan_launch_form0(int DP, const gmd_scan::ScanParams& p, cudaStream_t st
     switch (DP) {
 #define X(d) \
     case d:  \
-        return gmd_scan::scan_launch<d, 0, 8, 4>(p, st);
+        return gmd_scan::scan_dispatch<d, 0>(p, st);
         GMD_SCAN_DIMS(X)
-#undef X
-#define X(d) \
-    case d:  \
-        return gmd_scan::scan_launch<d, 0, 4, 2>(p, st);
-        GMD_SCAN_DIMS_BIG(X)
 #undef X
         default:
             break;

@@ -1,20 +1,27 @@
 // The hot kernel: FP32 distance tiles + fused warp-level top-kk selection.
 //
-// One CTA owns BQ = 32*NW query rows (resident in shared memory for the whole
-// scan) and streams a contiguous range of candidate tiles through an NST-stage
-// shared-memory ring filled by a dedicated producer warp with bulk async copies
-// (cp.async.bulk -> SASS UBLKCP) that complete on mbarriers.  Each compute warp
-// owns 32 of the CTA's queries outright -- its 32q x 64c warp tile is an 8x8
-// register tile per lane -- so the running top-kk sets (shared-memory max-heaps of
-// u64 keys = order-preserving(value) << 32 | index) are warp-private and the
-// warps never synchronise with one another.  The fast path per candidate tile is
-// D x 64 FFMA + a min-tree against the per-query threshold; only when some
-// value beats a threshold does the warp take the insert path (hits are queued per
-// query, then lane L updates the heap of the warp's query L).
+// One CTA owns BQ = 32*NW query rows (resident in shared memory for the whole scan) and
+// streams a contiguous range of 64-candidate tiles through an NST-stage shared-memory ring.
+// A dedicated producer warp fills the ring with bulk async copies (cp.async.bulk -> SASS
+// UBLKCP, the TMA engine without a tensor map) that complete on mbarriers; a stage is one
+// (tile, dimension chunk), so the ring is the same size for D = 4 and D = 136.  Each compute
+// warp owns 32 of the CTA's queries outright: its 32q x 64c warp tile is an 8q x 8c register
+// tile per lane, accumulated with Blackwell's packed FP32 FMA (fma.rn.f32x2 -> SASS FFMA2,
+// two FMAs per issue slot, the query operand broadcast from one 32-bit register).  The
+// running top-kk sets (shared-memory max-heaps of u64 keys = order-preserving(value) << 32 |
+// index) are warp-private, so compute warps never synchronise with one another.
 //
-// Candidate tiles are visited in ascending index order and the threshold test is
-// strict, so equal values keep the lowest index (np.argmin's first-occurrence
-// rule, torusMesh.py:127) no matter how the work is split.
+// Fast path per tile: D x 32 FFMA2 + a min-tree against the per-query threshold.  Only when
+// some value beats a threshold does the warp take the insert path: hits are queued per
+// query, then lane L updates the heap of the warp's query L.
+//
+// Register-tile shape and warp count were chosen by measurement (tools/probe_tile.cu,
+// tools/probe_ffma2.cu): 8x8 with 8+1 warps keeps the compute warps
+// under the 168-register cap of a 9-warp CTA; 8x16 tiles do not run faster.
+//
+// Candidates are visited in ascending index order and the threshold test is strict, so
+// equal values keep the lowest index (np.argmin's first-occurrence rule,
+// torusMesh.py:127) no matter how the work is split.
 #pragma once
 #include "common.cuh"
 
@@ -55,11 +62,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+#define GMD_SMEM_LIMIT (227 * 1024)
+
 struct ScanParams {
     const float* qtiles;
     const float* ctiles;
     long long Nq, Nc;
-    int ntiles_q, ntiles_c;
+    int ntiles_q, ntiles_c;  // allocated tile counts
     int nsplit, kk;
     long long c_index_offset;
     uint32_t* cand_idx;
@@ -67,19 +76,11 @@ struct ScanParams {
     float* cand_tau;
 };
 
-__device__ __forceinline__ float sel8(const float (&a)[8], int j) {
-    float v = a[0];
-#pragma unroll
-    for (int t = 1; t < 8; ++t) v = (j == t) ? a[t] : v;
-    return v;
-}
-
 // Per-query running top-kk set: a binary MAX-heap of u64 keys in shared memory
-// (root = current kk-th best = the threshold).  Each compute warp owns 32 queries
-// and, on the rare path, lane L maintains the heap of the warp's query L by itself,
-// so up to 32 inserts proceed in parallel with no shuffles; the float64 re-rank
-// orders the survivors anyway.  Empty slots hold GMD_EMPTY_KEY (largest key), so a
-// freshly initialised array is already a valid heap.
+// (root = current kk-th best = the threshold).  On the rare path lane L maintains the heap
+// of the warp's query L by itself, so up to 32 inserts proceed in parallel with no
+// shuffles; the float64 re-rank orders the survivors anyway.  Empty slots hold
+// GMD_EMPTY_KEY (largest key), so a freshly initialised array is already a valid heap.
 __device__ __forceinline__ void heap_replace_root(uint64_t* h, int kk, uint64_t key) {
     int pos = 0;
     while (true) {
@@ -96,16 +97,25 @@ __device__ __forceinline__ void heap_replace_root(uint64_t* h, int kk, uint64_t 
     h[pos] = key;
 }
 
-constexpr int QCAP = 8;  // pending-hit queue slots per query and round
+constexpr int QCAP = 8;    // pending-hit queue slots per query and round
 
-// d-loop shape: a straight-line prefix of PRE steps (d = 0 initialises the accumulators)
-// then a rolled loop whose body is U steps, so the hot loop stays inside the
-// instruction cache (a fully unrolled D=30 body is 34 KB of SASS and starves issue).
-__host__ __device__ constexpr int pick_unroll(int D) {
-    if (D <= 9) return D;  // whole thing straight-line
-    int best_u = 8, best_rem = (D - 1) % 8;
+// Dimension chunk per stage: whole rows up to 64 dimensions, else an even split
+// (96 = 3 x 32, 136 = 4 x 34) so the accumulators persist across the chunks of one tile pair.
+__host__ __device__ constexpr int dim_chunk(int D) {
+    if (D <= 64) return D;
+    for (int c = 34; c >= 16; --c)
+        if (D % c == 0) return c;
+    return D;
+}
+
+// d-loop shape inside a chunk: a straight-line prefix of PRE steps then a rolled loop whose
+// body is U steps, so the hot loop stays inside the instruction cache (a fully unrolled
+// D=30 body starves issue with instruction fetch).
+__host__ __device__ constexpr int pick_unroll(int DC) {
+    if (DC <= 9) return DC;  // whole chunk straight-line
+    int best_u = 8, best_rem = (DC - 1) % 8;
     for (int u = 9; u >= 4; --u) {
-        const int rem = (D - 1) % u;
+        const int rem = (DC - 1) % u;
         if (rem < best_rem) {
             best_rem = rem;
             best_u = u;
@@ -114,40 +124,62 @@ __host__ __device__ constexpr int pick_unroll(int D) {
     return best_u;
 }
 
+// Operands of one d-step: 8 query values (broadcast operands) and 8 candidate values
+// (4 packed pairs).
 struct Frag {
-    float4 qa, qb, ca, cb;
+    float4 qa, qb;  // q0..q3, q4..q7
+    float4 c0, c1;  // candidates 0..3 | 4..7
 };
 
 template <int FORM, bool FIRST>
-__device__ __forceinline__ void tile_step(float (&acc)[8][8], const Frag& f, const float (&cn)[8]) {
+__device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f, const float2 (&cn)[4]) {
     const float q[8] = {f.qa.x, f.qa.y, f.qa.z, f.qa.w, f.qb.x, f.qb.y, f.qb.z, f.qb.w};
-    const float c[8] = {f.ca.x, f.ca.y, f.ca.z, f.ca.w, f.cb.x, f.cb.y, f.cb.z, f.cb.w};
+    const float2 c[4] = {make_float2(f.c0.x, f.c0.y), make_float2(f.c0.z, f.c0.w), make_float2(f.c1.x, f.c1.y),
+                         make_float2(f.c1.z, f.c1.w)};
+    const float2 m1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
+        const float2 qq = make_float2(q[i], q[i]);  // folds into FFMA2's scalar-broadcast operand
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int p = 0; p < 4; ++p) {
             if (FORM == GMD_FORM_EXPANDED) {
-                acc[i][j] = fmaf(q[i], c[j], FIRST ? cn[j] : acc[i][j]);
-            } else if (FORM == GMD_FORM_DIRECT_L2) {
-                const float df = q[i] - c[j];
-                acc[i][j] = FIRST ? df * df : fmaf(df, df, acc[i][j]);
+                acc[i][p] = __ffma2_rn(qq, c[p], FIRST ? cn[p] : acc[i][p]);
             } else {
-                const float df = fabsf(q[i] - c[j]);
-                acc[i][j] = FIRST ? df : acc[i][j] + df;
+                const float2 df = __ffma2_rn(c[p], m1, qq);  // q - c
+                if (FORM == GMD_FORM_DIRECT_L2) {
+                    acc[i][p] = FIRST ? __fmul2_rn(df, df) : __ffma2_rn(df, df, acc[i][p]);
+                } else {
+                    acc[i][p].x = FIRST ? fabsf(df.x) : acc[i][p].x + fabsf(df.x);
+                    acc[i][p].y = FIRST ? fabsf(df.y) : acc[i][p].y + fabsf(df.y);
+                }
             }
         }
+    }
 }
+
+template <int D, int NW, int NST>
+struct ScanShape {
+    static constexpr int BQ = NW * 32;
+    static constexpr int DC = dim_chunk(D);             // dimensions per stage
+    static constexpr int NCH = D / DC;                  // stages per tile pair
+    static constexpr int TILE_F = (D + 1) * GMD_TW;     // floats of one HBM tile
+    static constexpr int STAGE_F = (DC + 1) * GMD_TW;   // floats of one stage (chunk rows + norm row)
+    static size_t smem_bytes(int kk) {
+        return (size_t)(NST * STAGE_F + D * BQ + 3 * BQ) * 4 + 2 * NST * 8 + (size_t)BQ * QCAP * 8 +
+               (size_t)BQ * (kk | 1) * 8;
+    }
+};
 
 template <int D, int FORM, int NW, int NST>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanParams p) {
-    constexpr int BQ = NW * 32;
-    constexpr int TILE_F = (D + 1) * GMD_TW;
+    using S = ScanShape<D, NW, NST>;
+    constexpr int BQ = S::BQ, DC = S::DC, NCH = S::NCH, TILE_F = S::TILE_F, STAGE_F = S::STAGE_F;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    constexpr int U = pick_unroll(D);
-    constexpr int PRE = (D <= 9) ? D : 1 + (D - 1) % U;
+    constexpr int U = pick_unroll(DC);
+    constexpr int PRE = (DC <= 9) ? DC : 1 + (DC - 1) % U;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* Cs = reinterpret_cast<float*>(smem_raw);                // NST x [D+1][64]
-    float* Qs = Cs + NST * TILE_F;                                 // [D][BQ]
+    float* Cs = reinterpret_cast<float*>(smem_raw);                // NST x [DC+1][64]
+    float* Qs = Cs + NST * STAGE_F;                                // [D][BQ]
     float* qn = Qs + D * BQ;                                       // [BQ]  ||q||^2 (form 0)
     float* thr_s = qn + BQ;                                        // [BQ]  heap-root value (+inf until full)
     int* qcnt = reinterpret_cast<int*>(thr_s + BQ);                // [BQ]  pending hits this round
@@ -198,13 +230,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
     // no CTA-wide barrier below this line: the producer warp retires early
 
     if (warp == NW) {
-        // ---- producer: keep the ring full
+        // ---- producer: keep the ring full.  Stage `it` = (tile it / NCH, dimension chunk it % NCH).
         if (lane == 0) {
-            for (int t = tb; t < te; ++t) {
-                const int it = t - tb, s = it % NST;
+            const int nit = (te - tb) * NCH;
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % NST;
                 if (it >= NST) mbar_wait(&bars[NST + s], ((it / NST) - 1) & 1);
-                mbar_expect_tx(&bars[s], TILE_F * 4);
-                bulk_g2s(Cs + s * TILE_F, p.ctiles + (size_t)t * TILE_F, TILE_F * 4, &bars[s]);
+                const int t = tb + it / NCH, ch = it % NCH;
+                const float* ta = p.ctiles + (size_t)t * TILE_F;
+                float* dst = Cs + s * STAGE_F;
+                if (NCH == 1) {
+                    mbar_expect_tx(&bars[s], STAGE_F * 4);  // whole tile, norm row included
+                    bulk_g2s(dst, ta, STAGE_F * 4, &bars[s]);
+                } else {
+                    const uint32_t cb = DC * GMD_TW * 4, nb = GMD_TW * 4;
+                    mbar_expect_tx(&bars[s], cb + (ch == 0 ? nb : 0));
+                    bulk_g2s(dst, ta + ch * DC * GMD_TW, cb, &bars[s]);
+                    if (ch == 0) bulk_g2s(dst + DC * GMD_TW, ta + D * GMD_TW, nb, &bars[s]);
+                }
             }
         }
         return;
@@ -221,67 +264,72 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
 #pragma unroll
     for (int i = 0; i < 8; ++i) thr[i] = __int_as_float(0x7f800000);
 
+    int it = 0;
     for (int t = tb; t < te; ++t) {
-        const int it = t - tb, s = it % NST;
-        mbar_wait(&bars[s], (it / NST) & 1);
-        const float* Ct = Cs + s * TILE_F + lc * 4;
-        auto load = [&](int d) {
-            Frag f;
-            f.qa = *reinterpret_cast<const float4*>(Qw + d * BQ);
-            f.qb = *reinterpret_cast<const float4*>(Qw + d * BQ + 16);
-            f.ca = *reinterpret_cast<const float4*>(Ct + d * GMD_TW);
-            f.cb = *reinterpret_cast<const float4*>(Ct + d * GMD_TW + 32);
-            return f;
-        };
-
-        float acc[8][8];
-        float cn[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (FORM == GMD_FORM_EXPANDED) {
-            const float4 na = *reinterpret_cast<const float4*>(Ct + D * GMD_TW);
-            const float4 nb = *reinterpret_cast<const float4*>(Ct + D * GMD_TW + 32);
-            cn[0] = na.x, cn[1] = na.y, cn[2] = na.z, cn[3] = na.w;
-            cn[4] = nb.x, cn[5] = nb.y, cn[6] = nb.z, cn[7] = nb.w;
-        }
-        // one step ahead in registers; reading "row D" at the very end is harmless
-        // (the norm row of the tile / the qn array follow the last coordinate row)
-        Frag cur = load(0);
+        float2 acc2[8][4];
 #pragma unroll
-        for (int d = 0; d < PRE; ++d) {
-            const Frag nxt = load(d + 1);
-            if (d == 0)
-                tile_step<FORM, true>(acc, cur, cn);
-            else
-                tile_step<FORM, false>(acc, cur, cn);
-            cur = nxt;
-        }
-        if (PRE < D) {
+        for (int ch = 0; ch < NCH; ++ch, ++it) {
+            const int s = it % NST;
+            mbar_wait(&bars[s], (it / NST) & 1);
+            const float* Ct = Cs + s * STAGE_F + lc * 4;
+            const float* Qc = Qw + ch * DC * BQ;
+            auto load = [&](int d) {
+                Frag f;
+                f.qa = *reinterpret_cast<const float4*>(Qc + d * BQ);
+                f.qb = *reinterpret_cast<const float4*>(Qc + d * BQ + 16);
+                f.c0 = *reinterpret_cast<const float4*>(Ct + d * GMD_TW);
+                f.c1 = *reinterpret_cast<const float4*>(Ct + d * GMD_TW + 32);
+                return f;
+            };
+            float2 cn[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) cn[x] = make_float2(0.f, 0.f);
+            if (FORM == GMD_FORM_EXPANDED && ch == 0) {
+                const Frag n = load(DC);  // row DC of the stage holds ||c||^2
+                cn[0] = make_float2(n.c0.x, n.c0.y), cn[1] = make_float2(n.c0.z, n.c0.w);
+                cn[2] = make_float2(n.c1.x, n.c1.y), cn[3] = make_float2(n.c1.z, n.c1.w);
+            }
+            // one step ahead in registers; the read one row past the chunk at its end is
+            // harmless (norm row of the stage / next rows of Qs, qn)
+            Frag cur = load(0);
+#pragma unroll
+            for (int d = 0; d < PRE; ++d) {
+                const Frag nxt = load(d + 1);
+                if (d == 0 && ch == 0)
+                    tile_step<FORM, true>(acc2, cur, cn);
+                else
+                    tile_step<FORM, false>(acc2, cur, cn);
+                cur = nxt;
+            }
+            if (PRE < DC) {
 #pragma unroll 1
-            for (int d0 = PRE; d0 < D; d0 += U) {
+                for (int d0 = PRE; d0 < DC; d0 += U) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const Frag nxt = load(d0 + u + 1);
-                    tile_step<FORM, false>(acc, cur, cn);
-                    cur = nxt;
+                    for (int u = 0; u < U; ++u) {
+                        const Frag nxt = load(d0 + u + 1);
+                        tile_step<FORM, false>(acc2, cur, cn);
+                        cur = nxt;
+                    }
                 }
             }
+            // this stage's shared memory is no longer needed by this warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[NST + s]);
         }
-        // this stage's shared memory is no longer needed by this warp
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[NST + s]);
 
         // ---- selection fast path: one min-tree per query row against its threshold
         unsigned rf = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float m01 = fminf(acc[i][0], acc[i][1]), m23 = fminf(acc[i][2], acc[i][3]);
-            const float m45 = fminf(acc[i][4], acc[i][5]), m67 = fminf(acc[i][6], acc[i][7]);
-            const float m = fminf(fminf(m01, m23), fminf(m45, m67));
+            float m = fminf(acc2[i][0].x, acc2[i][0].y);
+#pragma unroll
+            for (int x = 1; x < 4; ++x) m = fminf(m, fminf(acc2[i][x].x, acc2[i][x].y));
             rf |= (m < thr[i]) ? (1u << i) : 0u;
         }
         if (__any_sync(FULL, rf != 0)) {
             // ---- rare path.  Phase 1: every lane queues its hits on the owning query;
             // phase 2: lane L drains query L's queue into its heap.  Rounds repeat while a
-            // queue overflowed (only during list warm-up).
+            // queue overflowed (only during heap warm-up).
             const unsigned rows = __reduce_or_sync(FULL, rf);
             const uint32_t cbase = (uint32_t)t * GMD_TW + (lc << 2);
             unsigned pend[8];
@@ -290,7 +338,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
                 pend[i] = 0;
                 if (rows & (1u << i)) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pend[i] |= (acc[i][j] < thr[i]) ? (1u << j) : 0u;
+                    for (int x = 0; x < 4; ++x) {
+                        pend[i] |= (acc2[i][x].x < thr[i]) ? (1u << (2 * x)) : 0u;
+                        pend[i] |= (acc2[i][x].y < thr[i]) ? (2u << (2 * x)) : 0u;
+                    }
                 }
             }
             bool more;
@@ -305,7 +356,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
                         if (pend[i] & (1u << j)) {
                             const int slot = atomicAdd(&wcnt[ql], 1);
                             if (slot < QCAP) {
-                                wqueue[ql * QCAP + slot] = gmd_key(acc[i][j], cbase + ((j >> 2) << 5) + (j & 3));
+                                // candidate j of this lane: group j>>2 (32 rows apart), element j&3
+                                const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
+                                wqueue[ql * QCAP + slot] = gmd_key(v, cbase + ((j >> 2) << 5) + (j & 3));
                                 pend[i] &= ~(1u << j);
                             } else {
                                 left = true;
@@ -338,8 +391,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
                     for (int i = 0; i < 8; ++i) {
                         if (pend[i]) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (!(acc[i][j] < thr[i])) pend[i] &= ~(1u << j);
+                            for (int x = 0; x < 4; ++x) {
+                                if (!(acc2[i][x].x < thr[i])) pend[i] &= ~(1u << (2 * x));
+                                if (!(acc2[i][x].y < thr[i])) pend[i] &= ~(2u << (2 * x));
+                            }
                         }
                     }
                 }
@@ -379,31 +434,35 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
 }
 
 template <int D, int FORM, int NW, int NST>
-static size_t scan_smem_bytes(int kk) {
-    constexpr int BQ = NW * 32;
-    constexpr int TILE_F = (D + 1) * GMD_TW;
-    return (size_t)(NST * TILE_F + D * BQ + 3 * BQ) * 4 + 2 * NST * 8 + (size_t)BQ * QCAP * 8 + (size_t)BQ * (kk | 1) * 8;
-}
-
-template <int D, int FORM, int NW, int NST>
 static int scan_launch(const ScanParams& p, cudaStream_t st) {
-    constexpr int BQ = NW * 32;
-    const size_t smem = scan_smem_bytes<D, FORM, NW, NST>(p.kk);
-    GMD_REQUIRE(smem <= 227 * 1024, GMD_ERR_UNSUPPORTED,
+    using S = ScanShape<D, NW, NST>;
+    const size_t smem = S::smem_bytes(p.kk);
+    GMD_REQUIRE(smem <= GMD_SMEM_LIMIT, GMD_ERR_UNSUPPORTED,
                 "scan: D=%d kk=%d needs %zu B of shared memory (> 227 KB)", D, p.kk, smem);
     auto kern = scan_topk_kernel<D, FORM, NW, NST>;
     GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((p.Nq + BQ - 1) / BQ), (unsigned)p.nsplit);
+    dim3 grid((unsigned)((p.Nq + S::BQ - 1) / S::BQ), (unsigned)p.nsplit);
     kern<<<grid, (NW + 1) * 32, smem, st>>>(p);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }
 
+// 8 compute warps (256 queries) per CTA when the heaps fit in shared memory, otherwise 4
+template <int D, int FORM>
+static int scan_dispatch(const ScanParams& p, cudaStream_t st) {
+    if constexpr (D <= 64) {
+        if (ScanShape<D, 8, 4>::smem_bytes(p.kk) <= GMD_SMEM_LIMIT) return scan_launch<D, FORM, 8, 4>(p, st);
+        return scan_launch<D, FORM, 4, 4>(p, st);
+    } else {
+        return scan_launch<D, FORM, 4, 3>(p, st);
+    }
+}
+
 }  // namespace gmd_scan
 
 // padded dimensions the scan is instantiated for; gmd_scan_pad_dim(D) is the smallest >= D
-#define GMD_SCAN_DIMS(X) X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(20) X(24) X(28) X(30) X(32) X(40) X(48) X(64)
-#define GMD_SCAN_DIMS_BIG(X) X(96) X(136)
+#define GMD_SCAN_DIMS(X) \
+    X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(20) X(24) X(28) X(30) X(32) X(40) X(48) X(64) X(96) X(136)
 
 int gmd_scan_pad_dim(int D);
 int gmd_scan_launch_form0(int DP, const gmd_scan::ScanParams& p, cudaStream_t st);

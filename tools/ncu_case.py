@@ -1,14 +1,16 @@
-"""One short pipeline run for ncu captures: python tools/ncu_case.py N D k metric [nq]."""
+"""One short pipeline run for ncu captures: python tools/ncu_case.py N D k [metric] [nq]."""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 from groopm_b200 import engine, synth
 n, d, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 metric = sys.argv[4] if len(sys.argv) > 4 else "euclidean"
+nq = int(sys.argv[5]) if len(sys.argv) > 5 else n
 x = synth.cfg_knn_rows(n, d, 5)
 xd = torch.from_numpy(x).cuda()
-pipe = engine.KnnPipeline(n, n, d, k, metric, same=True)
+qd = xd if nq == n else xd[:nq].contiguous()
+pipe = engine.KnnPipeline(nq, n, d, k, metric, same=(nq == n))
 for _ in range(2):
-    pipe.run(xd, xd)
+    pipe.run(qd, xd)
 torch.cuda.synchronize()
-print("ok", pipe.exact_row_count())
+print("ok", pipe.exact_row_count(), pipe.nsplit)
