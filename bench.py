@@ -246,7 +246,7 @@ def engine_arm(args):
         out_dist_host.copy_(dist_[:n_local], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    peak_probe = engine.fp32_peak_tflops(iters=256)          # measured FFMA peak of this GPU
+    peak_probe = engine.fp32_peak_tflops()          # measured FFMA peak of this GPU
 
     # ---- (A) device-resident throughput
     for _ in range(args.warmup):

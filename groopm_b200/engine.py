@@ -230,8 +230,9 @@ def knn_host(q: np.ndarray, c: Optional[np.ndarray], k: int, metric="euclidean")
     return out_i, out_d
 
 
-def fp32_peak_tflops(iters: int = 64, repeats: int = 5) -> float:
-    """Measured FFMA peak of the current device (TFLOP/s), best of ``repeats``."""
+def fp32_peak_tflops(iters: int = 4096, repeats: int = 3) -> float:
+    """Measured FP32 FMA peak of the current device (TFLOP/s), best of ``repeats``: a register-only
+    8x8 outer-product stream of packed FMAs (FFMA2), long enough (~15 ms) that launch gaps vanish."""
     lib = _lib.lib()
     dev = _device()
     sink = torch.zeros(4, dtype=torch.float32, device=dev)

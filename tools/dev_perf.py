@@ -43,7 +43,7 @@ def run(name, q, c, k, metric, form=None, peak=None):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg2", "cfg3", "cfg5s"]
     print(torch.cuda.get_device_name(0))
-    peak = engine.fp32_peak_tflops(iters=256)
+    peak = engine.fp32_peak_tflops()
     print("fp32 probe peak TFLOP/s:", peak, flush=True)
     if "cfg2" in which:
         x = synth.cfg_knn_rows(100_000, 10, 2)
