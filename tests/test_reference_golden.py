@@ -1,0 +1,111 @@
+"""The oracle (CPU) and the CUDA path (GPU) against outputs of the REFERENCE ITSELF.
+
+``tests/golden/ref_*.npz`` were produced by ``tests/golden/make_reference_golden.py``,
+which executes the reference's own ``TorusMesh.bestMatch`` (torusMesh.py:123-130),
+``SOM.classifyContig`` (som.py:572-575), ``ClusterEngine.twoWayContraction``
+(cluster.py:411-600) and ``RefineEngine.kDist`` / ``kDistBetweenBins`` / ``kDistMergedBins``
+(refine.py:1490-1503) from /root/reference under Python 3.  Inputs travel inside the
+fixtures, so nothing here depends on regenerating them or on /root/reference."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+# ------------------------------------------------------------------ CPU: oracle == reference
+
+def test_oracle_bestmatch_equals_reference(golden):
+    g = golden("ref_bestmatch.npz")
+    nodes, x, rc = g["nodes"], g["x"], g["rc"]
+    flat = nodes.reshape(-1, 4)
+    loc = oracle.bmu_batch(flat, x)
+    assert np.array_equal(loc, rc[:, 0] * 24 + rc[:, 1])     # square mesh: [row, col] <-> flat index
+    for i in range(0, len(x), 97):
+        assert oracle.best_match(flat, x[i], 24, 24) == rc[i].tolist()
+    # duplicates and masked (-1) nodes: first minimum wins, masked nodes never do
+    assert rc[50].tolist() == [2, 9] and rc[51].tolist() == [0, 0]
+    assert not np.any((rc[52:, 0] == 3) & (rc[52:, 1] == 5))  # rows 52.. are data in [0, 1]
+    # non-square mesh: the reference's col = loc - row*rows (torusMesh.py:128-129)
+    flat2 = g["nodes2"].reshape(-1, 3)
+    got = np.array([oracle.best_match(flat2, v, 12, 20) for v in g["x2"]])
+    assert np.array_equal(got, g["rc2"])
+    assert np.array_equal(oracle.classify_contigs(flat, x, g["bin_assignments"], 24, 24), g["bids"])
+
+
+def test_oracle_contraction_equals_reference(golden):
+    g = golden("ref_contraction.npz")
+    for tag in "abc":
+        got = oracle.two_way_contraction_step(g[f"{tag}_transformedCP"], g[f"{tag}_kmerPCs"])
+        assert got["eps"] == int(g[f"{tag}_eps_neighbours"])
+        assert got["c_radius"] == float(g[f"{tag}_c_radius"]) and got["k_radius"] == float(g[f"{tag}_k_radius"])
+        assert np.array_equal(got["k_dat"], g[f"{tag}_k_dat"]) and np.array_equal(got["c_dat"], g[f"{tag}_c_dat"])
+        assert sorted(got["k_noise"]) == g[f"{tag}_k_noise"].tolist()
+        assert sorted(got["c_noise"]) == g[f"{tag}_c_noise"].tolist()
+
+
+def _kdist_cases(g):
+    rows = [g[f"rows{i}"] for i in range(int(g["n_sets"]))]
+    return g["kmerPCs"], rows
+
+
+def test_oracle_kdist_equals_reference(golden):
+    g = golden("ref_kdist.npz")
+    pcs, rows = _kdist_cases(g)
+    for r, want in zip(rows, g["k_dist"]):
+        got = oracle.k_dist(pcs[r])
+        assert (got is None and np.isnan(want)) or got == want
+    for (a, b), want in zip(g["pairs"], g["k_dist_between"]):
+        assert oracle.k_dist_between(pcs[rows[a]], pcs[rows[b]]) == want
+    for (a, b), want in zip(g["pairs"], g["k_dist_merged"]):
+        assert oracle.k_dist(pcs[np.concatenate((rows[a], rows[b]))]) == want
+
+
+# ------------------------------------------------------------------ GPU: engine == reference
+
+@pytest.mark.gpu
+def test_engine_bestmatch_equals_reference(cuda, golden):
+    from groopm_b200 import dropin, engine
+
+    g = golden("ref_bestmatch.npz")
+    nodes, x, rc = g["nodes"], g["x"], g["rc"]
+    flat = nodes.reshape(-1, 4)
+    row, col = dropin.best_match_many(flat, x, 24, 24)
+    assert np.array_equal(np.stack([row, col], 1), rc)
+    for i in (0, 50, 51, 1234):
+        assert dropin.best_match(flat, x[i], 24, 24) == rc[i].tolist()
+    flat2 = g["nodes2"].reshape(-1, 3)
+    row2, col2 = dropin.best_match_many(flat2, g["x2"], 12, 20)
+    assert np.array_equal(np.stack([row2, col2], 1), g["rc2"])
+    assert np.array_equal(dropin.classify_contigs(flat, x, g["bin_assignments"], 24, 24), g["bids"])
+    assert np.array_equal(engine.bmu(flat, x), rc[:, 0] * 24 + rc[:, 1])
+
+
+@pytest.mark.gpu
+def test_engine_contraction_equals_reference(cuda, golden):
+    from groopm_b200 import dropin
+
+    g = golden("ref_contraction.npz")
+    for tag in "abc":
+        got = dropin.two_way_contraction_step(g[f"{tag}_transformedCP"], g[f"{tag}_kmerPCs"])
+        # radii, neighbour lists and noise sets are distance work: exact
+        assert got["c_radius"] == float(g[f"{tag}_c_radius"]) and got["k_radius"] == float(g[f"{tag}_k_radius"])
+        assert sorted(got["k_noise"]) == g[f"{tag}_k_noise"].tolist()
+        assert sorted(got["c_noise"]) == g[f"{tag}_c_noise"].tolist()
+        # the weighted moves are host numpy sums in a different association order
+        np.testing.assert_allclose(got["k_dat"], g[f"{tag}_k_dat"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(got["c_dat"], g[f"{tag}_c_dat"], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_engine_kdist_equals_reference(cuda, golden):
+    from groopm_b200 import dropin
+
+    g = golden("ref_kdist.npz")
+    pcs, rows = _kdist_cases(g)
+    for r, want in zip(rows, g["k_dist"]):
+        got = dropin.k_dist(pcs[r])
+        assert (got is None and np.isnan(want)) or got == want
+    for (a, b), want in zip(g["pairs"], g["k_dist_between"]):
+        assert dropin.k_dist_between(pcs[rows[a]], pcs[rows[b]]) == want
+    for (a, b), want in zip(g["pairs"], g["k_dist_merged"]):
+        assert dropin.k_dist(pcs[np.concatenate((rows[a], rows[b]))]) == want
