@@ -11,9 +11,11 @@
 // running top-kk sets (shared-memory max-heaps of u64 keys = order-preserving(value) << 32 |
 // index) are warp-private, so compute warps never synchronise with one another.
 //
-// Fast path per tile: D x 32 FFMA2 + a min-tree against the per-query threshold.  Only when
-// some value beats a threshold does the warp take the insert path: hits are queued per
-// query, then lane L updates the heap of the warp's query L.
+// Fast path per tile: D x 32 FFMA2 + a min-tree against the per-query threshold.  A lane
+// whose tile holds a value under a threshold appends (value, index) to that query's
+// shared-memory queue and carries on; the queues are folded into the heaps (lane L owns
+// query L) only when one of them is filling up, so heap maintenance is amortised over
+// many hits and most tiles with a hit cost one atomic and one store.
 //
 // Register-tile shape and warp count were chosen by measurement (tools/probe_tile.cu,
 // tools/probe_ffma2.cu): 8x8 with 8+1 warps keeps the compute warps
@@ -52,6 +54,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// The producer's wait on an EMPTY barrier: the ring is normally full, so this wait lasts a
+// whole tile time; sleep between polls instead of spinning on the issue port that the
+// producer shares with two compute warps.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
 }
 // 1-D bulk async copy global -> shared, completing on an mbarrier (TMA engine, no tensor map)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -97,7 +118,8 @@ __device__ __forceinline__ void heap_replace_root(uint64_t* h, int kk, uint64_t 
     h[pos] = key;
 }
 
-constexpr int QCAP = 8;    // pending-hit queue slots per query and round
+constexpr int QCAP = 16;   // pending-hit queue slots per query
+constexpr int QHIGH = 8;   // a queue this full asks for a drain of the warp's queues
 
 // Dimension chunk per stage: whole rows up to 64 dimensions, else an even split
 // (96 = 3 x 32, 136 = 4 x 34) so the accumulators persist across the chunks of one tile pair.
@@ -235,7 +257,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
             const int nit = (te - tb) * NCH;
             for (int it = 0; it < nit; ++it) {
                 const int s = it % NST;
-                if (it >= NST) mbar_wait(&bars[NST + s], ((it / NST) - 1) & 1);
+                if (it >= NST) mbar_wait_backoff(&bars[NST + s], ((it / NST) - 1) & 1, 20 * DC);
                 const int t = tb + it / NCH, ch = it % NCH;
                 const float* ta = p.ctiles + (size_t)t * TILE_F;
                 float* dst = Cs + s * STAGE_F;
@@ -327,29 +349,25 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
             rf |= (m < thr[i]) ? (1u << i) : 0u;
         }
         if (__any_sync(FULL, rf != 0)) {
-            // ---- rare path.  Phase 1: every lane queues its hits on the owning query;
-            // phase 2: lane L drains query L's queue into its heap.  Rounds repeat while a
-            // queue overflowed (only during heap warm-up).
-            const unsigned rows = __reduce_or_sync(FULL, rf);
+            // ---- hit path.  A lane with a hit only APPENDS (value, index) to the owning
+            // query's queue (one shared-memory atomic + one store); thresholds stay as they
+            // are.  Only when some queue is filling up (>= QHIGH) or overflowed does the warp
+            // drain: lane L folds query L's queue into its heap and refreshes its threshold.
+            // A stale threshold is an upper bound of the true one, so nothing is lost; the
+            // heap orders by the full (value, index) key, so the result does not depend on
+            // the order in which hits were queued.
             const uint32_t cbase = (uint32_t)t * GMD_TW + (lc << 2);
             unsigned pend[8];
+            bool flag = false;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 pend[i] = 0;
-                if (rows & (1u << i)) {
+                if (rf & (1u << i)) {
 #pragma unroll
                     for (int x = 0; x < 4; ++x) {
                         pend[i] |= (acc2[i][x].x < thr[i]) ? (1u << (2 * x)) : 0u;
                         pend[i] |= (acc2[i][x].y < thr[i]) ? (2u << (2 * x)) : 0u;
                     }
-                }
-            }
-            bool more;
-            do {
-                bool left = false;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (!(rows & (1u << i))) continue;  // warp-uniform
                     const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -360,46 +378,78 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
                                 const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
                                 wqueue[ql * QCAP + slot] = gmd_key(v, cbase + ((j >> 2) << 5) + (j & 3));
                                 pend[i] &= ~(1u << j);
+                                flag |= slot >= QHIGH - 1;
                             } else {
-                                left = true;
+                                flag = true;
                             }
                         }
                     }
                 }
-                __syncwarp();
-                {
-                    const int n = min(wcnt[lane], QCAP);
-                    if (n > 0) {
-                        uint64_t* h = wheap + (size_t)lane * kkp;
-                        for (int r = 0; r < n; ++r) {
-                            const uint64_t key = wqueue[lane * QCAP + r];
-                            if (key < h[0]) heap_replace_root(h, kk, key);
+            }
+            if (__any_sync(FULL, flag)) {
+                bool more;
+                do {
+                    __syncwarp();
+                    {
+                        const int n = min(wcnt[lane], QCAP);
+                        if (n > 0) {
+                            uint64_t* h = wheap + (size_t)lane * kkp;
+                            for (int r = 0; r < n; ++r) {
+                                const uint64_t key = wqueue[lane * QCAP + r];
+                                if (key < h[0]) heap_replace_root(h, kk, key);
+                            }
+                            const uint64_t root = h[0];
+                            wthr[lane] = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000)
+                                                                 : gmd_unflip((uint32_t)(root >> 32));
+                            wcnt[lane] = 0;
                         }
-                        const uint64_t root = h[0];
-                        wthr[lane] = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000)
-                                                             : gmd_unflip((uint32_t)(root >> 32));
-                        wcnt[lane] = 0;
                     }
-                }
-                __syncwarp();
+                    __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) thr[i] = wthr[((i >> 2) << 4) + (lq << 2) + (i & 3)];
-                more = __any_sync(FULL, left);
-                if (more) {
-                    // drop queued-out hits that no longer beat the refreshed thresholds
+                    for (int i = 0; i < 8; ++i) thr[i] = wthr[((i >> 2) << 4) + (lq << 2) + (i & 3)];
+                    // hits that found their queue full: retry those that still beat the
+                    // refreshed threshold (only during heap warm-up in practice)
+                    bool left = false;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (pend[i]) {
+                            const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
 #pragma unroll
-                            for (int x = 0; x < 4; ++x) {
-                                if (!(acc2[i][x].x < thr[i])) pend[i] &= ~(1u << (2 * x));
-                                if (!(acc2[i][x].y < thr[i])) pend[i] &= ~(2u << (2 * x));
+                            for (int j = 0; j < 8; ++j) {
+                                if (pend[i] & (1u << j)) {
+                                    const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
+                                    if (!(v < thr[i])) {
+                                        pend[i] &= ~(1u << j);
+                                    } else {
+                                        const int slot = atomicAdd(&wcnt[ql], 1);
+                                        if (slot < QCAP) {
+                                            wqueue[ql * QCAP + slot] = gmd_key(v, cbase + ((j >> 2) << 5) + (j & 3));
+                                            pend[i] &= ~(1u << j);
+                                        } else {
+                                            left = true;
+                                        }
+                                    }
+                                }
                             }
                         }
                     }
-                }
-            } while (more);
+                    more = __any_sync(FULL, left);
+                } while (more);
+            }
         }
+    }
+
+    // ---- fold what is still queued into the heaps
+    __syncwarp();
+    {
+        const int n = min(wcnt[lane], QCAP);
+        uint64_t* h = wheap + (size_t)lane * kkp;
+        for (int r = 0; r < n; ++r) {
+            const uint64_t key = wqueue[lane * QCAP + r];
+            if (key < h[0]) heap_replace_root(h, kk, key);
+        }
+        const uint64_t root = h[0];
+        wthr[lane] = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
     }
 
     // ---- write this warp's proposals: cand_*[q][split][kk], cand_tau[q][split]

@@ -49,6 +49,17 @@ if __name__ == "__main__":
         x = synth.cfg_knn_rows(100_000, 10, 2)
         run("cfg2 100k x10 L2 k16", x, None, 16, "euclidean", peak=peak)
         run("cfg2 100k x10 L1 k16", x, None, 16, "cityblock", peak=peak / 2)
+    if "cfg2split" in which:
+        import os
+        x = synth.cfg_knn_rows(100_000, 10, 2)
+        for ns in (1, 2, 3, 4, 6):
+            os.environ["GMD_NSPLIT"] = str(ns)
+            run(f"cfg2 100k x10 L2 k16 nsplit={ns}", x, None, 16, "euclidean", peak=peak)
+        x = synth.cfg_knn_rows(250_000, 30, 5)
+        for ns in (1, 2, 3):
+            os.environ["GMD_NSPLIT"] = str(ns)
+            run(f"cfg5 250k x30 L2 k32 nsplit={ns}", x, None, 32, "euclidean", peak=peak)
+        del os.environ["GMD_NSPLIT"]
     if "cfg3" in which:
         b, n = synth.cfg_bmu(1_000_000, 64)
         run("cfg3 1M x4 BMU 4096", b, n.reshape(-1, 4), 1, "euclidean", peak=peak)
