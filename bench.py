@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="cfg5_1m_x30_k32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     return ap.parse_args()
 
 
@@ -112,6 +113,48 @@ def reference_arm(args):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def secondary_workloads(engine, synth, torch, peak):
+    """The other single-GPU configurations of BASELINE.json, device-resident, for context
+    (configs[1] 100 k x 10 k=16 both metrics; configs[2] BMU of 1 M contigs on a 64 x 64 mesh)."""
+    out = []
+
+    def run(name, q, c, k, metric, steps=10):
+        same = c is None
+        qd = torch.from_numpy(q).cuda()
+        cd = qd if same else torch.from_numpy(c).cuda()
+        pipe = engine.KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, same=same)
+        for _ in range(3):
+            pipe.run(qd, cd)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            pipe.reset(); pipe.col_mean(cd); pipe.prep_candidates(cd); pipe.prep_queries(qd)
+            if i == steps - 1:
+                s0.record()
+            pipe.scan()
+            if i == steps - 1:
+                s1.record()
+            pipe.refine(qd, cd); pipe.exact_rows(qd, cd)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        scan_ms = s0.elapsed_time(s1)
+        pairs = float(qd.shape[0]) * float(cd.shape[0])
+        tf = 2.0 * qd.shape[1] * pairs / (scan_ms * 1e-3) / 1e12
+        pk = peak if metric == "euclidean" else peak / 2       # L1 has no FMA form: FADD rate
+        out.append({"workload": name, "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "scan_ms": scan_ms,
+                    "scan_tflops": tf, "roofline_frac": tf / pk, "exact_rows": pipe.exact_row_count()})
+
+    x = synth.cfg_knn_rows(100_000, 10, 2)
+    run("cfg2_100k_x10_k16_euclidean", x, None, 16, "euclidean")
+    run("cfg2_100k_x10_k16_cityblock", x, None, 16, "cityblock")
+    block, nodes = synth.cfg_bmu(1_000_000, 64)
+    run("cfg3_bmu_1m_x4_on_64x64", block, nodes.reshape(-1, 4), 1, "euclidean")
+    return out
 
 
 def cpu_baseline_leg(x, k, metric, seconds_target=12.0):
@@ -246,7 +289,8 @@ def engine_arm(args):
         out_dist_host.copy_(dist_[:n_local], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    peak_probe = engine.fp32_peak_tflops()          # measured FFMA peak of this GPU
+    peak_probe = engine.fp32_peak_tflops()                   # measured FFMA2 peak of this GPU (uniform operand)
+    peak_vector = engine.fp32_peak_tflops(form="vector")     # same stream with the scan's operand mix
 
     # ---- (A) device-resident throughput
     for _ in range(args.warmup):
@@ -316,12 +360,15 @@ def engine_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": "gmd_scan::scan_topk_kernel", "achieved": achieved,
                          "peak": peak_probe, "unit": "TFLOP/s", "frac": achieved / peak_probe,
-                         "peak_source": "FFMA probe kernel measured on this GPU in this run "
-                                        "(MEASURED_PEAKS.json has no FP32 entry)",
+                         "peak_source": "FFMA2 probe kernel (uniform-register multiplicand) measured on this GPU "
+                                        "in this run; MEASURED_PEAKS.json has no FP32 entry",
+                         "peak_vector_operands": peak_vector,
                          "peak_nominal": nominal, "frac_of_nominal": (achieved / nominal) if nominal else None,
                          "scan_ms_per_launch": scan_avg_ms_max, "flop_per_launch": launch_flop,
                          "traffic": traffic},
         }
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary_workloads(engine, synth, torch, peak_probe)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(x, k, metric)
         print(json.dumps(line), flush=True)

@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libgmdist.so"
+import os
+
+# GMDIST_LIB: developer override to A/B another build of the same ABI on one GPU box
+LIB_PATH = Path(os.environ.get("GMDIST_LIB") or Path(__file__).resolve().parent / "libgmdist.so")
 
 OK, ERR_BAD_ARG, ERR_NONFINITE, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 L2, L1 = 0, 1

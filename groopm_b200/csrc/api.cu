@@ -48,8 +48,11 @@ extern "C" int gmd_pick_nsplit(int64_t Nq, int64_t Nc, int D, int kk) {
     for (int s = 1; s <= smax; ++s) {
         const double ctas = (double)nqb * s;
         const double waves = std::ceil(ctas / sms);
-        // per-CTA time ~ tiles scanned + a fixed cost for list warm-up and write-out
-        const double cost = waves * ((double)ntiles / s + 24.0);
+        // per-CTA time ~ tiles scanned + the cost of a split's own heap warm-up, hit
+        // handling and write-out, measured at 300-500 tile times on B200 (cfg2 / cfg5 sweeps,
+        // DESIGN.md section 5): cutting the candidates only pays when the query blocks
+        // alone leave most SMs idle
+        const double cost = waves * ((double)ntiles / s + 300.0);
         if (cost < best_cost * 0.98) {
             best_cost = cost;
             best = s;

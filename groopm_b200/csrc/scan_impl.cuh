@@ -12,10 +12,11 @@
 // index) are warp-private, so compute warps never synchronise with one another.
 //
 // Fast path per tile: D x 32 FFMA2 + a min-tree against the per-query threshold.  A lane
-// whose tile holds a value under a threshold appends (value, index) to that query's
-// shared-memory queue and carries on; the queues are folded into the heaps (lane L owns
-// query L) only when one of them is filling up, so heap maintenance is amortised over
-// many hits and most tiles with a hit cost one atomic and one store.
+// whose tile holds values under a threshold appends (index, value) to its OWN cell of the
+// query's pending set in shared memory -- a cell per (lane, register-tile row), its fill
+// count kept in a register nibble -- so a hit costs predicated stores only: no atomics, no
+// cross-lane traffic.  The cells are folded into the heaps (lane L owns query L) only when
+// one of them is full, so heap maintenance is amortised over many hits.
 //
 // Register-tile shape and warp count were chosen by measurement (tools/probe_tile.cu,
 // tools/probe_ffma2.cu): 8x8 with 8+1 warps keeps the compute warps
@@ -118,8 +119,69 @@ __device__ __forceinline__ void heap_replace_root(uint64_t* h, int kk, uint64_t 
     h[pos] = key;
 }
 
-constexpr int QCAP = 16;   // pending-hit queue slots per query
-constexpr int QHIGH = 8;   // a queue this full asks for a drain of the warp's queues
+// Two ways of parking hits until a heap update is worth it, chosen per dimension by
+// measurement:
+//   HP_CELLS  a cell per (lane, register-tile row), fill counts in a register nibble: no
+//             atomics, all flagged rows handled in one sweep -- best when hits are dense
+//             relative to the tile time (expanded form, D <= 16)
+//   HP_QUEUE  one queue per query, slots reserved with a shared-memory atomic, one row per
+//             lane and pass through a scratch row -- least work when hits are sparse
+constexpr int HP_CELLS = 0, HP_QUEUE = 1;
+constexpr int QL = 4;      // HP_CELLS: pending-hit slots per (lane, row) cell; 8 cells per query
+constexpr int QCAP = 16;   // HP_QUEUE: pending-hit slots per query
+constexpr int QHIGH = 8;   // HP_QUEUE: a queue this full asks for a drain of the warp's queues
+__host__ __device__ constexpr int pick_hitpath(int D, int form) {
+    return (form == GMD_FORM_EXPANDED && D <= 16) ? HP_CELLS : HP_QUEUE;
+}
+
+// ---- cold-path helper, deliberately out of line: the hot loop (distance tile + min-tree)
+// must stay resident in the ~6 KB L0 / 32 KB L1.5 instruction caches.
+
+// Lane L folds the 8 cells of query L into its heap and publishes the new threshold.
+// cells: this warp's [8 rows][QL][32 lanes] array of (index, value bits); the cell of
+// (row i, lane s) holds nib(counts of lane s, i) entries.  The query of lane L is row
+// iL = ((L >> 4) << 2) + (L & 3) of the lanes 8*((L >> 2) & 3) + c, c = 0..7.
+static __device__ __noinline__ void drain_cells(uint64_t* h, int kk, const uint2* cells, unsigned cnts, int lane,
+                                                float* thr_out) {
+    const int iL = ((lane >> 4) << 2) + (lane & 3);
+    const int s0 = ((lane >> 2) & 3) << 3;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+        const int n = (int)((__shfl_sync(0xFFFFFFFFu, cnts, s0 + c) >> (4 * iL)) & 15u);
+        for (int r = 0; r < n; ++r) {
+            const uint2 e = cells[(iL * QL + r) * 32 + s0 + c];
+            const uint64_t key = gmd_key(__uint_as_float(e.y), e.x);
+            if (key < h[0]) heap_replace_root(h, kk, key);
+        }
+    }
+    const uint64_t root = h[0];
+    *thr_out = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
+}
+
+// HP_QUEUE: lane L folds query L's queue of raw (index, value bits) pairs into its heap.
+static __device__ __noinline__ void drain_queue(uint64_t* h, int kk, const uint2* q, int* cnt, float* thr_out) {
+    const int n = min(*cnt, QCAP);
+    for (int r = 0; r < n; ++r) {
+        const uint2 e = q[r];
+        const uint64_t key = gmd_key(__uint_as_float(e.y), e.x);
+        if (key < h[0]) heap_replace_root(h, kk, key);
+    }
+    const uint64_t root = h[0];
+    *thr_out = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
+    *cnt = 0;
+}
+
+// predicated 8-byte shared-memory store (kept as a predicated STS, never a branch)
+__device__ __forceinline__ void sts64_if(unsigned ok, uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "@p st.shared.v2.u32 [%1], {%2, %3};\n\t"
+        "}\n" ::"r"(ok),
+        "r"(addr), "r"(a), "r"(b)
+        : "memory");
+}
 
 // Dimension chunk per stage: whole rows up to 64 dimensions, else an even split
 // (96 = 3 x 32, 136 = 4 x 34) so the accumulators persist across the chunks of one tile pair.
@@ -130,20 +192,24 @@ __host__ __device__ constexpr int dim_chunk(int D) {
     return D;
 }
 
-// d-loop shape inside a chunk: a straight-line prefix of PRE steps then a rolled loop whose
-// body is U steps, so the hot loop stays inside the instruction cache (a fully unrolled
-// D=30 body starves issue with instruction fetch).
+// Ring depth: about 32 KB of candidate stages in flight, so that small-D tiles (a few hundred
+// cycles of work each) still hide the ~1 us latency of a bulk copy.
+__host__ __device__ constexpr int pick_nst(int D) {
+    if (D > 64) return 3;
+    const int n = 32768 / ((dim_chunk(D) + 1) * GMD_TW * 4);
+    return n < 4 ? 4 : (n > 12 ? 12 : n);
+}
+
+// d-loop shape inside a chunk: a rolled loop of U steps per iteration, U a divisor of DC.
+// The accumulators are initialised before the loop (from the norm row / zero) and every
+// step has the same shape; with a peeled first step ptxas failed to coalesce the
+// loop-carried accumulators and left up to 37 register moves per iteration in the loop.
 __host__ __device__ constexpr int pick_unroll(int DC) {
-    if (DC <= 9) return DC;  // whole chunk straight-line
-    int best_u = 8, best_rem = (DC - 1) % 8;
-    for (int u = 9; u >= 4; --u) {
-        const int rem = (DC - 1) % u;
-        if (rem < best_rem) {
-            best_rem = rem;
-            best_u = u;
-        }
-    }
-    return best_u;
+    if (DC <= 12) return DC;  // whole chunk straight-line
+    if (DC % 10 == 0) return 10;
+    for (int u = 17; u >= 2; --u)
+        if (DC % u == 0) return u;
+    return DC;
 }
 
 // Operands of one d-step: 8 query values (broadcast operands) and 8 candidate values
@@ -153,8 +219,8 @@ struct Frag {
     float4 c0, c1;  // candidates 0..3 | 4..7
 };
 
-template <int FORM, bool FIRST>
-__device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f, const float2 (&cn)[4]) {
+template <int FORM>
+__device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f) {
     const float q[8] = {f.qa.x, f.qa.y, f.qa.z, f.qa.w, f.qb.x, f.qb.y, f.qb.z, f.qb.w};
     const float2 c[4] = {make_float2(f.c0.x, f.c0.y), make_float2(f.c0.z, f.c0.w), make_float2(f.c1.x, f.c1.y),
                          make_float2(f.c1.z, f.c1.w)};
@@ -165,14 +231,14 @@ __device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f, co
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             if (FORM == GMD_FORM_EXPANDED) {
-                acc[i][p] = __ffma2_rn(qq, c[p], FIRST ? cn[p] : acc[i][p]);
+                acc[i][p] = __ffma2_rn(qq, c[p], acc[i][p]);
             } else {
                 const float2 df = __ffma2_rn(c[p], m1, qq);  // q - c
                 if (FORM == GMD_FORM_DIRECT_L2) {
-                    acc[i][p] = FIRST ? __fmul2_rn(df, df) : __ffma2_rn(df, df, acc[i][p]);
+                    acc[i][p] = __ffma2_rn(df, df, acc[i][p]);
                 } else {
-                    acc[i][p].x = FIRST ? fabsf(df.x) : acc[i][p].x + fabsf(df.x);
-                    acc[i][p].y = FIRST ? fabsf(df.y) : acc[i][p].y + fabsf(df.y);
+                    acc[i][p].x += fabsf(df.x);
+                    acc[i][p].y += fabsf(df.y);
                 }
             }
         }
@@ -182,12 +248,15 @@ __device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f, co
 template <int D, int NW, int NST>
 struct ScanShape {
     static constexpr int BQ = NW * 32;
+    static constexpr int NQT = BQ / GMD_TW;             // query tiles of the CTA
     static constexpr int DC = dim_chunk(D);             // dimensions per stage
     static constexpr int NCH = D / DC;                  // stages per tile pair
     static constexpr int TILE_F = (D + 1) * GMD_TW;     // floats of one HBM tile
     static constexpr int STAGE_F = (DC + 1) * GMD_TW;   // floats of one stage (chunk rows + norm row)
-    static size_t smem_bytes(int kk) {
-        return (size_t)(NST * STAGE_F + D * BQ + 3 * BQ) * 4 + 2 * NST * 8 + (size_t)BQ * QCAP * 8 +
+    static size_t smem_bytes(int kk, int form) {
+        // pending hits: HP_CELLS 8 cells x QL x 8 B per query; HP_QUEUE QCAP x 8 B + count + scratch row
+        const size_t pend = pick_hitpath(D, form) == HP_CELLS ? (size_t)8 * QL * 8 : (size_t)QCAP * 8 + 4 + 32;
+        return (size_t)(NST * STAGE_F + NQT * TILE_F + BQ) * 4 + (2 * NST + 2) * 8 + (size_t)BQ * pend +
                (size_t)BQ * (kk | 1) * 8;
     }
 };
@@ -195,19 +264,25 @@ struct ScanShape {
 template <int D, int FORM, int NW, int NST>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanParams p) {
     using S = ScanShape<D, NW, NST>;
-    constexpr int BQ = S::BQ, DC = S::DC, NCH = S::NCH, TILE_F = S::TILE_F, STAGE_F = S::STAGE_F;
+    constexpr int BQ = S::BQ, NQT = S::NQT, DC = S::DC, NCH = S::NCH, TILE_F = S::TILE_F, STAGE_F = S::STAGE_F;
     constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr int HP = pick_hitpath(D, FORM);
+    constexpr int PEND_B = HP == HP_CELLS ? 8 * QL * 8 : QCAP * 8 + 4 + 32;  // bytes per query
     constexpr int U = pick_unroll(DC);
-    constexpr int PRE = (DC <= 9) ? DC : 1 + (DC - 1) % U;
+    static_assert(DC % U == 0, "d-loop shape");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* Cs = reinterpret_cast<float*>(smem_raw);                // NST x [DC+1][64]
-    float* Qs = Cs + NST * STAGE_F;                                // [D][BQ]
-    float* qn = Qs + D * BQ;                                       // [BQ]  ||q||^2 (form 0)
-    float* thr_s = qn + BQ;                                        // [BQ]  heap-root value (+inf until full)
-    int* qcnt = reinterpret_cast<int*>(thr_s + BQ);                // [BQ]  pending hits this round
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + BQ);       // full[NST], empty[NST]
-    uint64_t* queue = bars + 2 * NST;                              // [BQ][QCAP] pending (value, index)
-    uint64_t* lists = queue + BQ * QCAP;                           // [BQ][kkp]  max-heaps
+    float* Qs = Cs + NST * STAGE_F;                                // NQT x [D+1][64]  (HBM tile layout)
+    float* thr_s = Qs + NQT * TILE_F;                              // [BQ]  heap-root value (+inf until full)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + BQ);      // full[NST], empty[NST], queries, pad
+    unsigned char* pend_raw = reinterpret_cast<unsigned char*>(bars + 2 * NST + 2);
+    // HP_CELLS: NW x [8 rows][QL][32 lanes] (index, value bits)
+    uint2* cells = reinterpret_cast<uint2*>(pend_raw);
+    // HP_QUEUE: [BQ][QCAP] (index, value bits) | [BQ][8] scratch rows | [BQ] counts
+    uint2* queue = reinterpret_cast<uint2*>(pend_raw);
+    float* rowbuf = reinterpret_cast<float*>(pend_raw + (size_t)BQ * QCAP * 8);
+    int* qcnt = reinterpret_cast<int*>(pend_raw + (size_t)BQ * (QCAP * 8 + 32));
+    uint64_t* lists = reinterpret_cast<uint64_t*>(pend_raw + (size_t)BQ * PEND_B);  // [BQ][kkp]  max-heaps
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -220,33 +295,33 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
     const int tb = split * tps;
     const int te = min(p.ntiles_c, tb + tps);
 
-    // ---- stage the CTA's queries: Qs[d][r] (x -2 for the expanded form), qn[r]
-    {
-        const float qscale = (FORM == GMD_FORM_EXPANDED) ? -2.0f : 1.0f;
-        const int qt0 = (int)(q0 / GMD_TW);
-        for (int e = tid; e < (D + 1) * BQ; e += (NW + 1) * 32) {
-            const int d = e / BQ, r = e - d * BQ;
-            const int t = qt0 + (r >> 6);
-            float v = 0.0f;
-            if (t < p.ntiles_q) v = p.qtiles[(size_t)t * TILE_F + d * GMD_TW + (r & 63)];
-            if (d < D)
-                Qs[d * BQ + r] = v * qscale;
-            else
-                qn[r] = v;
+    // ---- stage the CTA's query tiles with bulk copies (they arrive while the heaps are
+    // initialised), then scale them in place (x -2 for the expanded form)
+    const int qt0 = (int)(q0 / GMD_TW);
+    const int nqt = min(NQT, p.ntiles_q - qt0);
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[NST + s], NW);
         }
-        for (int e = tid; e < BQ * kkp; e += (NW + 1) * 32) lists[e] = GMD_EMPTY_KEY;
-        for (int e = tid; e < BQ; e += (NW + 1) * 32) {
-            thr_s[e] = __int_as_float(0x7f800000);
-            qcnt[e] = 0;
-        }
-        if (tid == 0) {
-            for (int s = 0; s < NST; ++s) {
-                mbar_init(&bars[s], 1);
-                mbar_init(&bars[NST + s], NW);
-            }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
+        mbar_init(&bars[2 * NST], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[2 * NST], (uint32_t)nqt * TILE_F * 4);
+        for (int j = 0; j < nqt; ++j)
+            bulk_g2s(Qs + j * TILE_F, p.qtiles + (size_t)(qt0 + j) * TILE_F, TILE_F * 4, &bars[2 * NST]);
+    }
+    for (int e = tid; e < BQ * kkp; e += (NW + 1) * 32) lists[e] = GMD_EMPTY_KEY;
+    for (int e = tid; e < BQ; e += (NW + 1) * 32) {
+        thr_s[e] = __int_as_float(0x7f800000);
+        if (HP == HP_QUEUE) qcnt[e] = 0;
+    }
+    for (int e = nqt * TILE_F + tid; e < NQT * TILE_F; e += (NW + 1) * 32) Qs[e] = 0.0f;  // tiles past the end
+    __syncthreads();
+    mbar_wait(&bars[2 * NST], 0);
+    if (FORM == GMD_FORM_EXPANDED) {
+        for (int e = tid; e < nqt * TILE_F; e += (NW + 1) * 32)
+            if (e % TILE_F < D * GMD_TW) Qs[e] *= -2.0f;
     }
     __syncthreads();
     // no CTA-wide barrier below this line: the producer warp retires early
@@ -257,7 +332,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
             const int nit = (te - tb) * NCH;
             for (int it = 0; it < nit; ++it) {
                 const int s = it % NST;
-                if (it >= NST) mbar_wait_backoff(&bars[NST + s], ((it / NST) - 1) & 1, 20 * DC);
+                if (it >= NST) mbar_wait_backoff(&bars[NST + s], ((it / NST) - 1) & 1, 16 * DC);
                 const int t = tb + it / NCH, ch = it % NCH;
                 const float* ta = p.ctiles + (size_t)t * TILE_F;
                 float* dst = Cs + s * STAGE_F;
@@ -275,68 +350,76 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
         return;
     }
 
-    // ---- compute warps
+    // ---- compute warps: warp w owns queries [32w, 32w+32) = half (w & 1) of query tile w >> 1
     const int lq = lane >> 3, lc = lane & 7;
-    const float* Qw = Qs + warp * 32 + lq * 4;
+    const float* Qw = Qs + (warp >> 1) * TILE_F + (warp & 1) * 32 + lq * 4;
+    const float* qnw = Qs + (warp >> 1) * TILE_F + D * GMD_TW + (warp & 1) * 32;  // ||q||^2 of the warp's queries
     float* wthr = thr_s + warp * 32;
+    uint2* wcells = cells + warp * (8 * QL * 32);
+    const uint32_t mycell = smem_u32(wcells + lane);  // + (row * QL + slot) * 256 bytes
+    unsigned cnts = 0;                                // fill of this lane's 8 cells, a nibble per row
     int* wcnt = qcnt + warp * 32;
-    uint64_t* wqueue = queue + warp * 32 * QCAP;
+    uint2* wqueue = queue + warp * 32 * QCAP;
+    float4* myrow = reinterpret_cast<float4*>(rowbuf + (size_t)(warp * 32 + lane) * 8);
     uint64_t* wheap = lists + (size_t)warp * 32 * kkp;
+    // register copy of the thresholds of this lane's 8 rows (re-reading them from shared
+    // memory every tile put an LDS on the selection's critical path: -2 % at D = 30)
     float thr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) thr[i] = __int_as_float(0x7f800000);
-
-    int it = 0;
+    int s = 0;             // ring stage and its phase parity
+    uint32_t ph = 0;
     for (int t = tb; t < te; ++t) {
         float2 acc2[8][4];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch, ++it) {
-            const int s = it % NST;
-            mbar_wait(&bars[s], (it / NST) & 1);
-            const float* Ct = Cs + s * STAGE_F + lc * 4;
-            const float* Qc = Qw + ch * DC * BQ;
+        for (int ch = 0; ch < NCH; ++ch) {
+            mbar_wait(&bars[s], ph);
+            const float* cp = Cs + s * STAGE_F + lc * 4;   // running operand pointers
+            const float* qp = Qw + ch * DC * GMD_TW;
             auto load = [&](int d) {
                 Frag f;
-                f.qa = *reinterpret_cast<const float4*>(Qc + d * BQ);
-                f.qb = *reinterpret_cast<const float4*>(Qc + d * BQ + 16);
-                f.c0 = *reinterpret_cast<const float4*>(Ct + d * GMD_TW);
-                f.c1 = *reinterpret_cast<const float4*>(Ct + d * GMD_TW + 32);
+                f.qa = *reinterpret_cast<const float4*>(qp + d * GMD_TW);
+                f.qb = *reinterpret_cast<const float4*>(qp + d * GMD_TW + 16);
+                f.c0 = *reinterpret_cast<const float4*>(cp + d * GMD_TW);
+                f.c1 = *reinterpret_cast<const float4*>(cp + d * GMD_TW + 32);
                 return f;
             };
-            float2 cn[4];
+            if (ch == 0) {
+                // accumulators start from ||c||^2 (row DC of the stage) or zero
+                float2 cn[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) cn[x] = make_float2(0.f, 0.f);
-            if (FORM == GMD_FORM_EXPANDED && ch == 0) {
-                const Frag n = load(DC);  // row DC of the stage holds ||c||^2
-                cn[0] = make_float2(n.c0.x, n.c0.y), cn[1] = make_float2(n.c0.z, n.c0.w);
-                cn[2] = make_float2(n.c1.x, n.c1.y), cn[3] = make_float2(n.c1.z, n.c1.w);
-            }
-            // one step ahead in registers; the read one row past the chunk at its end is
-            // harmless (norm row of the stage / next rows of Qs, qn)
-            Frag cur = load(0);
-#pragma unroll
-            for (int d = 0; d < PRE; ++d) {
-                const Frag nxt = load(d + 1);
-                if (d == 0 && ch == 0)
-                    tile_step<FORM, true>(acc2, cur, cn);
-                else
-                    tile_step<FORM, false>(acc2, cur, cn);
-                cur = nxt;
-            }
-            if (PRE < DC) {
-#pragma unroll 1
-                for (int d0 = PRE; d0 < DC; d0 += U) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const Frag nxt = load(d0 + u + 1);
-                        tile_step<FORM, false>(acc2, cur, cn);
-                        cur = nxt;
-                    }
+                for (int x = 0; x < 4; ++x) cn[x] = make_float2(0.f, 0.f);
+                if (FORM == GMD_FORM_EXPANDED) {
+                    const Frag n = load(DC);
+                    cn[0] = make_float2(n.c0.x, n.c0.y), cn[1] = make_float2(n.c0.z, n.c0.w);
+                    cn[2] = make_float2(n.c1.x, n.c1.y), cn[3] = make_float2(n.c1.z, n.c1.w);
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) acc2[i][x] = cn[x];
+            }
+            // software pipeline one step ahead in registers; the read one row past the chunk
+            // at its end is harmless (norm row of the stage / of the query tile)
+            Frag cur = load(0);
+#pragma unroll 1
+            for (int d0 = 0; d0 < DC; d0 += U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const Frag nxt = load(u + 1);
+                    tile_step<FORM>(acc2, cur);
+                    cur = nxt;
+                }
+                qp += U * GMD_TW;
+                cp += U * GMD_TW;
             }
             // this stage's shared memory is no longer needed by this warp
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[NST + s]);
+            if (++s == NST) {
+                s = 0;
+                ph ^= 1;
+            }
         }
 
         // ---- selection fast path: one min-tree per query row against its threshold
@@ -349,108 +432,129 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
             rf |= (m < thr[i]) ? (1u << i) : 0u;
         }
         if (__any_sync(FULL, rf != 0)) {
-            // ---- hit path.  A lane with a hit only APPENDS (value, index) to the owning
-            // query's queue (one shared-memory atomic + one store); thresholds stay as they
-            // are.  Only when some queue is filling up (>= QHIGH) or overflowed does the warp
-            // drain: lane L folds query L's queue into its heap and refreshes its threshold.
-            // A stale threshold is an upper bound of the true one, so nothing is lost; the
-            // heap orders by the full (value, index) key, so the result does not depend on
-            // the order in which hits were queued.
+          if constexpr (HP == HP_CELLS) {
+            // ---- hit path.  Rows with a hit in ANY lane are visited (warp-uniform branches);
+            // a lane appends its values under the threshold to its own cell of that row.
+            // Thresholds stay as they are until a cell fills up: then lane L folds query L's
+            // cells into its heap and refreshes the threshold.  A stale threshold is an upper
+            // bound of the true one, so nothing is lost, and the heap orders by the full
+            // (value, index) key, so the result does not depend on queueing order.
             const uint32_t cbase = (uint32_t)t * GMD_TW + (lc << 2);
-            unsigned pend[8];
-            bool flag = false;
+            unsigned rows = __reduce_or_sync(FULL, rf);
+            unsigned left_lo = 0xFFFFFFFFu, left_hi = 0xFFFFFFFFu;  // values still to be queued, a byte per row
+            bool again;
+            do {
+                bool full = false;
+                unsigned over = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                pend[i] = 0;
-                if (rf & (1u << i)) {
+                for (int i = 0; i < 8; ++i) {
+                    if (rows & (1u << i)) {
+                        const float v[8] = {acc2[i][0].x, acc2[i][0].y, acc2[i][1].x, acc2[i][1].y,
+                                            acc2[i][2].x, acc2[i][2].y, acc2[i][3].x, acc2[i][3].y};
+                        unsigned mask = 0;
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        pend[i] |= (acc2[i][x].x < thr[i]) ? (1u << (2 * x)) : 0u;
-                        pend[i] |= (acc2[i][x].y < thr[i]) ? (2u << (2 * x)) : 0u;
-                    }
-                    const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
+                        for (int j = 0; j < 8; ++j) mask |= (v[j] < thr[i]) ? (1u << j) : 0u;
+                        mask &= ((i < 4 ? left_lo : left_hi) >> ((i & 3) * 8)) & 0xFFu;
+                        const unsigned cnt = (cnts >> (4 * i)) & 15u;
+                        unsigned slot = cnt, lost = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (pend[i] & (1u << j)) {
-                            const int slot = atomicAdd(&wcnt[ql], 1);
-                            if (slot < QCAP) {
-                                // candidate j of this lane: group j>>2 (32 rows apart), element j&3
-                                const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
-                                wqueue[ql * QCAP + slot] = gmd_key(v, cbase + ((j >> 2) << 5) + (j & 3));
-                                pend[i] &= ~(1u << j);
-                                flag |= slot >= QHIGH - 1;
-                            } else {
-                                flag = true;
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            const unsigned b = (mask >> j) & 1u;
+                            const unsigned ok = b & (slot < QL ? 1u : 0u);
+                            // value j: candidate group j>>2 (32 rows apart), element j&3
+                            sts64_if(ok, mycell + (i * QL + slot) * 256u, cbase + ((j >> 2) << 5) + (j & 3),
+                                     __float_as_uint(v[j]));
+                            lost |= (b & (ok ^ 1u)) << j;
+                            slot += b;
                         }
+                        const unsigned fill = min(slot, (unsigned)QL);
+                        cnts = (cnts & ~(15u << (4 * i))) | (fill << (4 * i));
+                        full |= fill == QL;
+                        over |= lost ? (1u << i) : 0u;
+                        if (i < 4)
+                            left_lo = (left_lo & ~(0xFFu << (i * 8))) | (lost << (i * 8));
+                        else
+                            left_hi = (left_hi & ~(0xFFu << ((i - 4) * 8))) | (lost << ((i - 4) * 8));
                     }
                 }
-            }
-            if (__any_sync(FULL, flag)) {
-                bool more;
-                do {
+                again = false;
+                if (__any_sync(FULL, full)) {
                     __syncwarp();
-                    {
-                        const int n = min(wcnt[lane], QCAP);
-                        if (n > 0) {
-                            uint64_t* h = wheap + (size_t)lane * kkp;
-                            for (int r = 0; r < n; ++r) {
-                                const uint64_t key = wqueue[lane * QCAP + r];
-                                if (key < h[0]) heap_replace_root(h, kk, key);
-                            }
-                            const uint64_t root = h[0];
-                            wthr[lane] = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000)
-                                                                 : gmd_unflip((uint32_t)(root >> 32));
-                            wcnt[lane] = 0;
-                        }
-                    }
+                    drain_cells(wheap + (size_t)lane * kkp, kk, wcells, cnts, lane, &wthr[lane]);
+                    cnts = 0;
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) thr[i] = wthr[((i >> 2) << 4) + (lq << 2) + (i & 3)];
-                    // hits that found their queue full: retry those that still beat the
-                    // refreshed threshold (only during heap warm-up in practice)
-                    bool left = false;
+                    for (int ii = 0; ii < 8; ++ii) thr[ii] = wthr[((ii >> 2) << 4) + (lq << 2) + (ii & 3)];
+                    // values that found their cell full (heap warm-up, in practice): once more
+                    rows = __reduce_or_sync(FULL, over);
+                    again = rows != 0;
+                }
+            } while (again);
+          } else {
+            // ---- hit path, HP_QUEUE: a warp-uniform loop in which every lane with hits handles
+            // ONE of its rows per pass.  The row's 8 values go through a 32-byte shared-memory
+            // scratch (stores from the statically indexed registers, one load back), so the
+            // body exists once.  A lane appends (index, value) pairs to the owning query's
+            // queue (one shared-memory atomic reserves the slots); thresholds stay as they
+            // are.  Only when a queue reaches QHIGH entries or overflows does the warp drain.
+            const uint32_t cbase = (uint32_t)t * GMD_TW + (lc << 2);
+            unsigned left = 0;  // values of the current row that found the queue full
+            do {
+                const int i = __ffs(rf) - 1;  // this lane's row for the pass (-1: none)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (pend[i]) {
-                            const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
+                for (int ii = 0; ii < 8; ++ii) {
+                    if (i == ii) {
+                        myrow[0] = make_float4(acc2[ii][0].x, acc2[ii][0].y, acc2[ii][1].x, acc2[ii][1].y);
+                        myrow[1] = make_float4(acc2[ii][2].x, acc2[ii][2].y, acc2[ii][3].x, acc2[ii][3].y);
+                    }
+                }
+                bool drain = false;
+                if (i >= 0) {
+                    const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
+                    const float th = wthr[ql];
+                    const float4 r0 = myrow[0], r1 = myrow[1];
+                    const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    unsigned mask = 0;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (pend[i] & (1u << j)) {
-                                    const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
-                                    if (!(v < thr[i])) {
-                                        pend[i] &= ~(1u << j);
-                                    } else {
-                                        const int slot = atomicAdd(&wcnt[ql], 1);
-                                        if (slot < QCAP) {
-                                            wqueue[ql * QCAP + slot] = gmd_key(v, cbase + ((j >> 2) << 5) + (j & 3));
-                                            pend[i] &= ~(1u << j);
-                                        } else {
-                                            left = true;
-                                        }
-                                    }
-                                }
+                    for (int j = 0; j < 8; ++j) mask |= (v[j] < th) ? (1u << j) : 0u;
+                    if (left) mask &= left;
+                    left = 0;
+                    if (mask) {
+                        int slot = atomicAdd(&wcnt[ql], __popc(mask));
+                        uint2* qd = wqueue + ql * QCAP;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (mask & (1u << j)) {
+                                // value j: candidate group j>>2 (32 rows apart), element j&3
+                                if (slot < QCAP)
+                                    qd[slot] = make_uint2(cbase + ((j >> 2) << 5) + (j & 3), __float_as_uint(v[j]));
+                                else
+                                    left |= 1u << j;
+                                ++slot;
                             }
                         }
+                        drain = slot >= QHIGH;
                     }
-                    more = __any_sync(FULL, left);
-                } while (more);
-            }
+                    if (!left) rf &= rf - 1;  // row done
+                }
+                if (__any_sync(FULL, drain)) {
+                    __syncwarp();
+                    drain_queue(wheap + (size_t)lane * kkp, kk, wqueue + lane * QCAP, &wcnt[lane], &wthr[lane]);
+                    __syncwarp();
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii) thr[ii] = wthr[((ii >> 2) << 4) + (lq << 2) + (ii & 3)];
+                }
+            } while (__any_sync(FULL, rf != 0));
+          }
         }
     }
 
     // ---- fold what is still queued into the heaps
     __syncwarp();
-    {
-        const int n = min(wcnt[lane], QCAP);
-        uint64_t* h = wheap + (size_t)lane * kkp;
-        for (int r = 0; r < n; ++r) {
-            const uint64_t key = wqueue[lane * QCAP + r];
-            if (key < h[0]) heap_replace_root(h, kk, key);
-        }
-        const uint64_t root = h[0];
-        wthr[lane] = (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
-    }
+    if constexpr (HP == HP_CELLS)
+        drain_cells(wheap + (size_t)lane * kkp, kk, wcells, cnts, lane, &wthr[lane]);
+    else
+        drain_queue(wheap + (size_t)lane * kkp, kk, wqueue + lane * QCAP, &wcnt[lane], &wthr[lane]);
 
     // ---- write this warp's proposals: cand_*[q][split][kk], cand_tau[q][split]
     __syncwarp();
@@ -458,7 +562,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
         const long long q = q0 + warp * 32 + ql;
         if (q >= p.Nq) break;
         const uint64_t* h = wheap + (size_t)ql * kkp;
-        const float qnv = qn[warp * 32 + ql];
+        const float qnv = qnw[ql];
         const size_t ob = ((size_t)q * p.nsplit + split) * kk;
         for (int x = lane; x < kk; x += 32) {
             const uint64_t key = h[x];
@@ -486,7 +590,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
 template <int D, int FORM, int NW, int NST>
 static int scan_launch(const ScanParams& p, cudaStream_t st) {
     using S = ScanShape<D, NW, NST>;
-    const size_t smem = S::smem_bytes(p.kk);
+    const size_t smem = S::smem_bytes(p.kk, FORM);
     GMD_REQUIRE(smem <= GMD_SMEM_LIMIT, GMD_ERR_UNSUPPORTED,
                 "scan: D=%d kk=%d needs %zu B of shared memory (> 227 KB)", D, p.kk, smem);
     auto kern = scan_topk_kernel<D, FORM, NW, NST>;
@@ -500,11 +604,12 @@ static int scan_launch(const ScanParams& p, cudaStream_t st) {
 // 8 compute warps (256 queries) per CTA when the heaps fit in shared memory, otherwise 4
 template <int D, int FORM>
 static int scan_dispatch(const ScanParams& p, cudaStream_t st) {
+    constexpr int NST = pick_nst(D);
     if constexpr (D <= 64) {
-        if (ScanShape<D, 8, 4>::smem_bytes(p.kk) <= GMD_SMEM_LIMIT) return scan_launch<D, FORM, 8, 4>(p, st);
-        return scan_launch<D, FORM, 4, 4>(p, st);
+        if (ScanShape<D, 8, NST>::smem_bytes(p.kk, FORM) <= GMD_SMEM_LIMIT) return scan_launch<D, FORM, 8, NST>(p, st);
+        return scan_launch<D, FORM, 4, NST>(p, st);
     } else {
-        return scan_launch<D, FORM, 4, 3>(p, st);
+        return scan_launch<D, FORM, 4, NST>(p, st);
     }
 }
 

@@ -230,22 +230,40 @@ def knn_host(q: np.ndarray, c: Optional[np.ndarray], k: int, metric="euclidean")
     return out_i, out_d
 
 
-def fp32_peak_tflops(iters: int = 4096, repeats: int = 3) -> float:
-    """Measured FP32 FMA peak of the current device (TFLOP/s), best of ``repeats``: a register-only
-    8x8 outer-product stream of packed FMAs (FFMA2), long enough (~15 ms) that launch gaps vanish."""
+def fp32_peak_tflops(iters: int = 4096, repeats: int = 3, form: str = "uniform") -> float:
+    """Measured FP32 FMA peak of the current device (TFLOP/s), best of ``repeats``: a
+    register-only 8x8 outer-product stream of packed FMAs (FFMA2), ~15 ms per launch.
+
+    ``form="uniform"`` (default, the roofline denominator): one multiplicand in uniform
+    registers -- the highest rate the FMA pipe reaches.  ``form="vector"``: three vector-register
+    operands, the operand mix of the scan's inner loop (register-file bandwidth caps it at
+    ~85 % of the uniform form on B200).  ``form="scalar"``: unpacked FFMA."""
+    import os
+
     lib = _lib.lib()
     dev = _device()
     sink = torch.zeros(4, dtype=torch.float32, device=dev)
     flops = C.c_double(0.0)
     best = 0.0
-    for r in range(repeats + 1):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(lib.gmd_fp32_peak_probe(iters, sink.data_ptr(), C.byref(flops), _stream_ptr()))
-        e1.record()
-        e1.synchronize()
-        if r:
-            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    old = os.environ.get("GMD_PROBE")
+    if form == "uniform":
+        os.environ.pop("GMD_PROBE", None)
+    else:
+        os.environ["GMD_PROBE"] = form
+    try:
+        for r in range(repeats + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.gmd_fp32_peak_probe(iters, sink.data_ptr(), C.byref(flops), _stream_ptr()))
+            e1.record()
+            e1.synchronize()
+            if r:
+                best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    finally:
+        if old is None:
+            os.environ.pop("GMD_PROBE", None)
+        else:
+            os.environ["GMD_PROBE"] = old
     return best
 
 
