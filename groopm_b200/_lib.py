@@ -31,6 +31,9 @@ SIGNATURES = {
     "gmd_col_mean_f64": (_int, [_vp, _i64, _int, _vp, _vp]),
     "gmd_prep_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp]),
     "gmd_scan_topk_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _i64, _vp, _vp, _vp, _vp]),
+    "gmd_use_bmu_scan": (_int, [_int, _int, _int]),
+    "gmd_bmu_kk": (_int, []),
+    "gmd_scan_bmu_f32": (_int, [_vp, _i64, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
     "gmd_refine_topk_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_exact_rows_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),

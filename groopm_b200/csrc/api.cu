@@ -28,6 +28,14 @@ extern "C" int gmd_pick_form(int metric, int D) {
     return D <= 3 ? GMD_FORM_DIRECT_L2 : GMD_FORM_EXPANDED;
 }
 
+// k = 1 with the expanded form and a short profile: the dedicated best-matching-unit scan
+extern "C" int gmd_use_bmu_scan(int k, int metric, int D) {
+    if (k != 1 || metric != GMD_L2 || gmd_pick_form(metric, D) != GMD_FORM_EXPANDED) return 0;
+    const int DP = gmd_scan_pad_dim(D);
+    return DP >= 4 && DP <= GMD_BMU_MAX_D;
+}
+extern "C" int gmd_bmu_kk(void) { return gmd_scan::BMU_KK; }
+
 extern "C" int gmd_pick_kk(int k) { return k + std::min(8, std::max(3, k / 4)); }
 
 extern "C" int gmd_pick_nsplit(int64_t Nq, int64_t Nc, int D, int kk) {
@@ -97,6 +105,30 @@ extern "C" int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* c
     return GMD_ERR_BAD_ARG;
 }
 
+extern "C" int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc, int D,
+                                int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
+                                void* stream) {
+    GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG, "bmu scan: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll && Nc < (1ll << 29), GMD_ERR_BAD_ARG,
+                "bmu scan: bad sizes");
+    const int DP = gmd_scan_pad_dim(D);
+    GMD_REQUIRE(DP >= 4 && DP <= GMD_BMU_MAX_D, GMD_ERR_UNSUPPORTED, "bmu scan: D=%d outside its range", D);
+    gmd_scan::ScanParams p;
+    p.qtiles = qtiles;
+    p.ctiles = ctiles;
+    p.Nq = Nq;
+    p.Nc = Nc;
+    p.ntiles_q = (int)gmd_ntiles(Nq);
+    p.ntiles_c = (int)gmd_ntiles(Nc);
+    p.nsplit = 1;
+    p.kk = gmd_scan::BMU_KK;
+    p.c_index_offset = c_index_offset;
+    p.cand_idx = cand_idx;
+    p.cand_val = cand_val;
+    p.cand_tau = cand_tau;
+    return gmd_bmu_launch(DP, p, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ workspace layout
 namespace {
 struct Workspace {
@@ -138,8 +170,8 @@ Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, b
 }  // namespace
 
 extern "C" size_t gmd_knn_workspace_bytes(int64_t Nq, int64_t Nc, int D, int k) {
-    const int kk = gmd_pick_kk(k);
-    // same policy as gmd_knn_f64; sized for separate query tiles
+    // same policy as gmd_knn_f64 (the larger of the two scans' needs); sized for separate query tiles
+    const int kk = std::max(gmd_pick_kk(k), k == 1 ? gmd_scan::BMU_KK : 0);
     return carve(nullptr, Nq, Nc, D, kk, gmd_pick_nsplit(Nq, Nc, D, kk), false).bytes;
 }
 
@@ -155,8 +187,9 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     if (form == GMD_FORM_AUTO) form = gmd_pick_form(metric, D);
     GMD_REQUIRE((metric == GMD_L1) == (form == GMD_FORM_DIRECT_L1), GMD_ERR_BAD_ARG,
                 "knn: form %d does not compute metric %d", form, metric);
-    const int kk = gmd_pick_kk(k);
-    const int nsplit = gmd_pick_nsplit(Nq, Nc, D, kk);
+    const bool bmu = form == GMD_FORM_EXPANDED && gmd_use_bmu_scan(k, metric, D);
+    const int kk = bmu ? gmd_scan::BMU_KK : gmd_pick_kk(k);
+    const int nsplit = bmu ? 1 : gmd_pick_nsplit(Nq, Nc, D, kk);
     const bool same = (Q == C && Nq == Nc);
     Workspace w = carve(workspace, Nq, Nc, D, kk, nsplit, same);
     GMD_REQUIRE(w.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "knn: workspace %zu B < required %zu B",
@@ -169,9 +202,10 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     if ((rc = gmd_prep_f64(C, Nc, D, w.center, form, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
     if (!same && (rc = gmd_prep_f64(Q, Nq, D, w.center, form, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK)
         return rc;
-    if ((rc = gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,
-                                w.cand_tau, stream)) != GMD_OK)
-        return rc;
+    rc = bmu ? gmd_scan_bmu_f32(w.qtiles, Nq, w.ctiles, Nc, D, 0, w.cand_idx, w.cand_val, w.cand_tau, stream)
+             : gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,
+                                 w.cand_tau, stream);
+    if (rc != GMD_OK) return rc;
     if ((rc = gmd_refine_topk_f64(Q, Nq, C, Nc, D, w.center, k, kk, nsplit, metric, form, w.cand_idx, w.cand_val,
                                   w.cand_tau, w.stats, out_idx, out_dist, w.flags + 1, w.fail_rows, stream)) != GMD_OK)
         return rc;

@@ -219,8 +219,12 @@ struct Frag {
     float4 c0, c1;  // candidates 0..3 | 4..7
 };
 
-template <int FORM>
-__device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f) {
+// FIRST: the accumulators are written, not updated: acc = q*c + cn (expanded form, cn = the
+// norm row) or the first term alone (direct forms).  Only used where the d-steps of a tile
+// are straight-line code; in a rolled loop a peeled first step makes ptxas copy the
+// loop-carried accumulators around.
+template <int FORM, bool FIRST = false>
+__device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f, const float2* cn = nullptr) {
     const float q[8] = {f.qa.x, f.qa.y, f.qa.z, f.qa.w, f.qb.x, f.qb.y, f.qb.z, f.qb.w};
     const float2 c[4] = {make_float2(f.c0.x, f.c0.y), make_float2(f.c0.z, f.c0.w), make_float2(f.c1.x, f.c1.y),
                          make_float2(f.c1.z, f.c1.w)};
@@ -231,14 +235,14 @@ __device__ __forceinline__ void tile_step(float2 (&acc)[8][4], const Frag& f) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             if (FORM == GMD_FORM_EXPANDED) {
-                acc[i][p] = __ffma2_rn(qq, c[p], acc[i][p]);
+                acc[i][p] = __ffma2_rn(qq, c[p], FIRST ? cn[p] : acc[i][p]);
             } else {
                 const float2 df = __ffma2_rn(c[p], m1, qq);  // q - c
                 if (FORM == GMD_FORM_DIRECT_L2) {
-                    acc[i][p] = __ffma2_rn(df, df, acc[i][p]);
+                    acc[i][p] = FIRST ? __fmul2_rn(df, df) : __ffma2_rn(df, df, acc[i][p]);
                 } else {
-                    acc[i][p].x += fabsf(df.x);
-                    acc[i][p].y += fabsf(df.y);
+                    acc[i][p].x = FIRST ? fabsf(df.x) : acc[i][p].x + fabsf(df.x);
+                    acc[i][p].y = FIRST ? fabsf(df.y) : acc[i][p].y + fabsf(df.y);
                 }
             }
         }
@@ -384,34 +388,47 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_topk_kernel(const ScanP
                 f.c1 = *reinterpret_cast<const float4*>(cp + d * GMD_TW + 32);
                 return f;
             };
-            if (ch == 0) {
-                // accumulators start from ||c||^2 (row DC of the stage) or zero
-                float2 cn[4];
+            float2 cn[4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) cn[x] = make_float2(0.f, 0.f);
-                if (FORM == GMD_FORM_EXPANDED) {
-                    const Frag n = load(DC);
-                    cn[0] = make_float2(n.c0.x, n.c0.y), cn[1] = make_float2(n.c0.z, n.c0.w);
-                    cn[2] = make_float2(n.c1.x, n.c1.y), cn[3] = make_float2(n.c1.z, n.c1.w);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) acc2[i][x] = cn[x];
+            for (int x = 0; x < 4; ++x) cn[x] = make_float2(0.f, 0.f);
+            if (FORM == GMD_FORM_EXPANDED && ch == 0) {
+                const Frag n = load(DC);  // row DC of the stage holds ||c||^2
+                cn[0] = make_float2(n.c0.x, n.c0.y), cn[1] = make_float2(n.c0.z, n.c0.w);
+                cn[2] = make_float2(n.c1.x, n.c1.y), cn[3] = make_float2(n.c1.z, n.c1.w);
             }
             // software pipeline one step ahead in registers; the read one row past the chunk
             // at its end is harmless (norm row of the stage / of the query tile)
             Frag cur = load(0);
-#pragma unroll 1
-            for (int d0 = 0; d0 < DC; d0 += U) {
+            if constexpr (U == DC && NCH == 1) {
+                // short profiles: straight-line steps, the first one writes the accumulators
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
+                for (int u = 0; u < DC; ++u) {
                     const Frag nxt = load(u + 1);
-                    tile_step<FORM>(acc2, cur);
+                    if (u == 0)
+                        tile_step<FORM, true>(acc2, cur, cn);
+                    else
+                        tile_step<FORM>(acc2, cur);
                     cur = nxt;
                 }
-                qp += U * GMD_TW;
-                cp += U * GMD_TW;
+            } else {
+                if (ch == 0) {
+                    // accumulators start from ||c||^2 or zero, then every step has the same shape
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) acc2[i][x] = cn[x];
+                }
+#pragma unroll 1
+                for (int d0 = 0; d0 < DC; d0 += U) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const Frag nxt = load(u + 1);
+                        tile_step<FORM>(acc2, cur);
+                        cur = nxt;
+                    }
+                    qp += U * GMD_TW;
+                    cp += U * GMD_TW;
+                }
             }
             // this stage's shared memory is no longer needed by this warp
             __syncwarp();
@@ -613,13 +630,184 @@ static int scan_dispatch(const ScanParams& p, cudaStream_t st) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k = 1 (best-matching unit, torusMesh.py:127): no heaps, no thresholds, no hit path.
+//
+// Same CTA shape, ring and register tile as scan_topk_kernel (expanded form only, D <= 16,
+// straight-line d-steps).  A "cell" is the 8 candidates one lane holds of one tile.  Every
+// (lane, row) keeps, branch-free, the smallest cell minimum it has seen, the tile it came
+// from (strict <, so the earliest tile wins ties) and the second smallest cell minimum.
+// After the scan the 8 lanes that share a query row merge their records with shuffles: the
+// winning cell's 8 candidates are proposed (cand_* with kk = 8, nsplit = 1) and
+// tau = min(second smallest cell minimum) bounds every candidate that was not.  The float64
+// re-rank and certificate of refine.cu then work unchanged.
+constexpr int BMU_KK = 8;
+
+template <int D, int NW, int NST>
+struct BmuShape {
+    static constexpr int BQ = NW * 32;
+    static constexpr int NQT = BQ / GMD_TW;
+    static constexpr int TILE_F = (D + 1) * GMD_TW;
+    static size_t smem_bytes() { return (size_t)(NST * TILE_F + NQT * TILE_F) * 4 + (2 * NST + 2) * 8; }
+};
+
+template <int D, int NW, int NST>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) scan_bmu_kernel(const ScanParams p) {
+    using S = BmuShape<D, NW, NST>;
+    constexpr int BQ = S::BQ, NQT = S::NQT, TILE_F = S::TILE_F;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr int FORM = GMD_FORM_EXPANDED;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* Cs = reinterpret_cast<float*>(smem_raw);            // NST x [D+1][64]
+    float* Qs = Cs + NST * TILE_F;                             // NQT x [D+1][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Qs + NQT * TILE_F);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long q0 = (long long)blockIdx.x * BQ;
+    const int tb = 0, te = p.ntiles_c;
+    const int qt0 = (int)(q0 / GMD_TW);
+    const int nqt = min(NQT, p.ntiles_q - qt0);
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[NST + s], NW);
+        }
+        mbar_init(&bars[2 * NST], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[2 * NST], (uint32_t)nqt * TILE_F * 4);
+        for (int j = 0; j < nqt; ++j)
+            bulk_g2s(Qs + j * TILE_F, p.qtiles + (size_t)(qt0 + j) * TILE_F, TILE_F * 4, &bars[2 * NST]);
+    }
+    for (int e = nqt * TILE_F + tid; e < NQT * TILE_F; e += (NW + 1) * 32) Qs[e] = 0.0f;
+    __syncthreads();
+    mbar_wait(&bars[2 * NST], 0);
+    for (int e = tid; e < nqt * TILE_F; e += (NW + 1) * 32)
+        if (e % TILE_F < D * GMD_TW) Qs[e] *= -2.0f;
+    __syncthreads();
+
+    if (warp == NW) {
+        if (lane == 0) {
+            for (int it = 0; it < te - tb; ++it) {
+                const int s = it % NST;
+                if (it >= NST) mbar_wait_backoff(&bars[NST + s], ((it / NST) - 1) & 1, 16 * D);
+                mbar_expect_tx(&bars[s], TILE_F * 4);
+                bulk_g2s(Cs + s * TILE_F, p.ctiles + (size_t)(tb + it) * TILE_F, TILE_F * 4, &bars[s]);
+            }
+        }
+        return;
+    }
+
+    const int lq = lane >> 3, lc = lane & 7;
+    const float* Qw = Qs + (warp >> 1) * TILE_F + (warp & 1) * 32 + lq * 4;
+    const float* qnw = Qs + (warp >> 1) * TILE_F + D * GMD_TW + (warp & 1) * 32;
+    const float INF = __int_as_float(0x7f800000);
+    float best[8], second[8];
+    int btile[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) best[i] = INF, second[i] = INF, btile[i] = 0;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = tb; t < te; ++t) {
+        float2 acc2[8][4];
+        mbar_wait(&bars[s], ph);
+        const float* cp = Cs + s * TILE_F + lc * 4;
+        auto load = [&](int d) {
+            Frag f;
+            f.qa = *reinterpret_cast<const float4*>(Qw + d * GMD_TW);
+            f.qb = *reinterpret_cast<const float4*>(Qw + d * GMD_TW + 16);
+            f.c0 = *reinterpret_cast<const float4*>(cp + d * GMD_TW);
+            f.c1 = *reinterpret_cast<const float4*>(cp + d * GMD_TW + 32);
+            return f;
+        };
+        float2 cn[4];
+        {
+            const Frag n = load(D);
+            cn[0] = make_float2(n.c0.x, n.c0.y), cn[1] = make_float2(n.c0.z, n.c0.w);
+            cn[2] = make_float2(n.c1.x, n.c1.y), cn[3] = make_float2(n.c1.z, n.c1.w);
+        }
+        Frag cur = load(0);
+#pragma unroll
+        for (int u = 0; u < D; ++u) {
+            const Frag nxt = load(u + 1);
+            if (u == 0)
+                tile_step<FORM, true>(acc2, cur, cn);
+            else
+                tile_step<FORM>(acc2, cur);
+            cur = nxt;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[NST + s]);
+        if (++s == NST) {
+            s = 0;
+            ph ^= 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float m = fminf(acc2[i][0].x, acc2[i][0].y);
+#pragma unroll
+            for (int x = 1; x < 4; ++x) m = fminf(m, fminf(acc2[i][x].x, acc2[i][x].y));
+            second[i] = fminf(second[i], fmaxf(best[i], m));
+            btile[i] = (m < best[i]) ? t : btile[i];
+            best[i] = fminf(best[i], m);
+        }
+    }
+
+    // ---- merge the records of the 8 lanes (lc) that share each query row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float b1 = best[i], b2 = second[i];
+        uint32_t k1 = ((uint32_t)btile[i] << 3) | (uint32_t)lc;  // cell id: ascending with the candidate index
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const float ob1 = __shfl_xor_sync(FULL, b1, o), ob2 = __shfl_xor_sync(FULL, b2, o);
+            const uint32_t ok1 = __shfl_xor_sync(FULL, k1, o);
+            const bool take = ob1 < b1 || (ob1 == b1 && ok1 < k1);
+            b2 = fminf(fminf(b2, ob2), take ? b1 : ob1);
+            k1 = take ? ok1 : k1;
+            b1 = take ? ob1 : b1;
+        }
+        // lane lc proposes candidate j = lc of the winning cell
+        const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
+        const long long q = q0 + warp * 32 + ql;
+        if (q < p.Nq) {
+            const float qnv = qnw[ql];
+            const uint32_t wt = k1 >> 3, wl = k1 & 7u;
+            const uint32_t li = wt * GMD_TW + (wl << 2) + (((uint32_t)lc >> 2) << 5) + ((uint32_t)lc & 3u);
+            const bool real = (long long)li < p.Nc && b1 < INF;
+            const size_t ob = (size_t)q * BMU_KK + lc;
+            p.cand_idx[ob] = real ? li + (uint32_t)p.c_index_offset : GMD_EMPTY_IDX;
+            p.cand_val[ob] = real ? fmaxf(b1 + qnv, 0.0f) : INF;
+            if (lc == 0) p.cand_tau[q] = (b2 < INF) ? fmaxf(b2 + qnv, 0.0f) : INF;
+        }
+    }
+}
+
+template <int D>
+static int bmu_launch(const ScanParams& p, cudaStream_t st) {
+    constexpr int NW = 8, NST = pick_nst(D);
+    using S = BmuShape<D, NW, NST>;
+    const size_t smem = S::smem_bytes();
+    auto kern = scan_bmu_kernel<D, NW, NST>;
+    GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((p.Nq + S::BQ - 1) / S::BQ), (NW + 1) * 32, smem, st>>>(p);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
 }  // namespace gmd_scan
 
 // padded dimensions the scan is instantiated for; gmd_scan_pad_dim(D) is the smallest >= D
 #define GMD_SCAN_DIMS(X) \
     X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(20) X(24) X(28) X(30) X(32) X(40) X(48) X(64) X(96) X(136)
 
+// padded dimensions of the k = 1 kernel
+#define GMD_BMU_DIMS(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16)
+#define GMD_BMU_MAX_D 16
+
 int gmd_scan_pad_dim(int D);
+int gmd_bmu_launch(int DP, const gmd_scan::ScanParams& p, cudaStream_t st);
 int gmd_scan_launch_form0(int DP, const gmd_scan::ScanParams& p, cudaStream_t st);
 int gmd_scan_launch_form1(int DP, const gmd_scan::ScanParams& p, cudaStream_t st);
 int gmd_scan_launch_form2(int DP, const gmd_scan::ScanParams& p, cudaStream_t st);

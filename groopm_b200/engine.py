@@ -88,9 +88,14 @@ class KnnPipeline:
             raise ValueError(f"k={self.k} exceeds the {self.nc} candidates")
         self.form = self.lib.gmd_pick_form(self.metric, self.d) if form is None else int(form)
         self.same = bool(same)
+        # k = 1 on short profiles (BMU search) has its own heap-free scan
+        self.bmu = bool(form is None and self.lib.gmd_use_bmu_scan(self.k, self.metric, self.d))
         with torch.cuda.device(self.dev):
-            self.kk = self.lib.gmd_pick_kk(self.k)
-            self.nsplit = self.lib.gmd_pick_nsplit(self.nq, self.nc, self.d, self.kk)
+            if self.bmu:
+                self.kk, self.nsplit = self.lib.gmd_bmu_kk(), 1
+            else:
+                self.kk = self.lib.gmd_pick_kk(self.k)
+                self.nsplit = self.lib.gmd_pick_nsplit(self.nq, self.nc, self.d, self.kk)
         e = dict(device=self.dev)
         self.center = torch.zeros(_lib.MAX_D, dtype=torch.float64, **e)
         self.stats = torch.zeros(4, dtype=torch.float32, **e)
@@ -125,6 +130,11 @@ class KnnPipeline:
                                          _ptr(self.qtiles), _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))
 
     def scan(self):
+        if self.bmu:
+            _lib.check(self.lib.gmd_scan_bmu_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, 0,
+                                                 _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau),
+                                                 _stream_ptr()))
+            return
         _lib.check(self.lib.gmd_scan_topk_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d,
                                               self.form, self.kk, self.nsplit, 0, _ptr(self.cand_idx),
                                               _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))

@@ -113,6 +113,18 @@ GMD_API int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* ctil
                       int D, int form, int kk, int nsplit, int64_t c_index_offset,
                       uint32_t* cand_idx, float* cand_val, float* cand_tau, void* stream);
 
+/* The k = 1 case (best-matching unit: argmin(cdist(flatNodes, [v])), torusMesh.py:127,
+ * som.py:351) with a short profile: same tiles in, no heaps -- every (lane, row) tracks its
+ * best 8-candidate cell branch-free; the winning cell is proposed with kk = gmd_bmu_kk() = 8,
+ * nsplit = 1, and cand_tau bounds all other candidates, so gmd_refine_topk_f64 /
+ * gmd_exact_rows_f64 finish it exactly as for the general scan.  Valid when
+ * gmd_use_bmu_scan(k, metric, D) is non-zero (k = 1, Euclidean, expanded form, D <= 16). */
+GMD_API int gmd_use_bmu_scan(int k, int metric, int D);
+GMD_API int gmd_bmu_kk(void);
+GMD_API int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc, int D,
+                     int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
+                     void* stream);
+
 /* float64 re-rank of the proposed candidates from the ORIGINAL rows, lowest-index tie
  * rule, plus the per-row certificate; uncertified rows are appended to fail_rows
  * (count in fail_count[0]) and finished by gmd_exact_rows_f64.                        */
