@@ -48,6 +48,24 @@ def som_train_bmus(flat_nodes, train_vectors, index_array):
     return np.asarray(engine.bmu(flat_nodes, tv)).astype(np.int64)
 
 
+def som_train(nodes, trainVector, weights=None, iterations=1000, vectorSubSet=1000, weightImgFileNamePrefix="",
+              epsilom=0.0001, influenceRate=0.4, mask=None, radius=0., silent=True):
+    """SOM.train (som.py:214-392) with the reference's argument names; ``nodes`` stands for
+    ``self.weights.nodes`` and ``mask`` may be the reference's dict of (row, col) points or a
+    [rows, cols] array.  Image dumps (``weightImgFileNamePrefix``) and progress printing stay
+    with the reference; ``epsilom`` is unused there too.  Returns the trained weights; a caller
+    that passed ``weights=None`` stores them with ``self.weights.fixFlatNodes(weights=...)``."""
+    base = nodes if weights is None else weights
+    if isinstance(mask, dict):
+        rows, cols = np.shape(base)[0], np.shape(base)[1]
+        m = np.zeros((rows, cols), dtype=np.uint8)
+        for (r, c) in mask.keys():
+            m[r, c] = 1
+        mask = m
+    return engine.som_train(nodes, trainVector, weights=weights, iterations=iterations, vector_subset=vectorSubSet,
+                            influence_rate=influenceRate, mask=mask, radius=radius)
+
+
 # ------------------------------------------------------------------ refine.py
 
 class KDTree:

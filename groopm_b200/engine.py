@@ -439,3 +439,107 @@ def kth_neighbour_dist(x, k: int, metric="cityblock", device=None):
     row of the all-pairs matrix, self (0.0) at column 0 (cluster.py:496, 498)."""
     idx, dist = knn(x, None, k=k + 1, metric=metric, device=device)
     return dist[:, k]
+
+
+# ---------------------------------------------------------------------------
+# SOM training with the mesh resident on the device (SURVEY.md section 8, row f1)
+
+def som_stamp(radius_decaying: float, influence_rate: float) -> np.ndarray:
+    """The neighbourhood "stamp" of one SOM.train iteration (som.py:282-318), vectorised:
+    linear decay inside the rounded radius, axis entries halved, four quadrants overlaid,
+    centre = influence rate, all-zero borders culled.  Host-side and tiny."""
+    grad = -1 * influence_rate / radius_decaying
+    mr = int(radius_decaying)
+    r = np.arange(mr + 1)
+    dist = np.sqrt((r[:, None] ** 2 + r[None, :] ** 2).astype(np.float64))
+    q = np.where(np.round(dist + 0.00001) <= radius_decaying, dist * grad + influence_rate, 0.0)
+    q[:, 0] /= 2
+    q[0, :] /= 2
+    stamp = np.zeros((2 * mr + 1, 2 * mr + 1))
+    stamp[mr:, mr:] += q
+    stamp[:mr + 1, mr:] += np.rot90(q, 1)
+    stamp[:mr + 1, :mr + 1] += np.rot90(q, 2)
+    stamp[mr:, :mr + 1] += np.rot90(q, 3)
+    stamp[mr, mr] = influence_rate
+    nz = np.flatnonzero(np.max(stamp, axis=0) > 0.0)
+    if len(nz):
+        k = int(nz[0])
+        stamp = stamp[k:2 * mr + 1 - k, k:2 * mr + 1 - k]
+    return np.ascontiguousarray(stamp)
+
+
+def som_train(nodes, train_vectors, weights=None, iterations: int = 1000, vector_subset: int = 1000,
+              influence_rate: float = 0.4, mask=None, radius: float = 0.0, device=None) -> np.ndarray:
+    """SOM.train (som.py:214-392) with weights, training vectors and deltas on the device.
+
+    Per iteration: one BMU search of the iteration's vectors on the frozen weights (the
+    k = 1 scan + float64 re-rank, replacing the ``argmin(cdist(flat_nodes, [v]))`` loop of
+    som.py:348-353) and one gather-update kernel (``gmd_som_update_f64``).  The host keeps
+    what is not distance work: the stamp of the iteration and the subset shuffle, which draws
+    from numpy's GLOBAL generator exactly as the reference does (som.py:324-326), so a caller
+    that seeds ``np.random`` gets the reference's subsets.  All of the reference's semantics
+    are kept (see ``oracle.som_train`` for the list); the result is bit-identical.
+    ``nodes`` is the mesh [rows, cols, D] used when ``weights`` is None (``self.weights.nodes``);
+    ``mask`` a bool/uint8 [rows, cols] array of the nodes allowed to move.  Returns new weights."""
+    lib = _lib.lib()
+    replace = weights is None
+    w_host = np.array(nodes if replace else weights, dtype=np.float64, copy=True)
+    if w_host.ndim != 3:
+        raise ValueError("weights must be [rows, cols, dimension]")
+    rows, cols, dim = w_host.shape
+    tv = np.ascontiguousarray(train_vectors, dtype=np.float64)
+    if tv.ndim != 2 or tv.shape[1] != dim:
+        raise ValueError("training vectors must be [n, dimension] with the mesh's dimension")
+    if not (np.isfinite(w_host).all() and np.isfinite(tv).all()):
+        raise FloatingPointError("non-finite value in the SOM weights or training vectors")
+    if radius == 0.0:
+        radius = float(rows) / 2
+    time_constant = iterations / np.log(radius)
+    n = len(tv)
+    if n <= vector_subset:
+        index_array = np.arange(n)
+        cut_off = n
+    else:
+        rand_index_array = np.arange(n)
+        cut_off = vector_subset
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        w = torch.from_numpy(w_host).to(dev)                 # [rows, cols, D] float64, updated in place
+        flat_search = w.view(rows * cols, dim)               # what the BMU search reads
+        if not replace and mask is None:
+            flat_search = w.clone().view(rows * cols, dim)   # reference quirk: never refreshed (som.py:380-384)
+        x = torch.from_numpy(tv).to(dev)
+        mask_d = None
+        mask_any = True
+        if mask is not None:
+            m = np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
+            if m.shape != (rows, cols):
+                raise ValueError("mask must be [rows, cols]")
+            mask_any = bool(m.any())
+            mask_d = torch.from_numpy(m).to(dev)
+        pipe = None
+        if cut_off > 0:
+            pipe = KnnPipeline(cut_off, rows * cols, dim, 1, "euclidean", same=False, device=dev)
+        for i in range(1, iterations + 1):
+            radius_decaying = radius * np.exp(-1.0 * i / time_constant)
+            if radius_decaying < 2:
+                break
+            stamp = som_stamp(radius_decaying, influence_rate)
+            sr = int((len(stamp) - 1) / 2)
+            if n > vector_subset:
+                np.random.shuffle(rand_index_array)
+                index_array = rand_index_array[:cut_off]
+            if cut_off == 0:
+                continue
+            idx_d = torch.from_numpy(np.ascontiguousarray(index_array, dtype=np.int32)).to(dev)
+            q = x.index_select(0, idx_d.long())
+            loc, _ = pipe.run(q, flat_search)                # [T, 1] int32 BMU on the frozen weights
+            stamp_d = torch.from_numpy(stamp).to(dev)
+            _lib.check(lib.gmd_som_update_f64(_ptr(w), _ptr(w), rows, cols, dim, _ptr(x), n, _ptr(idx_d), _ptr(loc),
+                                              cut_off, _ptr(stamp_d), sr, _ptr(mask_d), _stream_ptr()))
+            if mask is not None and not mask_any:
+                pass                                          # nothing moved, flat_nodes not refreshed either
+        out = w.cpu().numpy()
+        if pipe is not None and pipe.saw_nonfinite():
+            raise FloatingPointError("non-finite value reached the BMU search")
+    return out

@@ -185,6 +185,17 @@ GMD_API size_t gmd_median_workspace_bytes(void);
 GMD_API int gmd_median_dist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,
                         double* out_median, void* workspace, void* stream);
 
+/* One iteration of SOM.train's weight update (som.py:328-384) for the T training vectors
+ * X[index[t]] whose best-matching units on the frozen weights are loc[t] (flat node index,
+ * row = loc / cols): every node gathers  -(w - x) * stamp  over the 3 x 3 torus tiling in the
+ * reference's summation order and Wout = clip(W + folded delta, 0, 1); nodes with mask[node]
+ * == 0 keep their weight (mask NULL: all nodes move).  stamp is the culled
+ * (2*stamp_radius+1)^2 influence array of the iteration.  Bit-identical to the reference's
+ * float64 result, deterministic.  W and Wout may be the same buffer.                      */
+GMD_API int gmd_som_update_f64(const double* W, double* Wout, int rows, int cols, int D, const double* X,
+                       int64_t n_train, const int32_t* index, const int32_t* loc, int T,
+                       const double* stamp, int stamp_radius, const unsigned char* mask, void* stream);
+
 /* split / slack policy shared with the host layer */
 GMD_API int gmd_pick_form(int metric, int D);
 GMD_API int gmd_pick_kk(int k);

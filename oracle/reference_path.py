@@ -14,7 +14,7 @@ __all__ = [
     "best_match", "bmu_batch", "classify_contigs", "som_train_bmus",
     "whiten", "allpairs_cityblock", "kth_neighbour_radius", "radius_neighbours",
     "contraction_weights", "two_way_contraction_step", "kdtree_knn", "knn",
-    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal",
+    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal", "som_stamp", "som_train",
 ]
 
 
@@ -221,3 +221,106 @@ def knn_tie_aware_equal(q, c, idx_engine, idx_oracle, dist_oracle, metric="eucli
         if np.any(np.abs(d - dist_oracle[r, cols]) > tie):
             bad += 1
     return bad
+
+
+# ---------------------------------------------------------------- f1: SOM training
+
+def som_stamp(radius_decaying: float, influence_rate: float) -> np.ndarray:
+    """The square "stamp" of neighbourhood influences of one training iteration,
+    som.py:282-318: linear decay -influence/radius * dist + influence inside the rounded
+    radius, axis entries halved before the four quadrants are overlaid, all-zero borders
+    culled."""
+    grad = -1 * influence_rate / radius_decaying
+    max_radius = int(radius_decaying)
+    q = np.zeros((max_radius + 1, max_radius + 1))
+    for row in range(0, max_radius + 1):
+        for col in range(0, max_radius + 1):
+            true_dist = np.sqrt(row ** 2 + col ** 2)
+            check_dist = np.round(true_dist + 0.00001)
+            if check_dist <= radius_decaying:
+                influence = true_dist * grad + influence_rate
+                q[row, col] = influence
+                q[col, row] = influence
+    q[:, 0] /= 2
+    q[0, :] /= 2
+    stamp = np.zeros((2 * max_radius + 1, 2 * max_radius + 1))
+    stamp[max_radius:, max_radius:] += q
+    stamp[:max_radius + 1, max_radius:] += np.rot90(q, 1)
+    stamp[:max_radius + 1, :max_radius + 1] += np.rot90(q, 2)
+    stamp[max_radius:, :max_radius + 1] += np.rot90(q, 3)
+    stamp[max_radius, max_radius] = influence_rate
+    max_vals = np.max(stamp, axis=0)
+    k = 0
+    while k < len(max_vals):
+        if max_vals[k] > 0.0:
+            break
+        k += 1
+    if k < len(max_vals):
+        stamp = stamp[k:2 * max_radius + 1 - k, k:2 * max_radius + 1 - k]
+    return stamp
+
+
+def som_train(nodes: np.ndarray, train_vectors: np.ndarray, weights=None, iterations: int = 1000,
+              vector_subset: int = 1000, influence_rate: float = 0.4, mask=None, radius: float = 0.0):
+    """SOM.train, som.py:214-392, as a function of the mesh ``nodes`` [rows, cols, D]
+    (``self.weights.nodes`` when ``weights`` is None, else the caller's ``weights`` patch).
+
+    Kept from the reference: the BMU search of every iteration runs on weights frozen for
+    that iteration (:348-353); deltas are accumulated on a 3 x 3 tiling of the mesh and folded
+    columns first, then rows (:366-370); clip to [0, 1] (:374); the subset shuffle draws from
+    numpy's GLOBAL generator and shuffles the same index array again every iteration
+    (:324-326); with caller-owned ``weights`` and no mask the BMU search keeps using the
+    weights it was handed (``flat_nodes`` is only refreshed at :380 / :384); training stops
+    when the decayed radius falls under 2 (:279-280).  ``mask`` is a uint8/bool [rows, cols]
+    array of the nodes allowed to move (the reference passes a dict of those points).
+    Returns the trained weights (a new array; the inputs are not modified)."""
+    replace = weights is None
+    w = np.array(nodes if replace else weights, dtype=np.float64, copy=True)
+    rows, cols, dim = w.shape
+    if radius == 0.0:
+        radius = float(rows) / 2
+    flat_nodes = w.reshape((rows * cols, dim))
+    tv = np.asarray(train_vectors, dtype=np.float64)
+    time_constant = iterations / np.log(radius)
+    if len(tv) <= vector_subset:
+        index_array = np.arange(len(tv))
+        cut_off = len(tv)
+    else:
+        rand_index_array = np.arange(len(tv))
+        cut_off = vector_subset
+    mask_pts = None if mask is None else np.argwhere(np.asarray(mask) != 0)
+    for i in range(1, iterations + 1):
+        radius_decaying = radius * np.exp(-1.0 * i / time_constant)
+        if radius_decaying < 2:
+            return w
+        stamp = som_stamp(radius_decaying, influence_rate)
+        sr = int((len(stamp) - 1) / 2)
+        if len(tv) > vector_subset:
+            np.random.shuffle(rand_index_array)
+            index_array = rand_index_array[:cut_off]
+        sheet = np.tile(w, (3, 3, 1))
+        delta = np.zeros_like(sheet)
+        for j in index_array:
+            loc = int(np.argmin(cdist(flat_nodes, [tv[j]])))
+            row = int(loc / cols)
+            col = loc - (row * cols)
+            r0, r1 = rows + row - sr, rows + row + sr + 1
+            c0, c1 = cols + col - sr, cols + col + sr + 1
+            patch = -1 * (sheet[r0:r1, c0:c1] - tv[j])
+            patch *= stamp[:, :, None]
+            delta[r0:r1, c0:c1] += patch
+        delta[:, cols:2 * cols] += delta[:, 0:cols]
+        delta[:, cols:2 * cols] += delta[:, 2 * cols:3 * cols]
+        delta[rows:2 * rows, cols:2 * cols] += delta[0:rows, cols:2 * cols]
+        delta[rows:2 * rows, cols:2 * cols] += delta[2 * rows:3 * rows, cols:2 * cols]
+        fold = delta[rows:2 * rows, cols:2 * cols]
+        if mask_pts is None:
+            w = np.clip(w + fold, 0, 1)
+            if replace:
+                flat_nodes = w.reshape((rows * cols, dim))
+        else:
+            for r, c in mask_pts:
+                w[r, c] = np.clip(w[r, c] + fold[r, c], 0, 1)
+            if len(mask_pts):
+                flat_nodes = w.reshape((rows * cols, dim))
+    return w

@@ -152,9 +152,28 @@ def gen_som_train(mods, rng):
     train = rng.random((n, 4))
     np.random.seed(8)  # the per-iteration subset shuffle (som.py:324-326)
     w = som.train(train, iterations=iters, vectorSubSet=400, influenceRate=0.4, silent=True)
+    # the sub-mesh retraining call shape of refine.py:1168-1173: caller-owned weights of a
+    # NON-square patch, a mask dict (only those nodes move), explicit radius
+    rng2 = np.random.default_rng(777)
+    sw0 = rng2.random((10, 14, 4))
+    block = rng2.random((300, 4))
+    mask_pts = {}
+    for r in range(10):
+        for c in range(14):
+            if (r * 3 + c * 5) % 4 != 0:
+                mask_pts[(r, c)] = np.array([r, c])
+    sw_in = np.array(sw0, copy=True)
+    np.random.seed(9)
+    sw = som.train(block, weights=sw_in, iterations=9, mask=mask_pts, radius=10 / 3, influenceRate=0.1)
+    mask_arr = np.zeros((10, 14), dtype=np.uint8)
+    for (r, c) in mask_pts:
+        mask_arr[r, c] = 1
     np.savez_compressed(OUT / "ref_som_train.npz", w0=w0, train=train, side=side, iterations=iters,
-                        vector_subset=400, shuffle_seed=8, weights=np.array(w))
-    print("ref_som_train: side", side, "iterations", iters, "-> weights", np.array(w).shape)
+                        vector_subset=400, shuffle_seed=8, weights=np.array(w),
+                        sub_w0=sw0, sub_block=block, sub_mask=mask_arr, sub_iterations=9, sub_radius=10 / 3,
+                        sub_influence=0.1, sub_weights=np.array(sw))
+    print("ref_som_train: side", side, "iterations", iters, "-> weights", np.array(w).shape,
+          "| sub-mesh", np.array(sw).shape, "moved", int((np.array(sw) != sw0).any(axis=2).sum()), "nodes")
 
 
 class _Abort(Exception):

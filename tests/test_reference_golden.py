@@ -109,3 +109,74 @@ def test_engine_kdist_equals_reference(cuda, golden):
         assert dropin.k_dist_between(pcs[rows[a]], pcs[rows[b]]) == want
     for (a, b), want in zip(g["pairs"], g["k_dist_merged"]):
         assert dropin.k_dist(pcs[np.concatenate((rows[a], rows[b]))]) == want
+
+
+# ------------------------------------------------------------------ SOM training (row f1)
+
+def _som_cases(g):
+    full = dict(nodes=g["w0"], train=g["train"], weights=None, iterations=int(g["iterations"]),
+                vector_subset=int(g["vector_subset"]), influence_rate=0.4, mask=None, radius=0.0,
+                seed=int(g["shuffle_seed"]), want=g["weights"])
+    sub = dict(nodes=None, train=g["sub_block"], weights=g["sub_w0"], iterations=int(g["sub_iterations"]),
+               vector_subset=1000, influence_rate=float(g["sub_influence"]), mask=g["sub_mask"],
+               radius=float(g["sub_radius"]), seed=9, want=g["sub_weights"])
+    return full, sub
+
+
+def test_oracle_som_train_equals_reference(golden):
+    """SOM.train run by the reference itself (som.py:214-392): the whole-mesh call of
+    refine.py:1066-1071 (subset shuffles from numpy's global generator) and the masked
+    sub-mesh call of refine.py:1168-1173 (caller-owned non-square weights, mask, radius)."""
+    for c in _som_cases(golden("ref_som_train.npz")):
+        np.random.seed(c["seed"])
+        w = oracle.som_train(c["nodes"], c["train"], weights=c["weights"], iterations=c["iterations"],
+                             vector_subset=c["vector_subset"], influence_rate=c["influence_rate"], mask=c["mask"],
+                             radius=c["radius"])
+        assert np.array_equal(w, c["want"])
+    assert (c["want"] != c["weights"]).any() and np.array_equal(c["want"][c["mask"] == 0], c["weights"][c["mask"] == 0])
+
+
+def test_host_stamp_equals_oracle():
+    from groopm_b200 import engine
+
+    for rd in np.linspace(2.0, 40.0, 191):
+        for ir in (0.4, 0.15, 0.1):
+            assert np.array_equal(engine.som_stamp(rd, ir), oracle.som_stamp(rd, ir))
+
+
+@pytest.mark.gpu
+def test_engine_som_train_equals_reference(cuda, golden):
+    from groopm_b200 import dropin
+
+    for c in _som_cases(golden("ref_som_train.npz")):
+        np.random.seed(c["seed"])
+        mask = c["mask"]
+        if mask is not None:   # the reference passes a dict of points (refine.py:1160-1172)
+            mask = {(int(r), int(col)): None for r, col in np.argwhere(mask != 0)}
+        w = dropin.som_train(c["nodes"], c["train"], weights=c["weights"], iterations=c["iterations"],
+                             vectorSubSet=c["vector_subset"], influenceRate=c["influence_rate"], mask=mask,
+                             radius=c["radius"])
+        assert np.array_equal(w, c["want"])            # bit-identical float64 weights
+
+
+@pytest.mark.gpu
+def test_engine_som_train_equals_oracle_larger(cuda):
+    from groopm_b200 import engine, synth
+
+    rng = np.random.default_rng(41)
+    nodes = synth.som_nodes(28, 4, 5)
+    block, _ = synth.cfg_bmu(5000, 8, 6)
+    for kw in (dict(iterations=25, vector_subset=600, influence_rate=0.15),
+               dict(iterations=12, vector_subset=10000, influence_rate=0.4, radius=9.0)):
+        np.random.seed(3)
+        want = oracle.som_train(nodes, block, **kw)
+        np.random.seed(3)
+        got = engine.som_train(nodes, block, **kw)
+        assert np.array_equal(got, want)
+    # caller-owned weights without a mask: the BMU search keeps the weights it was handed
+    w0 = rng.random((9, 13, 4))
+    np.random.seed(4)
+    want = oracle.som_train(None, block[:700], weights=w0, iterations=8, radius=5.0, influence_rate=0.2)
+    np.random.seed(4)
+    got = engine.som_train(None, block[:700], weights=w0, iterations=8, radius=5.0, influence_rate=0.2)
+    assert np.array_equal(got, want)
