@@ -40,6 +40,7 @@ SIGNATURES = {
     "gmd_knn_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "gmd_knn_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gmd_cdist_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp]),
+    "gmd_angle_block_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp]),
     "gmd_pdist_f64": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
     "gmd_radius_count_f64": (_int, [_vp, _i64, _int, _int, C.c_double, _vp, _vp]),
     "gmd_radius_fill_f64": (_int, [_vp, _i64, _int, _int, C.c_double, _vp, _vp, _vp, _vp]),

@@ -258,6 +258,38 @@ __global__ void select_finish_kernel(const unsigned long long* __restrict__ stat
 
 }  // namespace
 
+// ---- angle between coverage profiles (refine.py:1545, 1577): arccos(a.b / (|a| |b|)) for a
+// small block of pairs; pairs the reference drops with a FloatingPointError (argument outside
+// [-1, 1], zero norm) come back as NaN.
+namespace {
+__global__ void __launch_bounds__(256) angle_block_kernel(const double* __restrict__ A, long long mA,
+                                                          const double* __restrict__ B, long long mB, int D,
+                                                          double* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= mA * mB) return;
+    const double* a = A + (size_t)(e / mB) * D;
+    const double* b = B + (size_t)(e % mB) * D;
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int d = 0; d < D; ++d) {
+        dot = __dadd_rn(dot, __dmul_rn(a[d], b[d]));
+        na = __dadd_rn(na, __dmul_rn(a[d], a[d]));
+        nb = __dadd_rn(nb, __dmul_rn(b[d], b[d]));
+    }
+    const double den = __dmul_rn(sqrt(na), sqrt(nb));
+    const double arg = dot / den;
+    out[e] = (den > 0.0 && arg >= -1.0 && arg <= 1.0) ? acos(arg) : CUDART_NAN;
+}
+}  // namespace
+
+extern "C" int gmd_angle_block_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, double* out,
+                                   void* stream) {
+    GMD_REQUIRE(A && B && out && mA > 0 && mB > 0 && D > 0, GMD_ERR_BAD_ARG, "angle_block: bad arguments");
+    const long long n = (long long)mA * mB;
+    angle_block_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A, mA, B, mB, D, out);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
 extern "C" int gmd_cdist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,
                              double* out, void* stream) {
     GMD_REQUIRE(A && B && out && mA > 0 && mB > 0 && D >= 1, GMD_ERR_BAD_ARG, "cdist: bad arguments");

@@ -110,6 +110,61 @@ def k_dist_between(k1, k2):
     return engine.median_dist(k1, k2, "cityblock")
 
 
+def c_dist(cov_rows):
+    """RefineEngine.cDist (refine.py:1528-1551) on the already selected rows (<= 100 per
+    bin, refine.py:1529-1536): median angle over the pairs i < j, pairs that raise a
+    FloatingPointError in the reference left out.  nan when no pair is left (np.median([]))."""
+    ang = engine.angle_block(cov_rows)
+    iu = np.triu_indices(ang.shape[0], 1)
+    v = ang[iu]
+    v = v[~np.isnan(v)]
+    return float(np.median(v)) if len(v) else float("nan")
+
+
+def c_dist_between(cov1, cov2):
+    """RefineEngine.cDistBetweenBins (refine.py:1557-1583) on the selected rows."""
+    v = engine.angle_block(cov1, cov2).ravel()
+    v = v[~np.isnan(v)]
+    return float(np.median(v)) if len(v) else float("nan")
+
+
+# ------------------------------------------------------------------ binManager.py
+
+def vq(obs, code_book):
+    """``scipy.cluster.vq.vq(obs, code_book)`` as used by BinManager.getSplitties
+    (binManager.py:560-566): nearest centroid of every observation (first minimum) and the
+    Euclidean distance to it -> (code, dist).  1-D inputs are single-feature observations."""
+    o = np.asarray(obs, dtype=np.float64)
+    cb = np.asarray(code_book, dtype=np.float64)
+    if o.ndim != cb.ndim:
+        raise ValueError("Observation and code_book should have the same rank")
+    if o.ndim == 1:
+        o, cb = o[:, None], cb[:, None]
+    elif o.ndim != 2:
+        raise ValueError("ndim different than 1 or 2 are not supported")
+    if o.shape[1] != cb.shape[1]:
+        raise ValueError("Observation and code_book should have the same number of features")
+    code, dist = engine.bmu(cb, o, return_dist=True)
+    return np.asarray(code).astype(np.int32), np.asarray(dist)
+
+
+def kmeans_step(obs, code_book):
+    """One iteration of scipy's k-means loop (``kmeans`` at binManager.py:560): assign with
+    ``vq``, then move every centroid to the mean of its members; centroids without members
+    are dropped.  -> (new_code_book, codes, mean distortion)."""
+    o = np.asarray(obs, dtype=np.float64)
+    o2 = o[:, None] if o.ndim == 1 else o
+    cb = np.asarray(code_book, dtype=np.float64)
+    code, dist = vq(o, cb)
+    nc = len(cb)
+    sums = np.zeros((nc, o2.shape[1]))
+    np.add.at(sums, code, o2)              # observation order, like _vq.update_cluster_means
+    counts = np.bincount(code, minlength=nc)
+    has = counts > 0
+    new = sums[has] / counts[has][:, None]
+    return (new[:, 0] if o.ndim == 1 else new), code, float(dist.mean())
+
+
 # ------------------------------------------------------------------ cluster.py
 
 def whiten(dat):

@@ -332,6 +332,28 @@ def pdist(x, metric="euclidean", device=None):
         return _out(out, x_np)
 
 
+def angle_block(xa, xb=None, device=None):
+    """``arccos(dot(a, b) / (|a| |b|))`` for every pair of rows of two small profile sets
+    (refine.py:1545, 1577) -> [mA, mB] float64; pairs the reference drops with a
+    FloatingPointError are NaN.  ``xb=None``: pairs within ``xa``."""
+    at, a_np = _as_rows(xa, "XA")
+    bt = at if xb is None else _as_rows(xb, "XB")[0]
+    if at.shape[1] != bt.shape[1]:
+        raise ValueError("XA and XB must have the same number of columns "
+                         "(i.e. feature dimension.)")
+    dev = at.device if at.is_cuda else _device(device)
+    with torch.cuda.device(dev):
+        if at.shape[0] == 0 or bt.shape[0] == 0:
+            return _out(torch.empty((at.shape[0], bt.shape[0]), dtype=torch.float64, device=dev), a_np)
+        ad = _to_dev(at, dev)
+        bd = ad if xb is None else _to_dev(bt, dev)
+        _check_finite(ad, bd)
+        out = torch.empty((ad.shape[0], bd.shape[0]), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().gmd_angle_block_f64(_ptr(ad), ad.shape[0], _ptr(bd), bd.shape[0], ad.shape[1],
+                                                  _ptr(out), _stream_ptr()))
+        return _out(out, a_np)
+
+
 def squareform(v):
     """scipy.spatial.distance.squareform for the two directions the reference uses
     (condensed -> square at cluster.py:495; square -> condensed in small2indices math,

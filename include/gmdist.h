@@ -159,6 +159,12 @@ GMD_API int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc
 GMD_API int gmd_cdist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,
                   double* out, void* stream);
 
+/* Angles between coverage profiles, arccos(a.b / (|a| |b|)) for every pair of a small block
+ * (RefineEngine.cDist / cDistBetweenBins, refine.py:1528-1583) -> out [mA, mB]; pairs the
+ * reference skips (FloatingPointError: argument outside [-1, 1] or a zero norm) are NaN.  */
+GMD_API int gmd_angle_block_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, double* out,
+                        void* stream);
+
 /* pdist(X, metric) -> condensed out [n(n-1)/2], scipy order (cluster.py:495, 497;
  * refine.py:1492; index map of mstore.py:1880-1888).                                  */
 GMD_API int gmd_pdist_f64(const double* X, int64_t n, int D, int metric, double* out, void* stream);

@@ -14,7 +14,7 @@ __all__ = [
     "best_match", "bmu_batch", "classify_contigs", "som_train_bmus",
     "whiten", "allpairs_cityblock", "kth_neighbour_radius", "radius_neighbours",
     "contraction_weights", "two_way_contraction_step", "kdtree_knn", "knn",
-    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal", "som_stamp", "som_train",
+    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal", "som_stamp", "som_train", "c_dist", "c_dist_between", "vq",
 ]
 
 
@@ -324,3 +324,47 @@ def som_train(nodes: np.ndarray, train_vectors: np.ndarray, weights=None, iterat
             if len(mask_pts):
                 flat_nodes = w.reshape((rows * cols, dim))
     return w
+
+
+# ---------------------------------------------------------------- f3 / f4
+
+def _angle(a, b, na, nb):
+    """One pair of refine.py:1545-1546 / 1577-1578 under np.seterr(all='raise')."""
+    with np.errstate(all='raise'):
+        try:
+            return np.arccos(np.dot(a, b) / (na * nb))
+        except FloatingPointError:
+            return None
+
+
+def c_dist(cov_rows: np.ndarray):
+    """RefineEngine.cDist, refine.py:1528-1551, on the selected rows; ``normCoverages`` is the
+    per-row Euclidean norm (profileManager.py)."""
+    norms = [np.linalg.norm(r) for r in cov_rows]
+    angles = []
+    for i in range(len(cov_rows)):
+        for j in range(i + 1, len(cov_rows)):
+            a = _angle(cov_rows[i], cov_rows[j], norms[i], norms[j])
+            if a is not None:
+                angles.append(a)
+    return float(np.median(angles)) if angles else float("nan")
+
+
+def c_dist_between(cov1: np.ndarray, cov2: np.ndarray):
+    """RefineEngine.cDistBetweenBins, refine.py:1557-1583, on the selected rows."""
+    n1 = [np.linalg.norm(r) for r in cov1]
+    n2 = [np.linalg.norm(r) for r in cov2]
+    angles = []
+    for i in range(len(cov1)):
+        for j in range(len(cov2)):
+            a = _angle(cov1[i], cov2[j], n1[i], n2[j])
+            if a is not None:
+                angles.append(a)
+    return float(np.median(angles)) if angles else float("nan")
+
+
+def vq(obs: np.ndarray, code_book: np.ndarray):
+    """``scipy.cluster.vq.vq`` as called at binManager.py:564."""
+    from scipy.cluster.vq import vq as sp_vq
+
+    return sp_vq(obs, code_book)
