@@ -15,24 +15,24 @@
 
 namespace {
 
-__global__ void col_mean_kernel(const double* __restrict__ X, long long N, int D, double* __restrict__ center) {
-    // deterministic (fixed summation order) mean over a strided sample of <= 65536 rows;
-    // the centre only conditions the FP32 scan, the float64 re-rank never sees it rounded.
-    __shared__ double part[32];
+__global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ X, long long N, int D,
+                                                       double* __restrict__ center) {
+    // deterministic (fixed summation order) mean over a strided sample of <= 65536 rows, one
+    // block per dimension; the centre only conditions the FP32 scan, the float64 re-rank
+    // never sees it rounded.
+    __shared__ double part[8];
+    const int d = blockIdx.x;
     const long long stride = (N + 65535) / 65536;
     const long long ns = (N + stride - 1) / stride;
-    for (int d = 0; d < D; ++d) {
-        double s = 0.0;
-        for (long long i = threadIdx.x; i < ns; i += blockDim.x) s += X[(size_t)(i * stride) * D + d];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
-            center[d] = tot / (double)ns;
-        }
-        __syncthreads();
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < ns; i += blockDim.x) s += X[(size_t)(i * stride) * D + d];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+        center[d] = tot / (double)ns;
     }
 }
 
@@ -179,7 +179,7 @@ extern "C" size_t gmd_tiles_bytes(int64_t N, int D) {
 
 extern "C" int gmd_col_mean_f64(const double* X, int64_t N, int D, double* center, void* stream) {
     GMD_REQUIRE(X && center && N > 0 && D > 0, GMD_ERR_BAD_ARG, "col_mean: bad arguments");
-    col_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(X, N, D, center);
+    col_mean_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(X, N, D, center);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }

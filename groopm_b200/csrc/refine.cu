@@ -38,7 +38,9 @@ __device__ __forceinline__ bool key_less(double da, uint32_t ia, double db, uint
     return da < db || (da == db && ia < ib);
 }
 
-// one warp per query row
+// G lanes per query row (G = 32, or 8 when there are at most 8 proposals per row: the k = 1
+// scan), 32 / G rows per warp
+template <int G>
 __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ Q, long long Nq,
                                                      const double* __restrict__ C, int D,
                                                      const double* __restrict__ center, int k, int kk, int nsplit,
@@ -49,55 +51,66 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
                                                      double* __restrict__ out_dist, int32_t* fail_count,
                                                      int32_t* __restrict__ fail_rows) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
+    constexpr int RPW = 32 / G;  // rows per warp
+    constexpr unsigned FULL = 0xFFFFFFFFu;
     const int m = kk * nsplit;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* sd = reinterpret_cast<double*>(sm_raw) + (size_t)warp * m;
-    uint32_t* si = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(sm_raw) + (size_t)(blockDim.x >> 5) * m) +
-                   (size_t)warp * m;
-    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (q >= Nq) return;
-    const double* qrow = Q + (size_t)q * D;
-    const uint32_t* ci = cand_idx + (size_t)q * m;
+    const int grp = lane / G, sl = lane % G;
+    const int slot = warp * RPW + grp;                 // row slot inside the block
+    const int nslots = (blockDim.x >> 5) * RPW;
+    double* sd = reinterpret_cast<double*>(sm_raw) + (size_t)slot * m;
+    uint32_t* si = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(sm_raw) + (size_t)nslots * m) + (size_t)slot * m;
+    const long long q = (long long)blockIdx.x * nslots + slot;
+    const bool live = q < Nq;                          // dead groups still take part in the shuffles
+    const double* qrow = Q + (size_t)(live ? q : 0) * D;
+    const uint32_t* ci = cand_idx + (size_t)(live ? q : 0) * m;
 
-    for (int x = lane; x < m; x += 32) {
-        const uint32_t idx = ci[x];
-        double d = CUDART_INF;
-        if (idx != GMD_EMPTY_IDX) d = dist64(qrow, C + (size_t)idx * D, D, metric);
-        sd[x] = d;
-        si[x] = idx;
+    if (live) {
+        for (int x = sl; x < m; x += G) {
+            const uint32_t idx = ci[x];
+            double d = CUDART_INF;
+            if (idx != GMD_EMPTY_IDX) d = dist64(qrow, C + (size_t)idx * D, D, metric);
+            sd[x] = d;
+            si[x] = idx;
+        }
     }
     __syncwarp();
 
     double kth = CUDART_INF;
-    for (int x = lane; x < m; x += 32) {
-        const double d = sd[x];
-        const uint32_t idx = si[x];
-        int r = 0;
-        for (int y = 0; y < m; ++y) r += key_less(sd[y], si[y], d, idx) ? 1 : 0;
-        if (r < k && idx != GMD_EMPTY_IDX) {
-            out_idx[(size_t)q * k + r] = (int32_t)idx;
-            out_dist[(size_t)q * k + r] = d;
-            if (r == k - 1) kth = d;
+    if (live) {
+        for (int x = sl; x < m; x += G) {
+            const double d = sd[x];
+            const uint32_t idx = si[x];
+            int r = 0;
+            for (int y = 0; y < m; ++y) r += key_less(sd[y], si[y], d, idx) ? 1 : 0;
+            if (r < k && idx != GMD_EMPTY_IDX) {
+                out_idx[(size_t)q * k + r] = (int32_t)idx;
+                out_dist[(size_t)q * k + r] = d;
+                if (r == k - 1) kth = d;
+            }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) kth = fmin(kth, __shfl_xor_sync(0xFFFFFFFFu, kth, o));
+    for (int o = G / 2; o > 0; o >>= 1) kth = fmin(kth, __shfl_xor_sync(FULL, kth, o));
 
     // ---- certificate
     float tau32 = CUDART_INF_F;
-    for (int s = lane; s < nsplit; s += 32) tau32 = fminf(tau32, cand_tau[(size_t)q * nsplit + s]);
-    for (int o = 16; o > 0; o >>= 1) tau32 = fminf(tau32, __shfl_xor_sync(0xFFFFFFFFu, tau32, o));
-    bool ok = true;
-    if (tau32 != CUDART_INF_F) {
-        double n2 = 0.0, n1 = 0.0;
-        for (int d = lane; d < D; d += 32) {
+    if (live)
+        for (int s = sl; s < nsplit; s += G) tau32 = fminf(tau32, cand_tau[(size_t)q * nsplit + s]);
+    for (int o = G / 2; o > 0; o >>= 1) tau32 = fminf(tau32, __shfl_xor_sync(FULL, tau32, o));
+    double n2 = 0.0, n1 = 0.0;
+    if (live) {
+        for (int d = sl; d < D; d += G) {
             const double v = qrow[d] - (center ? center[d] : 0.0);
             n2 += v * v;
             n1 += fabs(v);
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            n2 += __shfl_xor_sync(0xFFFFFFFFu, n2, o);
-            n1 += __shfl_xor_sync(0xFFFFFFFFu, n1, o);
-        }
+    }
+    for (int o = G / 2; o > 0; o >>= 1) {
+        n2 += __shfl_xor_sync(FULL, n2, o);
+        n1 += __shfl_xor_sync(FULL, n1, o);
+    }
+    bool ok = true;
+    if (tau32 != CUDART_INF_F) {
         const double tau = (double)tau32;
         double lower;
         if (form == GMD_FORM_EXPANDED) {
@@ -113,15 +126,15 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
         }
         ok = kth < lower;
     }
-    if (!ok && lane == 0) {
-        const int slot = atomicAdd(fail_count, 1);
-        fail_rows[slot] = (int32_t)q;
+    if (live && !ok && sl == 0) {
+        const int fs = atomicAdd(fail_count, 1);
+        fail_rows[fs] = (int32_t)q;
     }
 }
 
 // exact float64 scan of all candidates for the rows the certificate rejected
 constexpr int EX_CAP = 2048;
-constexpr int EX_THREADS = 256;
+constexpr int EX_THREADS = 1024;  // one block owns a row: memory-level parallelism is what it lacks
 
 struct KeyD {
     double d;
@@ -227,13 +240,16 @@ extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C,
                 "refine: bad sizes (Nq=%lld Nc=%lld D=%d k=%d kk=%d nsplit=%d)", (long long)Nq, (long long)Nc, D, k,
                 kk, nsplit);
     const int wpb = 4;
-    const size_t smem = (size_t)wpb * kk * nsplit * (sizeof(double) + sizeof(uint32_t));
+    const bool narrow = kk * nsplit <= 8;              // the k = 1 scan's 8 proposals: 8 lanes per row
+    const int rows_per_block = wpb * (narrow ? 4 : 1);
+    const size_t smem = (size_t)rows_per_block * kk * nsplit * (sizeof(double) + sizeof(uint32_t));
     GMD_REQUIRE(smem <= 200 * 1024, GMD_ERR_UNSUPPORTED, "refine: kk*nsplit=%d too large", kk * nsplit);
-    GMD_CUDA_CHECK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((Nq + wpb - 1) / wpb);
-    refine_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, Nq, C, D, center, k, kk, nsplit, metric, form,
-                                                                 cand_idx, cand_val, cand_tau, stats, out_idx, out_dist,
-                                                                 fail_count, fail_rows);
+    auto kern = narrow ? refine_kernel<8> : refine_kernel<32>;
+    GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((Nq + rows_per_block - 1) / rows_per_block);
+    kern<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, Nq, C, D, center, k, kk, nsplit, metric, form, cand_idx,
+                                                        cand_val, cand_tau, stats, out_idx, out_dist, fail_count,
+                                                        fail_rows);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }
@@ -247,7 +263,7 @@ extern "C" int gmd_exact_rows_f64(const double* Q, int64_t Nq, const double* C, 
     int dev = 0, sms = 0;
     GMD_CUDA_CHECK(cudaGetDevice(&dev));
     GMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    exact_rows_kernel<<<sms * 4, EX_THREADS, 0, (cudaStream_t)stream>>>(Q, C, Nc, D, k, metric, fail_count, fail_rows,
+    exact_rows_kernel<<<sms * 2, EX_THREADS, 0, (cudaStream_t)stream>>>(Q, C, Nc, D, k, metric, fail_count, fail_rows,
                                                                        out_idx, out_dist);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;

@@ -365,6 +365,44 @@ def _graph_properties(x, idx, dist, k):
         np.testing.assert_allclose(dist[rows, j], d, rtol=1e-12)
 
 
+@pytest.mark.parametrize("d", [4, 5, 8, 11, 16])
+@pytest.mark.parametrize("m", [1, 7, 64, 65, 1000, 5003])
+def test_bmu_scan_vs_oracle(cuda, d, m):
+    """The dedicated k = 1 scan (scan_bmu_kernel) over its whole dimension range, node counts
+    around the 64-row tile edge, duplicate nodes (first one must win) and queries that are nodes."""
+    rng = np.random.default_rng(1000 * d + m)
+    nodes = rng.random((m, d))
+    if m > 10:
+        nodes[m - 1] = nodes[3]
+        nodes[m // 2] = nodes[3]
+    x = rng.random((3001, d))
+    x[:40] = nodes[rng.integers(0, m, 40)]
+    x[40] = nodes[min(3, m - 1)]
+    assert _lib.lib().gmd_use_bmu_scan(1, _lib.L2, d) == 1
+    loc, dist = engine.bmu(nodes, x, return_dist=True)
+    want = oracle.bmu_batch(nodes, x)
+    assert np.array_equal(loc, want)
+    assert np.array_equal(dist, sp_cdist(x, nodes).min(axis=1))
+
+
+def test_cfg4_raw_signatures_100k_d136(cuda):
+    """BASELINE configs[3] at the size SURVEY.md section 8d names for the oracle check: all-pairs
+    k = 16 on a 100 k subset of the 136-d tetranucleotide signatures, and bin-vs-bin cityblock
+    medians on 2000-row bins."""
+    sigs = synth.quantise(synth.kmer_sigs(100_000, 4), 34)
+    idx, dist, info = engine.knn(sigs, None, k=16, return_info=True)
+    _graph_properties(sigs, idx, dist, 16)
+    rows = np.sort(np.random.default_rng(4).choice(len(sigs), 256, replace=False))
+    od, oi = oracle.knn(sigs[rows], sigs, 16)
+    assert_knn_parity(sigs[rows], sigs, idx[rows], dist[rows], oi, od)
+    l1_idx, l1_dist = engine.knn(sigs[rows], sigs, k=16, metric="cityblock")
+    od1, oi1 = oracle.knn(sigs[rows], sigs, 16, "cityblock")
+    assert_knn_parity(sigs[rows], sigs, l1_idx, l1_dist, oi1, od1, "cityblock")
+    for a, b in ((0, 1), (7, 3)):
+        ba, bb = sigs[a * 2000:(a + 1) * 2000], sigs[b * 2000:(b + 1) * 2000]
+        assert dropin.k_dist_between(ba, bb) == oracle.k_dist_between(ba, bb)
+
+
 def test_cfg2_full_100k_d10_k16(cuda):
     x = synth.cfg_knn_rows(100_000, 10, 2)
     idx, dist, info = engine.knn(x, None, k=16, return_info=True)

@@ -63,6 +63,10 @@ if __name__ == "__main__":
     if "cfg3" in which:
         b, n = synth.cfg_bmu(1_000_000, 64)
         run("cfg3 1M x4 BMU 4096", b, n.reshape(-1, 4), 1, "euclidean", peak=peak)
+    if "cfg4" in which:
+        x = synth.quantise(synth.kmer_sigs(100_000, 4), 34)
+        run("cfg4 100k x136 L2 k16", x, None, 16, "euclidean", peak=peak)
+        run("cfg4 100k x136 L1 k16", x, None, 16, "cityblock", peak=peak / 2)
     if "cfg5s" in which:
         x = synth.cfg_knn_rows(250_000, 30, 5)
         run("cfg5 250k x30 L2 k32", x, None, 32, "euclidean", peak=peak)
