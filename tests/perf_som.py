@@ -1,4 +1,5 @@
-"""SOM training at the reference's scale (refine.py:1043, 1066-1071: side = max(100, 5*bins),
+"""(Not a pytest module: a timing script that uses the oracle as the CPU side, hence under tests/.)
+SOM training at the reference's scale (refine.py:1043, 1066-1071: side = max(100, 5*bins),
 800 iterations, <= 1000 vectors per iteration): device trainer vs the oracle on a few iterations."""
 import sys, time
 import numpy as np
