@@ -353,6 +353,115 @@ extern "C" int gmd_gather_dist_f64(const double* X, int64_t n, int D, int metric
     return GMD_OK;
 }
 
+// ---- many small medians in one launch: one block per job, the whole radix select inside the
+// block (shared-memory histogram, no host round trips).  The reference takes these medians
+// bin by bin in Python loops (getKCut refine.py:1479-1488, findMergeGroups :718, :876) on bins
+// of 10..10^4 contigs, where a launch-per-pass select is slower than scipy.
+namespace {
+__device__ __forceinline__ double pair_dist64(const double* __restrict__ a, const double* __restrict__ b, int D,
+                                              int metric) {
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) s = acc_step(s, a[d], b[d], metric);
+    return finish(s, metric);
+}
+
+__global__ void __launch_bounds__(256) median_batch_kernel(const double* __restrict__ X, int D, int metric,
+                                                           const int32_t* __restrict__ rows,
+                                                           const int32_t* __restrict__ jobs,  // a_off, a_len, b_off, b_len (<0: pdist)
+                                                           double* __restrict__ out) {
+    __shared__ unsigned int h[RBINS];
+    __shared__ unsigned long long s_prefix, s_want, s_cnt, s_max;
+    const int job = blockIdx.x, tid = threadIdx.x;
+    const int a_off = jobs[4 * job], mA = jobs[4 * job + 1];
+    const bool self = jobs[4 * job + 3] < 0;
+    const int b_off = self ? a_off : jobs[4 * job + 2], mB = self ? mA : jobs[4 * job + 3];
+    const unsigned long long total =
+        self ? (unsigned long long)mA * (unsigned long long)(mA > 0 ? mA - 1 : 0) / 2 : (unsigned long long)mA * mB;
+    if (total == 0) {
+        if (tid == 0) out[job] = CUDART_NAN;  // np.median of nothing / the reference's "return None"
+        return;
+    }
+    const long long span = (long long)mA * mB;  // pdist walks the square and skips j <= i
+    if (tid == 0) {
+        s_prefix = 0ull;
+        s_want = total / 2;
+    }
+    for (int shift = 55; shift >= 0; shift -= RBITS) {
+        for (int e = tid; e < RBINS; e += 256) h[e] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const int top = shift + RBITS;
+        for (long long p = tid; p < span; p += 256) {
+            const int i = (int)(p / mB), j = (int)(p - (long long)i * mB);
+            if (self && j <= i) continue;
+            const double d = pair_dist64(X + (size_t)rows[a_off + i] * D, X + (size_t)rows[b_off + j] * D, D, metric);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+            if (top >= 64 || (bits >> top) == (prefix >> top)) atomicAdd(&h[(bits >> shift) & (RBINS - 1)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long want = s_want, run = 0;
+            int bin = RBINS - 1;
+            for (int b = 0; b < RBINS; ++b) {
+                const unsigned long long c = h[b];
+                if (want < run + c) {
+                    bin = b;
+                    break;
+                }
+                run += c;
+            }
+            s_prefix = prefix | ((unsigned long long)bin << shift);
+            s_want = want - run;
+            s_cnt = 0ull;
+            s_max = 0ull;
+        }
+        __syncthreads();
+    }
+    const unsigned long long vhi = s_prefix;
+    if (total & 1ull) {
+        if (tid == 0) out[job] = __longlong_as_double((long long)vhi);
+        return;
+    }
+    // even count: np.median averages ranks total/2 - 1 and total/2
+    unsigned long long cnt = 0, mx = 0;
+    for (long long p = tid; p < span; p += 256) {
+        const int i = (int)(p / mB), j = (int)(p - (long long)i * mB);
+        if (self && j <= i) continue;
+        const double d = pair_dist64(X + (size_t)rows[a_off + i] * D, X + (size_t)rows[b_off + j] * D, D, metric);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+        if (bits < vhi) {
+            cnt += 1;
+            mx = max(mx, bits);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    }
+    if ((tid & 31) == 0 && cnt) {
+        atomicAdd(&s_cnt, cnt);
+        atomicMax(&s_max, mx);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double hi = __longlong_as_double((long long)vhi);
+        const double lo = (s_cnt == total / 2) ? __longlong_as_double((long long)s_max) : hi;
+        out[job] = (lo + hi) / 2.0;
+    }
+}
+}  // namespace
+
+extern "C" int gmd_median_batch_f64(const double* X, int64_t N, int D, int metric, const int32_t* rows,
+                                    const int32_t* jobs, int n_jobs, double* out, void* stream) {
+    GMD_REQUIRE(X && rows && jobs && out && N > 0 && D >= 1 && n_jobs >= 0, GMD_ERR_BAD_ARG,
+                "median_batch: bad arguments");
+    GMD_REQUIRE(metric == GMD_L2 || metric == GMD_L1, GMD_ERR_BAD_ARG, "median_batch: bad metric %d", metric);
+    if (n_jobs == 0) return GMD_OK;
+    median_batch_kernel<<<(unsigned)n_jobs, 256, 0, (cudaStream_t)stream>>>(X, D, metric, rows, jobs, out);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
 extern "C" size_t gmd_median_workspace_bytes(void) { return 4 * sizeof(unsigned long long) + RBINS * sizeof(unsigned int); }
 
 extern "C" int gmd_median_dist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,

@@ -110,6 +110,19 @@ def k_dist_between(k1, k2):
     return engine.median_dist(k1, k2, "cityblock")
 
 
+def k_dist_many(kmer_pcs, bins_row_indices):
+    """kDist for every bin in one launch -- the loop of RefineEngine.getKCut
+    (refine.py:1479-1488) over ``self.BM.getBin(bid).rowIndices``: list of medians (None for a
+    bin of fewer than two contigs)."""
+    return engine.median_dist_batch(kmer_pcs, [(r, None) for r in bins_row_indices], "cityblock")
+
+
+def k_dist_between_many(kmer_pcs, bin_pairs):
+    """kDistBetweenBins for many (rowIndices1, rowIndices2) pairs in one launch -- the
+    neighbour tests of findMergeGroups / combineMergers (refine.py:718, 876)."""
+    return engine.median_dist_batch(kmer_pcs, list(bin_pairs), "cityblock")
+
+
 def c_dist(cov_rows):
     """RefineEngine.cDist (refine.py:1528-1551) on the already selected rows (<= 100 per
     bin, refine.py:1529-1536): median angle over the pairs i < j, pairs that raise a

@@ -456,6 +456,68 @@ def median_dist(a, b=None, metric="cityblock", device=None):
         return float(out.item())
 
 
+BATCH_MEDIAN_MAX_PAIRS = 1 << 21   # beyond this a job gets the multi-block select of median_dist
+
+
+def median_dist_batch(x, jobs, metric="cityblock", device=None):
+    """Medians of many never-materialised distance blocks of one profile array in a single
+    launch.  ``jobs`` is a sequence of ``(rows_a, rows_b)`` row-index arrays into ``x``;
+    ``rows_b=None`` asks for ``median(pdist(x[rows_a]))`` (kDist, refine.py:1490-1496) and
+    otherwise ``median(cdist(x[rows_a], x[rows_b]))`` (kDistBetweenBins, refine.py:1502-1503).
+    -> list of floats; ``None`` where a pdist job has fewer than two rows (the reference's
+    ``return None``), nan where a cdist job is empty."""
+    xt, _ = _as_rows(x, "X")
+    m = _metric(metric)
+    dev = xt.device if xt.is_cuda else _device(device)
+    lib = _lib.lib()
+    n_rows = xt.shape[0]
+    rows, quads, big = [], [], {}
+    off = 0
+    for j, (ra, rb) in enumerate(jobs):
+        ra = np.ascontiguousarray(ra, dtype=np.int32).ravel()
+        rbv = None if rb is None else np.ascontiguousarray(rb, dtype=np.int32).ravel()
+        for r in (ra,) if rbv is None else (ra, rbv):
+            if len(r) and (r.min() < 0 or r.max() >= n_rows):
+                raise IndexError("row index out of range")
+        pairs = len(ra) * (len(ra) - 1) // 2 if rbv is None else len(ra) * len(rbv)
+        if pairs > BATCH_MEDIAN_MAX_PAIRS:
+            big[j] = (ra, rbv)
+            quads.append((0, 0, 0, 0))
+            continue
+        a_off = off
+        rows.append(ra)
+        off += len(ra)
+        if rbv is None:
+            quads.append((a_off, len(ra), 0, -1))
+        else:
+            quads.append((a_off, len(ra), off, len(rbv)))
+            rows.append(rbv)
+            off += len(rbv)
+    with torch.cuda.device(dev):
+        xd = _to_dev(xt, dev)
+        _check_finite(xd)
+        out = torch.empty(max(len(quads), 1), dtype=torch.float64, device=dev)
+        if quads:
+            rows_d = torch.from_numpy(np.concatenate(rows) if rows else np.zeros(1, np.int32)).to(dev)
+            if rows_d.numel() == 0:
+                rows_d = torch.zeros(1, dtype=torch.int32, device=dev)
+            jobs_d = torch.from_numpy(np.asarray(quads, dtype=np.int32).reshape(-1)).to(dev)
+            _lib.check(lib.gmd_median_batch_f64(_ptr(xd), n_rows, xd.shape[1], m, _ptr(rows_d), _ptr(jobs_d),
+                                                len(quads), _ptr(out), _stream_ptr()))
+        vals = out.cpu().numpy()[:len(quads)].tolist()
+    res = []
+    for j, (q, v) in enumerate(zip(quads, vals)):
+        if j in big:
+            ra, rbv = big[j]
+            res.append(median_dist(xt[torch.from_numpy(ra).long()],
+                                   None if rbv is None else xt[torch.from_numpy(rbv).long()], metric, device=dev))
+        elif q[3] < 0 and q[1] < 2:
+            res.append(None)
+        else:
+            res.append(float(v))
+    return res
+
+
 def kth_neighbour_dist(x, k: int, metric="cityblock", device=None):
     """``np.sort(squareform(pdist(X, metric)))[:, k]`` -- the k-th smallest entry of every
     row of the all-pairs matrix, self (0.0) at column 0 (cluster.py:496, 498)."""

@@ -191,6 +191,17 @@ GMD_API size_t gmd_median_workspace_bytes(void);
 GMD_API int gmd_median_dist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,
                         double* out_median, void* workspace, void* stream);
 
+/* Many medians in ONE launch (one block per job, the radix select entirely inside the block):
+ * the per-bin loops of getKCut (refine.py:1479-1488 -> kDist) and of findMergeGroups /
+ * combineMergers (refine.py:718, 876 -> kDistBetweenBins).  X [N, D] holds all profiles;
+ * rows is a concatenation of int32 row-index lists; job j is the int32 quadruple
+ * jobs[4j..4j+3] = (a_off, a_len, b_off, b_len) into rows, b_len < 0 meaning
+ * median(pdist(X[a])) and otherwise median(cdist(X[a], X[b])).  out[j] is NaN when job j has
+ * no pairs.  Meant for bins up to a few thousand rows; larger blocks go through
+ * gmd_median_dist_f64.                                                                   */
+GMD_API int gmd_median_batch_f64(const double* X, int64_t N, int D, int metric, const int32_t* rows,
+                         const int32_t* jobs, int n_jobs, double* out, void* stream);
+
 /* One iteration of SOM.train's weight update (som.py:328-384) for the T training vectors
  * X[index[t]] whose best-matching units on the frozen weights are loc[t] (flat node index,
  * row = loc / cols): every node gathers  -(w - x) * stamp  over the 3 x 3 torus tiling in the

@@ -432,3 +432,28 @@ def test_cfg5_full_1m_d30_k32(cuda):
     rows = np.sort(np.random.default_rng(5).choice(len(x), 96, replace=False))
     od, oi = oracle.knn(x[rows], x, 32)
     assert_knn_parity(x[rows], x, idx[rows], dist[rows], oi, od)
+
+
+def test_batched_medians_vs_oracle(cuda):
+    """getKCut / findMergeGroups shapes: many small bins of one kmerPCs array in one launch."""
+    c = synth.cfg_core(6000, 3, 9)
+    kpc = c["kmerPCs"]
+    rng = np.random.default_rng(9)
+    sizes = [0, 1, 2, 3, 10, 57, 256, 700, 1500]
+    bins = [np.sort(rng.choice(len(kpc), m, replace=False)) for m in sizes]
+    got = dropin.k_dist_many(kpc, bins)
+    for b, g in zip(bins, got):
+        want = oracle.k_dist(kpc[b]) if len(b) else None
+        assert g == want
+    pairs = [(bins[4], bins[5]), (bins[6], bins[3]), (bins[7], bins[8]), (bins[2], bins[2]), (bins[5], bins[0])]
+    got = dropin.k_dist_between_many(kpc, pairs)
+    for (a, b), g in zip(pairs, got):
+        if len(a) == 0 or len(b) == 0:
+            assert np.isnan(g)
+        else:
+            assert g == oracle.k_dist_between(kpc[a], kpc[b])
+    # a job over the single-block limit falls through to the multi-block select
+    big = np.arange(2200)
+    assert dropin.k_dist_many(kpc, [big])[0] == oracle.k_dist(kpc[big])
+    with pytest.raises(IndexError):
+        dropin.k_dist_many(kpc, [np.array([0, len(kpc)])])
