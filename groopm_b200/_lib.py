@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ.get("GMDIST_LIB") or Path(__file__).resolve().parent 
 
 OK, ERR_BAD_ARG, ERR_NONFINITE, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 L2, L1 = 0, 1
-FORM_EXPANDED, FORM_DIRECT_L2, FORM_DIRECT_L1, FORM_AUTO = 0, 1, 2, -1
+FORM_EXPANDED, FORM_DIRECT_L2, FORM_DIRECT_L1, FORM_TC, FORM_AUTO = 0, 1, 2, 3, -1
 TILE_ROWS, MAX_K, MAX_D = 64, 64, 136
 
 _i64, _int, _vp, _sz = C.c_int64, C.c_int, C.c_void_p, C.c_size_t
@@ -34,6 +34,10 @@ SIGNATURES = {
     "gmd_use_bmu_scan": (_int, [_int, _int, _int]),
     "gmd_bmu_kk": (_int, []),
     "gmd_scan_bmu_f32": (_int, [_vp, _i64, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
+    "gmd_tc_supported": (_int, [_int, _int, _int]),
+    "gmd_tc_tiles_bytes": (_sz, [_i64]),
+    "gmd_prep_tc_f64": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_scan_tc_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp]),
     "gmd_refine_topk_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_exact_rows_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),

@@ -117,6 +117,13 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
             const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
             const double e2 = (2.0 * D + 8.0) * U32 * nn * nn;
             lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
+        } else if (form == GMD_FORM_TC) {
+            // 3 x TF32 dot product: representation (3 x 2^-22) and accumulation error measured at
+            // 2^-20.9 |q||c| (tools/tc_probe.cu); bounded here by 2^-18 |q||c| <= 2^-20 nn^2, doubled
+            // by the factor -2, plus the FP32 roundings of the norm terms: 48 x 2^-24 nn^2 in all
+            const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
+            const double e2 = 48.0 * U32 * nn * nn;
+            lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
         } else if (form == GMD_FORM_DIRECT_L2) {
             const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
             lower = sqrt(tau * (1.0 - (D + 6.0) * U32)) - 1.01 * U32 * nn;

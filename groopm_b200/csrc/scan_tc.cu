@@ -1,0 +1,369 @@
+// Tensor-core variant of the fused distance + top-k scan (expanded form, D <= 32).
+//
+// The dot products q.c of a 128-query x 128-candidate tile are one K = 32 contraction on the
+// 5th-generation tensor cores: tcgen05.mma kind::tf32, operands K-major SWIZZLE_128B images in
+// shared memory, FP32 accumulator in tensor memory.  TF32 alone (10-bit mantissa) is far too
+// coarse for a neighbour search, so every FP32 value is split v = hi + lo (both TF32) and the
+// contraction is issued three times: hi.hi + hi.lo + lo.hi.  Measured against float64
+// (tools/tc_probe.cu): |error| <= 2^-20.9 |q||c|, i.e. FP32-class, inside the certificate's
+// bound (refine.cu, GMD_FORM_TC).
+//
+// Roles (192 threads): warp 0 lane 0 streams candidate tiles HBM -> shared memory with bulk
+// async copies (mbarrier ring); warp 1 lane 0 issues the MMAs (12 per tile) into one of two
+// 128-column accumulator stages in tensor memory and commits completion to mbarriers; warps
+// 2..5 are the selection warps: thread r owns query r of the CTA = TMEM lane r, reads its 128
+// accumulators with tcgen05.ld (32 columns at a time), forms  ||c||^2 - 2 q.c , and keeps
+// the query's top-kk heap in shared memory all by itself (no queues, no atomics: a thread
+// sees every candidate of its query, in ascending index order).
+//
+// HBM tile format ("TC tile", 128 profiles): [hi image 16 KB][lo image 16 KB][||x||^2 128 f32]
+// [pad to 33 KB], images already in the swizzled shared-memory layout so that one bulk copy
+// per tile is all the producer does.
+#include "scan_impl.cuh"
+
+namespace gmd_tc {
+using namespace gmd_scan;
+
+constexpr int TM = 128;                  // profiles per TC tile (UMMA M and N)
+constexpr int TK = 32;                   // contraction length (padded D)
+constexpr int IMG_B = TM * TK * 4;       // one image: 16 KB
+constexpr int TILE_B = 2 * IMG_B + 1024; // hi, lo, norms (512 B used)
+constexpr int NSTB = 4;                  // candidate stages in shared memory
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    // K-major SWIZZLE_128B: LBO 1, SBO 1024 B (8 rows x 128 B), descriptor version 1 (sm_100)
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem),
+        "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// wait for the outstanding tcgen05.ld; the registers pass through the asm so that nothing that
+// reads them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ staging: float64 rows -> TC tiles
+__global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long N, int D,
+                                                      const double* __restrict__ center,
+                                                      unsigned char* __restrict__ tiles, float* __restrict__ stats,
+                                                      int* __restrict__ flags) {
+    const long long t = blockIdx.x, row0 = t * TM;
+    float* hi = reinterpret_cast<float*>(tiles + (size_t)t * TILE_B);
+    float* lo = hi + IMG_B / 4;
+    float* nrm = lo + IMG_B / 4;
+    bool bad = false;
+    for (int e = threadIdx.x; e < TM * TK; e += blockDim.x) {
+        const int r = e / TK, k = e - r * TK;
+        const long long row = row0 + r;
+        float v = 0.0f;
+        if (row < N && k < D) {
+            const double x = X[(size_t)row * D + k];
+            bad |= !isfinite(x);
+            v = (float)(x - (center ? center[k] : 0.0));
+        }
+        const float h = tf32_rn(v);
+        // shared-memory image: 8-row groups of 1024 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7)
+        const int off = ((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4) >> 2;
+        hi[off] = h;
+        lo[off] = tf32_rn(v - h);
+    }
+    if (bad) atomicExch(flags, 1);
+    if (threadIdx.x < TM) {
+        const int r = threadIdx.x;
+        const long long row = row0 + r;
+        double n2 = 0.0, n1 = 0.0;
+        if (row < N) {
+            for (int k = 0; k < D; ++k) {
+                const double v = (double)(float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0));
+                n2 += v * v;
+                n1 += fabs(v);
+            }
+        }
+        nrm[r] = row < N ? (float)n2 : GMD_PAD_AUX;
+        if (row < N && stats) {
+            atomicMax(reinterpret_cast<int*>(stats), __float_as_int(__double2float_ru(n2)));
+            atomicMax(reinterpret_cast<int*>(stats) + 1, __float_as_int(__double2float_ru(n1)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the scan
+constexpr int TQ = 16;   // parked hits per selection thread (a thread owns its query's queue)
+
+// Every lane folds its own queue into its own heap (the lanes work side by side: this is
+// why hits are parked instead of being pushed the moment they are seen, which would
+// serialise 32 divergent heap updates per warp).  Returns the new threshold value.
+static __device__ __noinline__ float drain_own(uint64_t* h, int kk, const uint2* q, int n) {
+    for (int r = 0; r < n; ++r) {
+        const uint2 e = q[r * TM];
+        const uint64_t key = gmd_key(__uint_as_float(e.y), e.x);
+        if (key < h[0]) heap_replace_root(h, kk, key);
+    }
+    const uint64_t root = h[0];
+    return (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned char* __restrict__ qtiles,
+                                                              const unsigned char* __restrict__ ctiles,
+                                                              long long Nq, long long Nc, int ntiles_c, int kk,
+                                                              long long c_index_offset,
+                                                              uint32_t* __restrict__ cand_idx,
+                                                              float* __restrict__ cand_val,
+                                                              float* __restrict__ cand_tau) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* Aimg = base;                          // hi, lo images + norms of the CTA's queries (one TC tile)
+    unsigned char* Bst = base + TILE_B;                  // NSTB candidate stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + (size_t)NSTB * TILE_B);
+    uint64_t* full = bars;                               // [NSTB] candidate tile landed
+    uint64_t* empty = bars + NSTB;                       // [NSTB] MMAs that read the stage are done
+    uint64_t* tfull = bars + 2 * NSTB;                   // [2] accumulator stage written
+    uint64_t* tempty = bars + 2 * NSTB + 2;              // [2] accumulator stage read back
+    uint64_t* qbar = bars + 2 * NSTB + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 6);
+    uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NSTB + 8);        // [TQ][128] parked (index, value bits)
+    float* nbuf = reinterpret_cast<float*>(queues + TQ * TM);             // [2][128] ||c||^2 of the tile in flight
+    uint64_t* lists = reinterpret_cast<uint64_t*>(nbuf + 2 * TM);         // [128][kkp] heaps
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kkp = kk | 1;
+    const long long qt = blockIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTB; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        mbar_init(qbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(qbar, TILE_B);
+        bulk_g2s(Aimg, qtiles + (size_t)qt * TILE_B, TILE_B, qbar);
+    }
+    for (int e = tid; e < TM * kkp; e += NTHREADS) lists[e] = GMD_EMPTY_KEY;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- producer
+        if (lane == 0) {
+            for (int t = 0; t < ntiles_c; ++t) {
+                const int s = t % NSTB;
+                if (t >= NSTB) mbar_wait_backoff(&empty[s], ((t / NSTB) - 1) & 1, 64);
+                mbar_expect_tx(&full[s], TILE_B);
+                bulk_g2s(Bst + (size_t)s * TILE_B, ctiles + (size_t)t * TILE_B, TILE_B, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            mbar_wait(qbar, 0);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t a_hi = smem_u32(Aimg), a_lo = a_hi + IMG_B;
+            for (int t = 0; t < ntiles_c; ++t) {
+                const int s = t % NSTB, a = t & 1;
+                mbar_wait(&full[s], (t / NSTB) & 1);
+                if (t >= 2) mbar_wait(&tempty[a], ((t >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t b_hi = smem_u32(Bst + (size_t)s * TILE_B), b_lo = b_hi + IMG_B;
+                const uint32_t acc = tmem + (uint32_t)(a * TM);
+                const uint32_t aa[3] = {a_hi, a_hi, a_lo}, bb[3] = {b_hi, b_lo, b_hi};
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int k = 0; k < TK / 8; ++k)
+                        umma_tf32(acc, umma_desc(aa[p] + k * 32), umma_desc(bb[p] + k * 32), idesc, (p | k) ? 1u : 0u);
+                umma_commit(&empty[s]);   // the stage may be refilled once these MMAs have read it
+                umma_commit(&tfull[a]);   // ... and the accumulator stage is complete
+            }
+        }
+    } else {
+        // ---- selection warps: thread <-> query row <-> TMEM lane
+        const int quarter = warp & 3;                      // TMEM lanes this warp may read
+        const int row = quarter * 32 + lane;
+        uint64_t* h = lists + (size_t)row * kkp;
+        uint2* myq = queues + row;                         // slot r of this thread at myq[r * TM]: conflict-free
+        int cnt = 0;
+        float thr = __int_as_float(0x7f800000);
+        constexpr unsigned FULLW = 0xFFFFFFFFu;
+        // the 128 selection threads stage the norms of the NEXT tile (one float each) while they
+        // work on the current one; a named barrier of the four selection warps orders the buffers
+        const int sel = tid - 64;                            // 0..127
+        nbuf[sel] = reinterpret_cast<const float*>(ctiles + 2 * IMG_B)[sel];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int t = 0; t < ntiles_c; ++t) {
+            const int a = t & 1;
+            float nnext = 0.0f;
+            if (t + 1 < ntiles_c) nnext = __ldg(reinterpret_cast<const float*>(ctiles + (size_t)(t + 1) * TILE_B + 2 * IMG_B) + sel);
+            const float4* nrm = reinterpret_cast<const float4*>(nbuf + a * TM);
+            mbar_wait(&tfull[a], (t >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t cbase = (uint32_t)t * TM;
+            const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TM);
+            uint32_t ra[32], rb[32];
+            tmem_ld32(trow, ra);
+            tmem_ld_wait(ra);
+            auto process = [&](const uint32_t (&r)[32], int c0) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 n4 = nrm[(c0 >> 2) + j];
+                    v[4 * j] = fmaf(-2.0f, __uint_as_float(r[4 * j]), n4.x);
+                    v[4 * j + 1] = fmaf(-2.0f, __uint_as_float(r[4 * j + 1]), n4.y);
+                    v[4 * j + 2] = fmaf(-2.0f, __uint_as_float(r[4 * j + 2]), n4.z);
+                    v[4 * j + 3] = fmaf(-2.0f, __uint_as_float(r[4 * j + 3]), n4.w);
+                }
+                // 8 values at a time: park what beats the (possibly stale) threshold, drain all the
+                // warp's queues side by side when one of them is half full
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float m = v[8 * g];
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) m = fminf(m, v[8 * g + j]);
+                    if (__any_sync(FULLW, m < thr)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (v[8 * g + j] < thr) {
+                                myq[cnt * TM] = make_uint2(cbase + c0 + 8 * g + j, __float_as_uint(v[8 * g + j]));
+                                ++cnt;
+                            }
+                        }
+                        if (__any_sync(FULLW, cnt > TQ - 8)) {
+                            thr = drain_own(h, kk, myq, cnt);
+                            cnt = 0;
+                        }
+                    }
+                }
+            };
+            // the TMEM read of the next 32 columns is in flight while these 32 are selected
+            tmem_ld32(trow + 32, rb);
+            process(ra, 0);
+            tmem_ld_wait(rb);
+            tmem_ld32(trow + 64, ra);
+            process(rb, 32);
+            tmem_ld_wait(ra);
+            tmem_ld32(trow + 96, rb);
+            process(ra, 64);
+            tmem_ld_wait(rb);
+            // all of this warp's reads of the accumulator stage are done
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+            process(rb, 96);
+            // publish the next tile's norms (buffer a^1 was last read during tile t-1)
+            nbuf[(a ^ 1) * TM + sel] = nnext;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        thr = drain_own(h, kk, myq, cnt);
+        // ---- write this query's proposals
+        const long long q = qt * TM + row;
+        if (q < Nq) {
+            const float qnv = reinterpret_cast<const float*>(Aimg + 2 * IMG_B)[row];
+            const size_t ob = (size_t)q * kk;
+            for (int x = 0; x < kk; ++x) {
+                const uint64_t key = h[x];
+                const uint32_t li = (uint32_t)key;
+                float vv = gmd_unflip((uint32_t)(key >> 32));
+                uint32_t oi = GMD_EMPTY_IDX;
+                if (key != GMD_EMPTY_KEY && (long long)li < Nc) {
+                    oi = li + (uint32_t)c_index_offset;
+                    vv = fmaxf(vv + qnv, 0.0f);
+                } else {
+                    vv = __int_as_float(0x7f800000);
+                }
+                cand_idx[ob + x] = oi;
+                cand_val[ob + x] = vv;
+            }
+            float tau = thr;
+            if (h[0] != GMD_EMPTY_KEY) tau = fmaxf(tau + qnv, 0.0f);
+            cand_tau[q] = tau;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+}
+
+}  // namespace gmd_tc
+
+extern "C" int gmd_tc_supported(int k, int metric, int D) {
+    return metric == GMD_L2 && k >= 2 && k <= GMD_MAX_K && D >= 4 && D <= gmd_tc::TK;
+}
+
+extern "C" size_t gmd_tc_tiles_bytes(int64_t N) {
+    if (N < 0) return 0;
+    return (size_t)((N + gmd_tc::TM - 1) / gmd_tc::TM) * gmd_tc::TILE_B;
+}
+
+extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, void* tiles, float* stats,
+                               int32_t* flags, void* stream) {
+    GMD_REQUIRE(X && tiles && flags && N > 0 && D >= 1 && D <= gmd_tc::TK, GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
+    const unsigned grid = (unsigned)((N + gmd_tc::TM - 1) / gmd_tc::TM);
+    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, center, (unsigned char*)tiles, stats, flags);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
+                               int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
+                               void* stream) {
+    GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG, "scan_tc: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan_tc: bad sizes");
+    GMD_REQUIRE(D >= 1 && D <= gmd_tc::TK && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
+    using namespace gmd_tc;
+    const size_t smem = 1024 + (size_t)(1 + NSTB) * TILE_B + (2 * NSTB + 8) * 8 + (size_t)TQ * TM * 8 + 2 * TM * 4 + (size_t)TM * (kk | 1) * 8;
+    GMD_REQUIRE(smem <= GMD_SMEM_LIMIT, GMD_ERR_UNSUPPORTED, "scan_tc: kk=%d needs %zu B of shared memory", kk, smem);
+    GMD_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((Nq + TM - 1) / TM);
+    scan_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(
+        (const unsigned char*)qtiles, (const unsigned char*)ctiles, Nq, Nc, (int)((Nc + TM - 1) / TM), kk,
+        c_index_offset, cand_idx, cand_val, cand_tau);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}

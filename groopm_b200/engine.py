@@ -87,12 +87,19 @@ class KnnPipeline:
         if self.k > self.nc:
             raise ValueError(f"k={self.k} exceeds the {self.nc} candidates")
         self.form = self.lib.gmd_pick_form(self.metric, self.d) if form is None else int(form)
+        self.tc = self.form == _lib.FORM_TC
+        if self.tc and not self.lib.gmd_tc_supported(self.k, self.metric, self.d):
+            raise ValueError("the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 32")
         self.same = bool(same)
         # k = 1 on short profiles (BMU search) has its own heap-free scan
         self.bmu = bool(form is None and self.lib.gmd_use_bmu_scan(self.k, self.metric, self.d))
+        if self.tc:
+            self.bmu = False
         with torch.cuda.device(self.dev):
             if self.bmu:
                 self.kk, self.nsplit = self.lib.gmd_bmu_kk(), 1
+            elif self.tc:
+                self.kk, self.nsplit = self.lib.gmd_pick_kk(self.k), 1
             else:
                 self.kk = self.lib.gmd_pick_kk(self.k)
                 self.nsplit = self.lib.gmd_pick_nsplit(self.nq, self.nc, self.d, self.kk)
@@ -100,9 +107,9 @@ class KnnPipeline:
         self.center = torch.zeros(_lib.MAX_D, dtype=torch.float64, **e)
         self.stats = torch.zeros(4, dtype=torch.float32, **e)
         self.flags = torch.zeros(4, dtype=torch.int32, **e)
-        self.ctiles = torch.empty(self.lib.gmd_tiles_bytes(self.nc, self.d) // 4, dtype=torch.float32, **e)
-        self.qtiles = self.ctiles if same else torch.empty(
-            self.lib.gmd_tiles_bytes(self.nq, self.d) // 4, dtype=torch.float32, **e)
+        tiles_bytes = self.lib.gmd_tc_tiles_bytes if self.tc else (lambda n: self.lib.gmd_tiles_bytes(n, self.d))
+        self.ctiles = torch.empty(tiles_bytes(self.nc) // 4, dtype=torch.float32, **e)
+        self.qtiles = self.ctiles if same else torch.empty(tiles_bytes(self.nq) // 4, dtype=torch.float32, **e)
         m = self.nq * self.nsplit * self.kk
         self.cand_idx = torch.empty(m, dtype=torch.int32, **e)
         self.cand_val = torch.empty(m, dtype=torch.float32, **e)
@@ -120,16 +127,29 @@ class KnnPipeline:
         _lib.check(self.lib.gmd_col_mean_f64(_ptr(c), self.nc, self.d, _ptr(self.center), _stream_ptr()))
 
     def prep_candidates(self, c: torch.Tensor):
+        if self.tc:
+            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(c), self.nc, self.d, _ptr(self.center), _ptr(self.ctiles),
+                                                _ptr(self.stats), _ptr(self.flags), _stream_ptr()))
+            return
         _lib.check(self.lib.gmd_prep_f64(_ptr(c), self.nc, self.d, _ptr(self.center), self.form,
                                          _ptr(self.ctiles), _ptr(self.stats), _ptr(self.flags), _stream_ptr()))
 
     def prep_queries(self, q: torch.Tensor):
         if self.same:
             return
+        if self.tc:
+            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(q), self.nq, self.d, _ptr(self.center), _ptr(self.qtiles),
+                                                _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))
+            return
         _lib.check(self.lib.gmd_prep_f64(_ptr(q), self.nq, self.d, _ptr(self.center), self.form,
                                          _ptr(self.qtiles), _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))
 
     def scan(self):
+        if self.tc:
+            _lib.check(self.lib.gmd_scan_tc_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, self.kk,
+                                                0, _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau),
+                                                _stream_ptr()))
+            return
         if self.bmu:
             _lib.check(self.lib.gmd_scan_bmu_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, 0,
                                                  _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau),
