@@ -120,9 +120,10 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
         } else if (form == GMD_FORM_TC) {
             // 3 x TF32 dot product: representation (3 x 2^-22) and accumulation error measured at
             // 2^-20.9 |q||c| (tools/tc_probe.cu); bounded here by 2^-18 |q||c| <= 2^-20 nn^2, doubled
-            // by the factor -2, plus the FP32 roundings of the norm terms: 48 x 2^-24 nn^2 in all
+            // by the factor -2, plus the norm column (hi + lo: 2^-22 ||c||^2) and the FP32 roundings of the
+            // write-out: 64 x 2^-24 nn^2 in all
             const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
-            const double e2 = 48.0 * U32 * nn * nn;
+            const double e2 = 64.0 * U32 * nn * nn;
             lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
         } else if (form == GMD_FORM_DIRECT_L2) {
             const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;

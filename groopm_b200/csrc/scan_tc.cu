@@ -16,9 +16,16 @@
 // the query's top-kk heap in shared memory all by itself (no queues, no atomics: a thread
 // sees every candidate of its query, in ascending index order).
 //
+// The norm rides in the contraction: column D of a QUERY image holds 1, column D of a
+// CANDIDATE image holds -||c||^2 / 2, so the accumulator is  u = q.c - ||c||^2/2 = -s/2  with
+// s = ||c||^2 - 2 q.c the value the FP32 scan ranks by; selection maximises u directly (no
+// per-pair FMA, no norm loads) and converts to s = -2u (exact) only for the few values it keeps.
+//
 // HBM tile format ("TC tile", 128 profiles): [hi image 16 KB][lo image 16 KB][||x||^2 128 f32]
 // [pad to 33 KB], images already in the swizzled shared-memory layout so that one bulk copy
-// per tile is all the producer does.
+// per tile is all the producer does.  Query and candidate tiles differ in column D only.
+#include <stdlib.h>
+
 #include "scan_impl.cuh"
 
 namespace gmd_tc {
@@ -80,9 +87,28 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 
 // ------------------------------------------------------------------ staging: float64 rows -> TC tiles
 __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long N, int D,
-                                                      const double* __restrict__ center,
+                                                      const double* __restrict__ center, int role,
                                                       unsigned char* __restrict__ tiles, float* __restrict__ stats,
                                                       int* __restrict__ flags) {
+    // role 0: query tile (column D = 1), role 1: candidate tile (column D = -||x||^2 / 2)
+    __shared__ float s_n2[TM];
+    if (threadIdx.x < TM) {
+        const long long row = (long long)blockIdx.x * TM + threadIdx.x;
+        double n2 = 0.0, n1 = 0.0;
+        if (row < N) {
+            for (int k = 0; k < D; ++k) {
+                const double v = (double)(float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0));
+                n2 += v * v;
+                n1 += fabs(v);
+            }
+        }
+        s_n2[threadIdx.x] = row < N ? (float)n2 : GMD_PAD_AUX;
+        if (row < N && stats) {
+            atomicMax(reinterpret_cast<int*>(stats), __float_as_int(__double2float_ru(n2)));
+            atomicMax(reinterpret_cast<int*>(stats) + 1, __float_as_int(__double2float_ru(n1)));
+        }
+    }
+    __syncthreads();
     const long long t = blockIdx.x, row0 = t * TM;
     float* hi = reinterpret_cast<float*>(tiles + (size_t)t * TILE_B);
     float* lo = hi + IMG_B / 4;
@@ -96,6 +122,8 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
             const double x = X[(size_t)row * D + k];
             bad |= !isfinite(x);
             v = (float)(x - (center ? center[k] : 0.0));
+        } else if (k == D) {
+            v = role == 0 ? 1.0f : -0.5f * s_n2[r];
         }
         const float h = tf32_rn(v);
         // shared-memory image: 8-row groups of 1024 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7)
@@ -104,23 +132,7 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
         lo[off] = tf32_rn(v - h);
     }
     if (bad) atomicExch(flags, 1);
-    if (threadIdx.x < TM) {
-        const int r = threadIdx.x;
-        const long long row = row0 + r;
-        double n2 = 0.0, n1 = 0.0;
-        if (row < N) {
-            for (int k = 0; k < D; ++k) {
-                const double v = (double)(float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0));
-                n2 += v * v;
-                n1 += fabs(v);
-            }
-        }
-        nrm[r] = row < N ? (float)n2 : GMD_PAD_AUX;
-        if (row < N && stats) {
-            atomicMax(reinterpret_cast<int*>(stats), __float_as_int(__double2float_ru(n2)));
-            atomicMax(reinterpret_cast<int*>(stats) + 1, __float_as_int(__double2float_ru(n1)));
-        }
-    }
+    if (threadIdx.x < TM) nrm[threadIdx.x] = s_n2[threadIdx.x];
 }
 
 // ------------------------------------------------------------------ the scan
@@ -142,7 +154,7 @@ static __device__ __noinline__ float drain_own(uint64_t* h, int kk, const uint2*
 __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned char* __restrict__ qtiles,
                                                               const unsigned char* __restrict__ ctiles,
                                                               long long Nq, long long Nc, int ntiles_c, int kk,
-                                                              long long c_index_offset,
+                                                              long long c_index_offset, int dbg,
                                                               uint32_t* __restrict__ cand_idx,
                                                               float* __restrict__ cand_val,
                                                               float* __restrict__ cand_tau) {
@@ -158,8 +170,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     uint64_t* qbar = bars + 2 * NSTB + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 6);
     uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NSTB + 8);        // [TQ][128] parked (index, value bits)
-    float* nbuf = reinterpret_cast<float*>(queues + TQ * TM);             // [2][128] ||c||^2 of the tile in flight
-    uint64_t* lists = reinterpret_cast<uint64_t*>(nbuf + 2 * TM);         // [128][kkp] heaps
+    uint64_t* lists = reinterpret_cast<uint64_t*>(queues + TQ * TM);      // [128][kkp] heaps
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kkp = kk | 1;
@@ -232,16 +243,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         int cnt = 0;
         float thr = __int_as_float(0x7f800000);
         constexpr unsigned FULLW = 0xFFFFFFFFu;
-        // the 128 selection threads stage the norms of the NEXT tile (one float each) while they
-        // work on the current one; a named barrier of the four selection warps orders the buffers
-        const int sel = tid - 64;                            // 0..127
-        nbuf[sel] = reinterpret_cast<const float*>(ctiles + 2 * IMG_B)[sel];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float uthr = __int_as_float(0xff800000);            // -thr / 2: the accumulators are u = -s/2
         for (int t = 0; t < ntiles_c; ++t) {
             const int a = t & 1;
-            float nnext = 0.0f;
-            if (t + 1 < ntiles_c) nnext = __ldg(reinterpret_cast<const float*>(ctiles + (size_t)(t + 1) * TILE_B + 2 * IMG_B) + sel);
-            const float4* nrm = reinterpret_cast<const float4*>(nbuf + a * TM);
             mbar_wait(&tfull[a], (t >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t cbase = (uint32_t)t * TM;
@@ -250,33 +254,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             tmem_ld32(trow, ra);
             tmem_ld_wait(ra);
             auto process = [&](const uint32_t (&r)[32], int c0) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 n4 = nrm[(c0 >> 2) + j];
-                    v[4 * j] = fmaf(-2.0f, __uint_as_float(r[4 * j]), n4.x);
-                    v[4 * j + 1] = fmaf(-2.0f, __uint_as_float(r[4 * j + 1]), n4.y);
-                    v[4 * j + 2] = fmaf(-2.0f, __uint_as_float(r[4 * j + 2]), n4.z);
-                    v[4 * j + 3] = fmaf(-2.0f, __uint_as_float(r[4 * j + 3]), n4.w);
-                }
-                // 8 values at a time: park what beats the (possibly stale) threshold, drain all the
-                // warp's queues side by side when one of them is half full
+                if (dbg == 1) return;  // developer probe: MMA + copy pipeline only
+                // group maxima as trees (a chain of dependent ops is pure latency for the one
+                // selection warp of a scheduler), one vote per 32 columns
+                float gm[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    float m = v[8 * g];
+                    const float m01 = fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
+                    const float m23 = fmaxf(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+                    const float m45 = fmaxf(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+                    const float m67 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                    gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+                }
+                const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+                if (__any_sync(FULLW, cm > uthr)) {
+                    // 8 values at a time: park what beats the (possibly stale) threshold, drain all
+                    // the warp's queues side by side when one of them is half full
 #pragma unroll
-                    for (int j = 1; j < 8; ++j) m = fminf(m, v[8 * g + j]);
-                    if (__any_sync(FULLW, m < thr)) {
+                    for (int g = 0; g < 4; ++g) {
+                        if (__any_sync(FULLW, gm[g] > uthr)) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (v[8 * g + j] < thr) {
-                                myq[cnt * TM] = make_uint2(cbase + c0 + 8 * g + j, __float_as_uint(v[8 * g + j]));
-                                ++cnt;
+                            for (int j = 0; j < 8; ++j) {
+                                const float u = __uint_as_float(r[8 * g + j]);
+                                if (u > uthr) {
+                                    myq[cnt * TM] = make_uint2(cbase + c0 + 8 * g + j, __float_as_uint(-2.0f * u));
+                                    ++cnt;
+                                }
                             }
-                        }
-                        if (__any_sync(FULLW, cnt > TQ - 8)) {
-                            thr = drain_own(h, kk, myq, cnt);
-                            cnt = 0;
+                            if (__any_sync(FULLW, cnt > TQ - 8)) {
+                                thr = drain_own(h, kk, myq, cnt);
+                                uthr = -0.5f * thr;
+                                cnt = 0;
+                            }
                         }
                     }
                 }
@@ -296,9 +305,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
             process(rb, 96);
-            // publish the next tile's norms (buffer a^1 was last read during tile t-1)
-            nbuf[(a ^ 1) * TM + sel] = nnext;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         thr = drain_own(h, kk, myq, cnt);
         // ---- write this query's proposals
@@ -333,7 +339,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
 }  // namespace gmd_tc
 
 extern "C" int gmd_tc_supported(int k, int metric, int D) {
-    return metric == GMD_L2 && k >= 2 && k <= GMD_MAX_K && D >= 4 && D <= gmd_tc::TK;
+    // one column of the K = 32 contraction carries the norm
+    return metric == GMD_L2 && k >= 2 && k <= GMD_MAX_K && D >= 4 && D < gmd_tc::TK;
 }
 
 extern "C" size_t gmd_tc_tiles_bytes(int64_t N) {
@@ -341,11 +348,13 @@ extern "C" size_t gmd_tc_tiles_bytes(int64_t N) {
     return (size_t)((N + gmd_tc::TM - 1) / gmd_tc::TM) * gmd_tc::TILE_B;
 }
 
-extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, void* tiles, float* stats,
-                               int32_t* flags, void* stream) {
-    GMD_REQUIRE(X && tiles && flags && N > 0 && D >= 1 && D <= gmd_tc::TK, GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
+extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role, void* tiles,
+                               float* stats, int32_t* flags, void* stream) {
+    GMD_REQUIRE(X && tiles && flags && N > 0 && D >= 1 && D < gmd_tc::TK && (role == 0 || role == 1), GMD_ERR_BAD_ARG,
+                "prep_tc: bad arguments");
     const unsigned grid = (unsigned)((N + gmd_tc::TM - 1) / gmd_tc::TM);
-    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, center, (unsigned char*)tiles, stats, flags);
+    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, center, role, (unsigned char*)tiles, stats,
+                                                                  flags);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }
@@ -355,15 +364,15 @@ extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctile
                                void* stream) {
     GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG, "scan_tc: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan_tc: bad sizes");
-    GMD_REQUIRE(D >= 1 && D <= gmd_tc::TK && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
+    GMD_REQUIRE(D >= 1 && D < gmd_tc::TK && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
     using namespace gmd_tc;
-    const size_t smem = 1024 + (size_t)(1 + NSTB) * TILE_B + (2 * NSTB + 8) * 8 + (size_t)TQ * TM * 8 + 2 * TM * 4 + (size_t)TM * (kk | 1) * 8;
+    const size_t smem = 1024 + (size_t)(1 + NSTB) * TILE_B + (2 * NSTB + 8) * 8 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8;
     GMD_REQUIRE(smem <= GMD_SMEM_LIMIT, GMD_ERR_UNSUPPORTED, "scan_tc: kk=%d needs %zu B of shared memory", kk, smem);
     GMD_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((Nq + TM - 1) / TM);
     scan_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(
         (const unsigned char*)qtiles, (const unsigned char*)ctiles, Nq, Nc, (int)((Nc + TM - 1) / TM), kk,
-        c_index_offset, cand_idx, cand_val, cand_tau);
+        c_index_offset, getenv("GMD_TC_DBG") ? atoi(getenv("GMD_TC_DBG")) : 0, cand_idx, cand_val, cand_tau);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }

@@ -89,7 +89,7 @@ class KnnPipeline:
         self.form = self.lib.gmd_pick_form(self.metric, self.d) if form is None else int(form)
         self.tc = self.form == _lib.FORM_TC
         if self.tc and not self.lib.gmd_tc_supported(self.k, self.metric, self.d):
-            raise ValueError("the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 32")
+            raise ValueError("the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 31")
         self.same = bool(same)
         # k = 1 on short profiles (BMU search) has its own heap-free scan
         self.bmu = bool(form is None and self.lib.gmd_use_bmu_scan(self.k, self.metric, self.d))
@@ -109,7 +109,9 @@ class KnnPipeline:
         self.flags = torch.zeros(4, dtype=torch.int32, **e)
         tiles_bytes = self.lib.gmd_tc_tiles_bytes if self.tc else (lambda n: self.lib.gmd_tiles_bytes(n, self.d))
         self.ctiles = torch.empty(tiles_bytes(self.nc) // 4, dtype=torch.float32, **e)
-        self.qtiles = self.ctiles if same else torch.empty(tiles_bytes(self.nq) // 4, dtype=torch.float32, **e)
+        # tensor-core tiles differ by role (column D), so queries are always staged separately there
+        self.qtiles = self.ctiles if (same and not self.tc) else torch.empty(
+            tiles_bytes(self.nq) // 4, dtype=torch.float32, **e)
         m = self.nq * self.nsplit * self.kk
         self.cand_idx = torch.empty(m, dtype=torch.int32, **e)
         self.cand_val = torch.empty(m, dtype=torch.float32, **e)
@@ -128,18 +130,18 @@ class KnnPipeline:
 
     def prep_candidates(self, c: torch.Tensor):
         if self.tc:
-            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(c), self.nc, self.d, _ptr(self.center), _ptr(self.ctiles),
+            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(c), self.nc, self.d, _ptr(self.center), 1, _ptr(self.ctiles),
                                                 _ptr(self.stats), _ptr(self.flags), _stream_ptr()))
             return
         _lib.check(self.lib.gmd_prep_f64(_ptr(c), self.nc, self.d, _ptr(self.center), self.form,
                                          _ptr(self.ctiles), _ptr(self.stats), _ptr(self.flags), _stream_ptr()))
 
     def prep_queries(self, q: torch.Tensor):
-        if self.same:
-            return
         if self.tc:
-            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(q), self.nq, self.d, _ptr(self.center), _ptr(self.qtiles),
+            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(q), self.nq, self.d, _ptr(self.center), 0, _ptr(self.qtiles),
                                                 _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))
+            return
+        if self.same:
             return
         _lib.check(self.lib.gmd_prep_f64(_ptr(q), self.nq, self.d, _ptr(self.center), self.form,
                                          _ptr(self.qtiles), _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))

@@ -134,11 +134,13 @@ GMD_API int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctile
  * per-query heaps.  Its operands are "TC tiles" (128 profiles: hi image, lo image, norms;
  * gmd_tc_tiles_bytes / gmd_prep_tc_f64).  Outputs as gmd_scan_topk_f32 with nsplit = 1, to be
  * finished by gmd_refine_topk_f64(form = GMD_FORM_TC) / gmd_exact_rows_f64.
- * gmd_tc_supported(k, metric, D): Euclidean, 2 <= k <= 64, 4 <= D <= 32.                  */
+ * Query and candidate tiles differ (column D carries 1 resp. -||c||^2/2, so the norm rides in
+ * the contraction): the same rows must be staged once per role.
+ * gmd_tc_supported(k, metric, D): Euclidean, 2 <= k <= 64, 4 <= D <= 31.                  */
 GMD_API int gmd_tc_supported(int k, int metric, int D);
 GMD_API size_t gmd_tc_tiles_bytes(int64_t N);
-GMD_API int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, void* tiles, float* stats,
-                    int32_t* flags, void* stream);
+GMD_API int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role /* 0 queries, 1 candidates */,
+                    void* tiles, float* stats, int32_t* flags, void* stream);
 GMD_API int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
                     int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
                     void* stream);
