@@ -36,6 +36,15 @@ extern "C" int gmd_use_bmu_scan(int k, int metric, int D) {
 }
 extern "C" int gmd_bmu_kk(void) { return gmd_scan::BMU_KK; }
 
+// The tensor-core scan (scan_tc.cu) wins once both sides are large enough to fill the SMs with
+// its 128-query CTAs and to amortise its per-CTA set-up (measured cross-over ~50 k rows at
+// D = 10; 2.4 x at 250 k x 30, 3.2 x at 1 M x 30).  GMD_TC=0 / 1 overrides (developer switch).
+extern "C" int gmd_use_tc_scan(int64_t Nq, int64_t Nc, int k, int metric, int D) {
+    if (!gmd_tc_supported(k, metric, D)) return 0;
+    if (const char* env = getenv("GMD_TC")) return atoi(env) != 0;
+    return Nq >= 32768 && Nc >= 32768;
+}
+
 extern "C" int gmd_pick_kk(int k) { return k + std::min(8, std::max(3, k / 4)); }
 
 extern "C" int gmd_pick_nsplit(int64_t Nq, int64_t Nc, int D, int kk) {
@@ -146,7 +155,7 @@ struct Workspace {
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, bool same) {
+Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, bool same, bool tc = false) {
     Workspace w;
     char* p = (char*)base;
     size_t off = 0;
@@ -158,8 +167,8 @@ Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, b
     w.center = (double*)take(sizeof(double) * GMD_MAX_D);
     w.stats = (float*)take(sizeof(float) * 4);
     w.flags = (int32_t*)take(sizeof(int32_t) * 4);
-    w.ctiles = (float*)take(gmd_tiles_bytes(Nc, D));
-    w.qtiles = same ? w.ctiles : (float*)take(gmd_tiles_bytes(Nq, D));
+    w.ctiles = (float*)take(tc ? gmd_tc_tiles_bytes(Nc) : gmd_tiles_bytes(Nc, D));
+    w.qtiles = (same && !tc) ? w.ctiles : (float*)take(tc ? gmd_tc_tiles_bytes(Nq) : gmd_tiles_bytes(Nq, D));
     w.cand_idx = (uint32_t*)take((size_t)Nq * nsplit * kk * sizeof(uint32_t));
     w.cand_val = (float*)take((size_t)Nq * nsplit * kk * sizeof(float));
     w.cand_tau = (float*)take((size_t)Nq * nsplit * sizeof(float));
@@ -172,7 +181,9 @@ Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, b
 extern "C" size_t gmd_knn_workspace_bytes(int64_t Nq, int64_t Nc, int D, int k) {
     // same policy as gmd_knn_f64 (the larger of the two scans' needs); sized for separate query tiles
     const int kk = std::max(gmd_pick_kk(k), k == 1 ? gmd_scan::BMU_KK : 0);
-    return carve(nullptr, Nq, Nc, D, kk, gmd_pick_nsplit(Nq, Nc, D, kk), false).bytes;
+    const size_t plain = carve(nullptr, Nq, Nc, D, kk, gmd_pick_nsplit(Nq, Nc, D, kk), false).bytes;
+    const size_t tc = gmd_tc_supported(k, GMD_L2, D) ? carve(nullptr, Nq, Nc, D, kk, 1, false, true).bytes : 0;
+    return std::max(plain, tc);
 }
 
 extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
@@ -184,14 +195,17 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     GMD_REQUIRE(k >= 1 && k <= GMD_MAX_K, GMD_ERR_UNSUPPORTED, "knn: k=%d outside [1, %d]", k, GMD_MAX_K);
     GMD_REQUIRE(k <= Nc, GMD_ERR_BAD_ARG, "knn: k=%d exceeds the %lld candidates", k, (long long)Nc);
     GMD_REQUIRE(metric == GMD_L2 || metric == GMD_L1, GMD_ERR_BAD_ARG, "knn: bad metric %d", metric);
-    if (form == GMD_FORM_AUTO) form = gmd_pick_form(metric, D);
+    if (form == GMD_FORM_AUTO) form = gmd_use_tc_scan(Nq, Nc, k, metric, D) ? GMD_FORM_TC : gmd_pick_form(metric, D);
     GMD_REQUIRE((metric == GMD_L1) == (form == GMD_FORM_DIRECT_L1), GMD_ERR_BAD_ARG,
                 "knn: form %d does not compute metric %d", form, metric);
+    const bool tc = form == GMD_FORM_TC;
+    GMD_REQUIRE(!tc || gmd_tc_supported(k, metric, D), GMD_ERR_UNSUPPORTED,
+                "knn: the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 31");
     const bool bmu = form == GMD_FORM_EXPANDED && gmd_use_bmu_scan(k, metric, D);
     const int kk = bmu ? gmd_scan::BMU_KK : gmd_pick_kk(k);
-    const int nsplit = bmu ? 1 : gmd_pick_nsplit(Nq, Nc, D, kk);
+    const int nsplit = (bmu || tc) ? 1 : gmd_pick_nsplit(Nq, Nc, D, kk);
     const bool same = (Q == C && Nq == Nc);
-    Workspace w = carve(workspace, Nq, Nc, D, kk, nsplit, same);
+    Workspace w = carve(workspace, Nq, Nc, D, kk, nsplit, same, tc);
     GMD_REQUIRE(w.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "knn: workspace %zu B < required %zu B",
                 workspace_bytes, w.bytes);
     cudaStream_t st = (cudaStream_t)stream;
@@ -199,10 +213,16 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     GMD_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, sizeof(int32_t) * 4, st));
     int rc;
     if ((rc = gmd_col_mean_f64(C, Nc, D, w.center, stream)) != GMD_OK) return rc;
-    if ((rc = gmd_prep_f64(C, Nc, D, w.center, form, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
-    if (!same && (rc = gmd_prep_f64(Q, Nq, D, w.center, form, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK)
-        return rc;
-    rc = bmu ? gmd_scan_bmu_f32(w.qtiles, Nq, w.ctiles, Nc, D, 0, w.cand_idx, w.cand_val, w.cand_tau, stream)
+    if (tc) {
+        if ((rc = gmd_prep_tc_f64(C, Nc, D, w.center, 1, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
+        if ((rc = gmd_prep_tc_f64(Q, Nq, D, w.center, 0, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK) return rc;
+    } else {
+        if ((rc = gmd_prep_f64(C, Nc, D, w.center, form, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
+        if (!same && (rc = gmd_prep_f64(Q, Nq, D, w.center, form, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK)
+            return rc;
+    }
+    rc = tc ? gmd_scan_tc_f32(w.qtiles, Nq, w.ctiles, Nc, D, kk, 0, w.cand_idx, w.cand_val, w.cand_tau, stream) :
+         bmu ? gmd_scan_bmu_f32(w.qtiles, Nq, w.ctiles, Nc, D, 0, w.cand_idx, w.cand_val, w.cand_tau, stream)
              : gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,
                                  w.cand_tau, stream);
     if (rc != GMD_OK) return rc;

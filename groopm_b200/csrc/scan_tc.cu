@@ -35,7 +35,6 @@ constexpr int TM = 128;                  // profiles per TC tile (UMMA M and N)
 constexpr int TK = 32;                   // contraction length (padded D)
 constexpr int IMG_B = TM * TK * 4;       // one image: 16 KB
 constexpr int TILE_B = 2 * IMG_B + 1024; // hi, lo, norms (512 B used)
-constexpr int NSTB = 4;                  // candidate stages in shared memory
 constexpr int NTHREADS = 192;
 
 __device__ __forceinline__ float tf32_rn(float x) {
@@ -151,6 +150,8 @@ static __device__ __noinline__ float drain_own(uint64_t* h, int kk, const uint2*
     return (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
 }
 
+// NSTB: candidate stages in shared memory (4 when the heaps leave room, else 3 or 2)
+template <int NSTB>
 __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned char* __restrict__ qtiles,
                                                               const unsigned char* __restrict__ ctiles,
                                                               long long Nq, long long Nc, int ntiles_c, int kk,
@@ -366,13 +367,22 @@ extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctile
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan_tc: bad sizes");
     GMD_REQUIRE(D >= 1 && D < gmd_tc::TK && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
     using namespace gmd_tc;
-    const size_t smem = 1024 + (size_t)(1 + NSTB) * TILE_B + (2 * NSTB + 8) * 8 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8;
+    const size_t fixed = 1024 + (size_t)TILE_B + 256 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8;
+    int nst = 4;
+    while (nst > 2 && fixed + (size_t)nst * TILE_B > GMD_SMEM_LIMIT) --nst;
+    const size_t smem = fixed + (size_t)nst * TILE_B;
     GMD_REQUIRE(smem <= GMD_SMEM_LIMIT, GMD_ERR_UNSUPPORTED, "scan_tc: kk=%d needs %zu B of shared memory", kk, smem);
-    GMD_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((Nq + TM - 1) / TM);
-    scan_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(
-        (const unsigned char*)qtiles, (const unsigned char*)ctiles, Nq, Nc, (int)((Nc + TM - 1) / TM), kk,
-        c_index_offset, getenv("GMD_TC_DBG") ? atoi(getenv("GMD_TC_DBG")) : 0, cand_idx, cand_val, cand_tau);
+    const int dbg = getenv("GMD_TC_DBG") ? atoi(getenv("GMD_TC_DBG")) : 0;  // developer probe
+    auto launch = [&](auto kern) -> int {
+        GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>((const unsigned char*)qtiles, (const unsigned char*)ctiles,
+                                                           Nq, Nc, (int)((Nc + TM - 1) / TM), kk, c_index_offset, dbg,
+                                                           cand_idx, cand_val, cand_tau);
+        return GMD_OK;
+    };
+    const int rc = nst == 4 ? launch(scan_tc_kernel<4>) : nst == 3 ? launch(scan_tc_kernel<3>) : launch(scan_tc_kernel<2>);
+    if (rc != GMD_OK) return rc;
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }

@@ -86,13 +86,20 @@ class KnnPipeline:
             raise ValueError(f"k={self.k} outside [1, {_lib.MAX_K}]")
         if self.k > self.nc:
             raise ValueError(f"k={self.k} exceeds the {self.nc} candidates")
-        self.form = self.lib.gmd_pick_form(self.metric, self.d) if form is None else int(form)
+        if form is None:
+            # large Euclidean problems go to the tensor-core scan, the rest to the FP32 forms
+            form = (_lib.FORM_TC if self.lib.gmd_use_tc_scan(self.nq, self.nc, self.k, self.metric, self.d)
+                    else self.lib.gmd_pick_form(self.metric, self.d))
+            auto = True
+        else:
+            auto = False
+        self.form = int(form)
         self.tc = self.form == _lib.FORM_TC
         if self.tc and not self.lib.gmd_tc_supported(self.k, self.metric, self.d):
             raise ValueError("the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 31")
         self.same = bool(same)
         # k = 1 on short profiles (BMU search) has its own heap-free scan
-        self.bmu = bool(form is None and self.lib.gmd_use_bmu_scan(self.k, self.metric, self.d))
+        self.bmu = bool(auto and self.lib.gmd_use_bmu_scan(self.k, self.metric, self.d))
         if self.tc:
             self.bmu = False
         with torch.cuda.device(self.dev):

@@ -138,6 +138,7 @@ GMD_API int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctile
  * the contraction): the same rows must be staged once per role.
  * gmd_tc_supported(k, metric, D): Euclidean, 2 <= k <= 64, 4 <= D <= 31.                  */
 GMD_API int gmd_tc_supported(int k, int metric, int D);
+GMD_API int gmd_use_tc_scan(int64_t Nq, int64_t Nc, int k, int metric, int D);  /* the size policy of gmd_knn_f64 */
 GMD_API size_t gmd_tc_tiles_bytes(int64_t N);
 GMD_API int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role /* 0 queries, 1 candidates */,
                     void* tiles, float* stats, int32_t* flags, void* stream);

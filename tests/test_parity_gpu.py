@@ -457,3 +457,49 @@ def test_batched_medians_vs_oracle(cuda):
     assert dropin.k_dist_many(kpc, [big])[0] == oracle.k_dist(kpc[big])
     with pytest.raises(IndexError):
         dropin.k_dist_many(kpc, [np.array([0, len(kpc)])])
+
+
+# ------------------------------------------------------------------ tensor-core scan (GMD_FORM_TC)
+
+@pytest.mark.parametrize("n,nq,d,k", [
+    (5000, None, 4, 2), (3000, None, 31, 64), (9000, None, 10, 16), (4097, 1000, 17, 6),
+    (129, None, 8, 32), (128, 77, 30, 5), (20000, None, 30, 32),
+])
+def test_tensor_core_scan_vs_oracle(cuda, n, nq, d, k):
+    """The tcgen05 3 x TF32 scan forced on (form=GMD_FORM_TC) at sizes the oracle finishes in
+    seconds: tile edges (128-row TC tiles), duplicates, separate query sets, k up to 64.
+    Results must be the float64 ones bit for bit, like every other form."""
+    rng = np.random.default_rng(7 * n + d)
+    c = rng.standard_normal((n, d)) * rng.uniform(0.5, 20.0, size=d) + rng.uniform(-50, 50, size=d)
+    synth.add_duplicates(c, rng, 0.01)
+    q = None if nq is None else c[rng.choice(n, nq, replace=False)] + 1e-3 * rng.standard_normal((nq, d))
+    k = min(k, n)
+    idx, dist, info = engine.knn(c if q is None else q, None if q is None else c, k=k, form=_lib.FORM_TC,
+                                 return_info=True)
+    assert info["form"] == _lib.FORM_TC
+    od, oi = oracle.knn(c if q is None else q, c, k)
+    assert_knn_parity(c if q is None else q, c, idx, dist, oi, od)
+    assert np.array_equal(dist, od)
+
+
+def test_tensor_core_scan_limits_and_policy(cuda):
+    lib = _lib.lib()
+    assert lib.gmd_tc_supported(16, _lib.L2, 31) == 1 and lib.gmd_tc_supported(16, _lib.L2, 32) == 0
+    assert lib.gmd_tc_supported(16, _lib.L1, 10) == 0 and lib.gmd_tc_supported(1, _lib.L2, 10) == 0
+    assert lib.gmd_use_tc_scan(100_000, 100_000, 16, _lib.L2, 10) == 1
+    assert lib.gmd_use_tc_scan(2_000, 100_000, 16, _lib.L2, 10) == 0
+    x = np.random.default_rng(0).random((500, 32))
+    with pytest.raises(ValueError):
+        engine.knn(x, None, k=4, form=_lib.FORM_TC)
+    with pytest.raises(ValueError):
+        engine.knn(x[:, :8], None, k=4, metric="cityblock", form=_lib.FORM_TC)
+
+
+def test_tensor_core_scan_ill_conditioned_falls_back(cuda):
+    # far-from-origin clusters with tiny spread: the certificate must send rows to the exact scan
+    rng = np.random.default_rng(12)
+    centres = rng.uniform(0, 999, size=(30, 4))
+    x = centres[rng.integers(0, 30, size=5000)] + 0.01 * rng.standard_normal((5000, 4))
+    idx, dist, info = engine.knn(x, None, k=6, form=_lib.FORM_TC, return_info=True)
+    od, oi = oracle.knn(x, x, 6)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
