@@ -150,7 +150,8 @@ static __device__ __noinline__ float drain_own(uint64_t* h, int kk, const uint2*
     return (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
 }
 
-// NSTB: candidate stages in shared memory (4 when the heaps leave room, else 3 or 2)
+// NSTB: pipeline depth = candidate stages in shared memory = accumulator stages in tensor memory
+// (4 when the heaps leave room in shared memory, else 3 or 2)
 template <int NSTB>
 __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned char* __restrict__ qtiles,
                                                               const unsigned char* __restrict__ ctiles,
@@ -164,13 +165,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     unsigned char* Aimg = base;                          // hi, lo images + norms of the CTA's queries (one TC tile)
     unsigned char* Bst = base + TILE_B;                  // NSTB candidate stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + (size_t)NSTB * TILE_B);
-    uint64_t* full = bars;                               // [NSTB] candidate tile landed
-    uint64_t* empty = bars + NSTB;                       // [NSTB] MMAs that read the stage are done
-    uint64_t* tfull = bars + 2 * NSTB;                   // [2] accumulator stage written
-    uint64_t* tempty = bars + 2 * NSTB + 2;              // [2] accumulator stage read back
-    uint64_t* qbar = bars + 2 * NSTB + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 6);
-    uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NSTB + 8);        // [TQ][128] parked (index, value bits)
+    uint64_t* full = bars;                               // [NSTB] candidate tile landed in shared memory
+    uint64_t* done = bars + NSTB;                        // [NSTB] the tile's MMAs are complete: the accumulator
+                                                         //        stage is written and the smem stage is free
+    uint64_t* tempty = bars + 2 * NSTB;                  // [NSTB] accumulator stage read back by the selection warps
+    uint64_t* qbar = bars + 3 * NSTB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NSTB + 2);
+    uint2* queues = reinterpret_cast<uint2*>(bars + 3 * NSTB + 4);        // [TQ][128] parked (index, value bits)
     uint64_t* lists = reinterpret_cast<uint64_t*>(queues + TQ * TM);      // [128][kkp] heaps
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -180,11 +181,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     if (tid == 0) {
         for (int s = 0; s < NSTB; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&done[s], 1);
+            mbar_init(&tempty[s], 4);
         }
         mbar_init(qbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,7 +192,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     }
     for (int e = tid; e < TM * kkp; e += NTHREADS) lists[e] = GMD_EMPTY_KEY;
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -207,7 +205,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         if (lane == 0) {
             for (int t = 0; t < ntiles_c; ++t) {
                 const int s = t % NSTB;
-                if (t >= NSTB) mbar_wait_backoff(&empty[s], ((t / NSTB) - 1) & 1, 64);
+                if (t >= NSTB) mbar_wait_backoff(&done[s], ((t / NSTB) - 1) & 1, 64);
+                if (dbg == 2) {  // developer probe: no candidate traffic (1 KB per tile), MMAs on stale data
+                    mbar_expect_tx(&full[s], 1024);
+                    bulk_g2s(Bst + (size_t)s * TILE_B, ctiles + (size_t)t * TILE_B, 1024, &full[s]);
+                    continue;
+                }
                 mbar_expect_tx(&full[s], TILE_B);
                 bulk_g2s(Bst + (size_t)s * TILE_B, ctiles + (size_t)t * TILE_B, TILE_B, &full[s]);
             }
@@ -217,22 +220,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         if (lane == 0) {
             mbar_wait(qbar, 0);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint32_t a_hi = smem_u32(Aimg), a_lo = a_hi + IMG_B;
+            // descriptors differ only in the 16-byte-granular start address: build them once and add
+            const uint64_t a_hi = umma_desc(smem_u32(Aimg)), a_lo = a_hi + (IMG_B >> 4);
+            const uint64_t b_base = umma_desc(smem_u32(Bst));
             for (int t = 0; t < ntiles_c; ++t) {
-                const int s = t % NSTB, a = t & 1;
+                const int s = t % NSTB;
                 mbar_wait(&full[s], (t / NSTB) & 1);
-                if (t >= 2) mbar_wait(&tempty[a], ((t >> 1) - 1) & 1);
+                if (t >= NSTB) mbar_wait(&tempty[s], ((t / NSTB) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t b_hi = smem_u32(Bst + (size_t)s * TILE_B), b_lo = b_hi + IMG_B;
-                const uint32_t acc = tmem + (uint32_t)(a * TM);
-                const uint32_t aa[3] = {a_hi, a_hi, a_lo}, bb[3] = {b_hi, b_lo, b_hi};
+                const uint64_t b_hi = b_base + (uint64_t)s * (TILE_B >> 4), b_lo = b_hi + (IMG_B >> 4);
+                const uint32_t acc = tmem + (uint32_t)(s * TM);
 #pragma unroll
                 for (int p = 0; p < 3; ++p)
 #pragma unroll
                     for (int k = 0; k < TK / 8; ++k)
-                        umma_tf32(acc, umma_desc(aa[p] + k * 32), umma_desc(bb[p] + k * 32), idesc, (p | k) ? 1u : 0u);
-                umma_commit(&empty[s]);   // the stage may be refilled once these MMAs have read it
-                umma_commit(&tfull[a]);   // ... and the accumulator stage is complete
+                        umma_tf32(acc, (p == 2 ? a_lo : a_hi) + 2 * k, (p == 1 ? b_lo : b_hi) + 2 * k, idesc,
+                                  (p | k) ? 1u : 0u);
+                umma_commit(&done[s]);   // one commit: accumulator stage written, shared-memory stage readable again
             }
         }
     } else {
@@ -246,16 +250,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         constexpr unsigned FULLW = 0xFFFFFFFFu;
         float uthr = __int_as_float(0xff800000);            // -thr / 2: the accumulators are u = -s/2
         for (int t = 0; t < ntiles_c; ++t) {
-            const int a = t & 1;
-            mbar_wait(&tfull[a], (t >> 1) & 1);
+            const int a = t % NSTB;
+            mbar_wait(&done[a], (t / NSTB) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t cbase = (uint32_t)t * TM;
             const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TM);
-            uint32_t ra[32], rb[32];
-            tmem_ld32(trow, ra);
-            tmem_ld_wait(ra);
+            // all 128 columns of the row in flight at once, then the accumulator stage goes back
+            uint32_t r0[32], r1[32], r2[32], r3[32];
+            tmem_ld32(trow, r0);
+            tmem_ld32(trow + 32, r1);
+            tmem_ld32(trow + 64, r2);
+            tmem_ld32(trow + 96, r3);
+            tmem_ld_wait(r0);
+            tmem_ld_wait(r1);
+            tmem_ld_wait(r2);
+            tmem_ld_wait(r3);
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
             auto process = [&](const uint32_t (&r)[32], int c0) {
-                if (dbg == 1) return;  // developer probe: MMA + copy pipeline only
+                if (dbg >= 1) return;  // developer probe: MMA + copy pipeline only
                 // group maxima as trees (a chain of dependent ops is pure latency for the one
                 // selection warp of a scheduler), one vote per 32 columns
                 float gm[4];
@@ -291,21 +305,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                     }
                 }
             };
-            // the TMEM read of the next 32 columns is in flight while these 32 are selected
-            tmem_ld32(trow + 32, rb);
-            process(ra, 0);
-            tmem_ld_wait(rb);
-            tmem_ld32(trow + 64, ra);
-            process(rb, 32);
-            tmem_ld_wait(ra);
-            tmem_ld32(trow + 96, rb);
-            process(ra, 64);
-            tmem_ld_wait(rb);
-            // all of this warp's reads of the accumulator stage are done
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
-            process(rb, 96);
+            process(r0, 0);
+            process(r1, 32);
+            process(r2, 64);
+            process(r3, 96);
         }
         thr = drain_own(h, kk, myq, cnt);
         // ---- write this query's proposals
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 }  // namespace gmd_tc
@@ -367,7 +370,7 @@ extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctile
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan_tc: bad sizes");
     GMD_REQUIRE(D >= 1 && D < gmd_tc::TK && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
     using namespace gmd_tc;
-    const size_t fixed = 1024 + (size_t)TILE_B + 256 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8;
+    const size_t fixed = 1024 + (size_t)TILE_B + 512 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8;
     int nst = 4;
     while (nst > 2 && fixed + (size_t)nst * TILE_B > GMD_SMEM_LIMIT) --nst;
     const size_t smem = fixed + (size_t)nst * TILE_B;
