@@ -241,6 +241,8 @@ def engine_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         tdist.init_process_group("nccl", device_id=dev)
 
     def barrier():
