@@ -204,7 +204,7 @@ class KnnPipeline:
     # launches of the engine's own kernels in one run() (col_mean, prep x1/2, scan, refine, exact)
     @property
     def launches_per_run(self) -> int:
-        return 5 if self.same else 6
+        return 5 if (self.same and not self.tc) else 6
 
 
 def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, device=None,
