@@ -503,3 +503,21 @@ def test_tensor_core_scan_ill_conditioned_falls_back(cuda):
     idx, dist, info = engine.knn(x, None, k=6, form=_lib.FORM_TC, return_info=True)
     od, oi = oracle.knn(x, x, 6)
     assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
+def test_tensor_core_scan_through_the_c_pipeline_and_nonfinite(cuda):
+    """gmd_knn_host_f64 (host pointers, library-owned workspace) picks the tensor-core scan by
+    itself at this size; sampled rows against the oracle, all rows against the torch-driven path."""
+    x = synth.cfg_knn_rows(40_000, 10, 11)
+    assert _lib.lib().gmd_use_tc_scan(len(x), len(x), 16, _lib.L2, 10) == 1
+    idx, dist = engine.knn_host(x, None, 16, "euclidean")
+    idx2, dist2, info = engine.knn(x, None, k=16, return_info=True)
+    assert info["form"] == _lib.FORM_TC
+    assert np.array_equal(idx, idx2) and np.array_equal(dist, dist2)
+    rows = np.sort(np.random.default_rng(11).choice(len(x), 300, replace=False))
+    od, oi = oracle.knn(x[rows], x, 16)
+    assert_knn_parity(x[rows], x, idx[rows], dist[rows], oi, od)
+    bad = x[:3000].copy()
+    bad[17, 3] = np.nan
+    with pytest.raises(FloatingPointError):
+        engine.knn(bad, None, k=4, form=_lib.FORM_TC)
