@@ -98,23 +98,28 @@ struct ScanParams {
     float* cand_tau;
 };
 
-// Per-query running top-kk set: a binary MAX-heap of u64 keys in shared memory
-// (root = current kk-th best = the threshold).  On the rare path lane L maintains the heap
-// of the warp's query L by itself, so up to 32 inserts proceed in parallel with no
-// shuffles; the float64 re-rank orders the survivors anyway.  Empty slots hold
-// GMD_EMPTY_KEY (largest key), so a freshly initialised array is already a valid heap.
+// Per-query running top-kk set: a 4-ary MAX-heap of u64 keys in shared memory (root = current
+// kk-th best = the threshold).  Four children per node: the sift-down of a replaced root is
+// a chain of ceil(log4 kk) dependent shared-memory round trips instead of log2 kk (3 instead of
+// 6 at kk = 40), each one loading its four children back to back.  The owning lane / thread
+// maintains the heap by itself; the float64 re-rank orders the survivors anyway.  Empty slots
+// hold GMD_EMPTY_KEY (largest key), so a freshly initialised array is already a valid heap.
 __device__ __forceinline__ void heap_replace_root(uint64_t* h, int kk, uint64_t key) {
     int pos = 0;
     while (true) {
-        const int l = 2 * pos + 1;
-        if (l >= kk) break;
-        const uint64_t kl = h[l];
-        const uint64_t kr = (l + 1 < kk) ? h[l + 1] : 0ull;
-        const bool right = kr > kl;
-        const uint64_t kc = right ? kr : kl;
-        if (kc <= key) break;
-        h[pos] = kc;
-        pos = right ? l + 1 : l;
+        const int c = 4 * pos + 1;
+        if (c >= kk) break;
+        const uint64_t k0 = h[c];
+        const uint64_t k1 = (c + 1 < kk) ? h[c + 1] : 0ull;
+        const uint64_t k2 = (c + 2 < kk) ? h[c + 2] : 0ull;
+        const uint64_t k3 = (c + 3 < kk) ? h[c + 3] : 0ull;
+        const bool b01 = k1 > k0, b23 = k3 > k2;
+        const uint64_t m01 = b01 ? k1 : k0, m23 = b23 ? k3 : k2;
+        const bool hi = m23 > m01;
+        const uint64_t best = hi ? m23 : m01;
+        if (best <= key) break;
+        h[pos] = best;
+        pos = c + (hi ? 2 + (int)b23 : (int)b01);
     }
     h[pos] = key;
 }
