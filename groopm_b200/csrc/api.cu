@@ -214,14 +214,17 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     int rc;
     if ((rc = gmd_col_mean_f64(C, Nc, D, w.center, stream)) != GMD_OK) return rc;
     if (tc) {
-        if ((rc = gmd_prep_tc_f64(C, Nc, D, w.center, 1, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
-        if ((rc = gmd_prep_tc_f64(Q, Nq, D, w.center, 0, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK) return rc;
+        if ((rc = gmd_tc_norms_f64(C, Nc, D, w.center, w.stats, w.flags, stream)) != GMD_OK) return rc;
+        if (!same && (rc = gmd_tc_norms_f64(Q, Nq, D, w.center, w.stats + 2, w.flags, stream)) != GMD_OK) return rc;
+        if ((rc = gmd_prep_tc_f64(C, Nc, D, w.center, 1, w.stats, w.stats + 2, w.ctiles, stream)) != GMD_OK) return rc;
+        if ((rc = gmd_prep_tc_f64(Q, Nq, D, w.center, 0, w.stats, w.stats + 2, w.qtiles, stream)) != GMD_OK) return rc;
     } else {
         if ((rc = gmd_prep_f64(C, Nc, D, w.center, form, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
         if (!same && (rc = gmd_prep_f64(Q, Nq, D, w.center, form, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK)
             return rc;
     }
-    rc = tc ? gmd_scan_tc_f32(w.qtiles, Nq, w.ctiles, Nc, D, kk, 0, w.cand_idx, w.cand_val, w.cand_tau, stream) :
+    rc = tc ? gmd_scan_tc_f32(w.qtiles, Nq, w.ctiles, Nc, D, kk, 0, w.stats, w.stats + 2, w.cand_idx, w.cand_val,
+                              w.cand_tau, stream) :
          bmu ? gmd_scan_bmu_f32(w.qtiles, Nq, w.ctiles, Nc, D, 0, w.cand_idx, w.cand_val, w.cand_tau, stream)
              : gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,
                                  w.cand_tau, stream);

@@ -33,6 +33,18 @@ void gmd_set_error(const char* fmt, ...);
 
 static inline int64_t gmd_ntiles(int64_t n) { return (n + GMD_TW - 1) / GMD_TW; }
 
+// Tensor-core scan: the centred rows are multiplied by 2^e before the FP16 hi/lo split so that the
+// largest row norm of the query and candidate sets lands in (128, 256].  stats[0] / stats[2] hold
+// max ||x||^2 of the candidate / query set (0 when the sets are the same array).
+__host__ __device__ __forceinline__ int gmd_tc_exponent(float max_n2_a, float max_n2_b) {
+    const float m = fmaxf(max_n2_a, max_n2_b);
+    if (!(m > 0.0f) || !(m < 3.0e38f)) return 0;
+    int ex;
+    frexpf(sqrtf(m), &ex);          // sqrt(m) = f * 2^ex, f in [0.5, 1)
+    int e = 8 - ex;                 // sqrt(m) * 2^e in [128, 256)
+    return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+
 // order-preserving float -> uint32 (so that (value, index) packs into one u64 key)
 __device__ __forceinline__ uint32_t gmd_flip(float v) {
     uint32_t b = __float_as_uint(v);

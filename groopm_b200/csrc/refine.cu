@@ -118,12 +118,14 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
             const double e2 = (2.0 * D + 8.0) * U32 * nn * nn;
             lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
         } else if (form == GMD_FORM_TC) {
-            // 3 x TF32 dot product: representation (3 x 2^-22) and accumulation error measured at
-            // 2^-20.9 |q||c| (tools/tc_probe.cu); bounded here by 2^-18 |q||c| <= 2^-20 nn^2, doubled
-            // by the factor -2, plus the norm column (hi + lo: 2^-22 ||c||^2) and the FP32 roundings of the
-            // write-out: 64 x 2^-24 nn^2 in all
-            const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
-            const double e2 = 64.0 * U32 * nn * nn;
+            // 3 x FP16 dot product of rows scaled by 2^e: representation (3 x 2^-22) and accumulation
+            // error measured at 2^-21.9 |q||c| (tools/tc_probe16.cu); bounded here by 2^-18 |q||c| <=
+            // 2^-20 nn^2, doubled by the factor -2, plus the norm column (hi + lo: 2^-22 ||c||^2) and the
+            // FP32 roundings of the write-out: 64 x 2^-24 nn^2 in all.  FP16 subnormals add an absolute
+            // 2^-25 per element in scaled units: 2^-24 sqrt(D) nn 2^-e on the value ranked by.
+            const double nn = (sqrt(n2) + sqrt((double)fmaxf(stats[0], stats[2]))) * 1.000001;
+            const double floor_term = ldexp(sqrt((double)D) * nn, -24 - gmd_tc_exponent(stats[0], stats[2]));
+            const double e2 = 64.0 * U32 * nn * nn + floor_term;
             lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
         } else if (form == GMD_FORM_DIRECT_L2) {
             const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;

@@ -1,29 +1,33 @@
-// Tensor-core variant of the fused distance + top-k scan (expanded form, D <= 32).
+// Tensor-core variant of the fused distance + top-k scan (expanded form, D <= 31).
 //
 // The dot products q.c of a 128-query x 128-candidate tile are one K = 32 contraction on the
-// 5th-generation tensor cores: tcgen05.mma kind::tf32, operands K-major SWIZZLE_128B images in
-// shared memory, FP32 accumulator in tensor memory.  TF32 alone (10-bit mantissa) is far too
-// coarse for a neighbour search, so every FP32 value is split v = hi + lo (both TF32) and the
-// contraction is issued three times: hi.hi + hi.lo + lo.hi.  Measured against float64
-// (tools/tc_probe.cu): |error| <= 2^-20.9 |q||c|, i.e. FP32-class, inside the certificate's
-// bound (refine.cu, GMD_FORM_TC).
+// 5th-generation tensor cores: tcgen05.mma kind::f16 (FP16 operands, FP32 accumulation in
+// tensor memory), operands K-major SWIZZLE_64B images in shared memory.  One FP16 (11-bit
+// significand) is far too coarse for a neighbour search, so every centred FP32 value, scaled by
+// a power of two that brings the largest row norm into (128, 256], is split v = hi + lo (both
+// FP16) and the contraction is issued three times: hi.hi + hi.lo + lo.hi.  Measured against
+// float64 (tools/tc_probe16.cu): |error| <= 2^-21.9 |q||c|, i.e. FP32-class, inside the
+// certificate's bound (refine.cu, GMD_FORM_TC).  The same split with TF32 operands
+// (tools/tc_probe.cu, 2^-20.9) needs twice the tensor time and twice the bytes; it was the
+// first version of this kernel.
 //
-// Roles (192 threads): warp 0 lane 0 streams candidate tiles HBM -> shared memory with bulk
-// async copies (mbarrier ring); warp 1 lane 0 issues the MMAs (12 per tile) into one of two
-// 128-column accumulator stages in tensor memory and commits completion to mbarriers; warps
-// 2..5 are the selection warps: thread r owns query r of the CTA = TMEM lane r, reads its 128
-// accumulators with tcgen05.ld (32 columns at a time), forms  ||c||^2 - 2 q.c , and keeps
-// the query's top-kk heap in shared memory all by itself (no queues, no atomics: a thread
-// sees every candidate of its query, in ascending index order).
-//
-// The norm rides in the contraction: column D of a QUERY image holds 1, column D of a
-// CANDIDATE image holds -||c||^2 / 2, so the accumulator is  u = q.c - ||c||^2/2 = -s/2  with
+// The norm rides in the contraction: column D of a QUERY image holds 8, column D of a
+// CANDIDATE image holds -||c||^2 / 16, so the accumulator is  u = q.c - ||c||^2/2 = -s/2  with
 // s = ||c||^2 - 2 q.c the value the FP32 scan ranks by; selection maximises u directly (no
 // per-pair FMA, no norm loads) and converts to s = -2u (exact) only for the few values it keeps.
 //
-// HBM tile format ("TC tile", 128 profiles): [hi image 16 KB][lo image 16 KB][||x||^2 128 f32]
-// [pad to 33 KB], images already in the swizzled shared-memory layout so that one bulk copy
-// per tile is all the producer does.  Query and candidate tiles differ in column D only.
+// Roles (192 threads): warp 0 lane 0 streams candidate tiles HBM -> shared memory with bulk
+// async copies (mbarrier ring); warp 1 lane 0 issues the MMAs (6 per tile) into one of the
+// 128-column accumulator stages in tensor memory and commits completion to an mbarrier; warps
+// 2..5 are the selection warps: thread r owns query r of the CTA = TMEM lane r, reads its 128
+// accumulators with tcgen05.ld, and keeps the query's top-kk heap in shared memory all by
+// itself (no atomics: a thread sees every candidate of its query, in ascending index order).
+//
+// HBM tile format ("TC tile", 128 profiles): [hi image 8 KB][lo image 8 KB][scaled ||x||^2 128 f32]
+// [pad to 17 KB], images already in the swizzled shared-memory layout (8-row x 64 B atoms,
+// 16-byte chunk c of row r at c ^ ((r >> 1) & 3)) so that one bulk copy per tile is all the
+// producer does.  Query and candidate tiles differ in column D only.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "scan_impl.cuh"
@@ -33,26 +37,23 @@ using namespace gmd_scan;
 
 constexpr int TM = 128;                  // profiles per TC tile (UMMA M and N)
 constexpr int TK = 32;                   // contraction length (padded D)
-constexpr int IMG_B = TM * TK * 4;       // one image: 16 KB
+constexpr int IMG_B = TM * TK * 2;       // one FP16 image: 8 KB
 constexpr int TILE_B = 2 * IMG_B + 1024; // hi, lo, norms (512 B used)
+constexpr float QCOL = 8.0f;             // column D of a query row; a candidate row holds -||c||^2 / (2 QCOL)
+constexpr float PAD_COL = -60000.0f;     // column D of a padding candidate: u = -480000, below any real value
 constexpr int NTHREADS = 192;
 
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    // K-major SWIZZLE_128B: LBO 1, SBO 1024 B (8 rows x 128 B), descriptor version 1 (sm_100)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    // K-major SWIZZLE_64B: LBO 1, SBO 512 B (8 rows x 64 B), descriptor version 1 (sm_100), layout type 4
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem),
         "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
         : "memory");
@@ -85,53 +86,79 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 // ------------------------------------------------------------------ staging: float64 rows -> TC tiles
+// pass 1: largest centred row norm of a profile set (fixes the power-of-two scale)
+__global__ void __launch_bounds__(256) tc_norms_kernel(const double* __restrict__ X, long long N, int D,
+                                                       const double* __restrict__ center, float* __restrict__ stats,
+                                                       int* __restrict__ flags) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float n2f = 0.0f, n1f = 0.0f;
+    bool bad = false;
+    if (row < N) {
+        double n2 = 0.0, n1 = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double x = X[(size_t)row * D + k];
+            bad |= !isfinite(x);
+            const double v = (double)(float)(x - (center ? center[k] : 0.0));
+            n2 += v * v;
+            n1 += fabs(v);
+        }
+        n2f = __double2float_ru(n2);
+        n1f = __double2float_ru(n1);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n2f = fmaxf(n2f, __shfl_xor_sync(0xFFFFFFFFu, n2f, o));
+        n1f = fmaxf(n1f, __shfl_xor_sync(0xFFFFFFFFu, n1f, o));
+    }
+    if ((threadIdx.x & 31) == 0 && isfinite(n2f)) {
+        atomicMax(reinterpret_cast<int*>(stats), __float_as_int(n2f));
+        atomicMax(reinterpret_cast<int*>(stats) + 1, __float_as_int(n1f));
+    }
+    if (bad) atomicExch(flags, 1);
+}
+
+// pass 2: scaled FP16 hi / lo images.  role 0: query tile (column D = QCOL), role 1: candidate tile
+// (column D = -||x||^2 / (2 QCOL), in scaled units).  stats_c / stats_q: max ||x||^2 of the two sets.
 __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long N, int D,
                                                       const double* __restrict__ center, int role,
-                                                      unsigned char* __restrict__ tiles, float* __restrict__ stats,
-                                                      int* __restrict__ flags) {
-    // role 0: query tile (column D = 1), role 1: candidate tile (column D = -||x||^2 / 2)
+                                                      const float* __restrict__ stats_c, const float* __restrict__ stats_q,
+                                                      unsigned char* __restrict__ tiles) {
     __shared__ float s_n2[TM];
+    const float scale = ldexpf(1.0f, gmd_tc_exponent(stats_c[0], stats_q[0]));
+    const long long t = blockIdx.x, row0 = t * TM;
     if (threadIdx.x < TM) {
-        const long long row = (long long)blockIdx.x * TM + threadIdx.x;
-        double n2 = 0.0, n1 = 0.0;
+        const long long row = row0 + threadIdx.x;
+        double n2 = 0.0;
         if (row < N) {
             for (int k = 0; k < D; ++k) {
-                const double v = (double)(float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0));
+                const double v = (double)((float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0)) * scale);
                 n2 += v * v;
-                n1 += fabs(v);
             }
         }
-        s_n2[threadIdx.x] = row < N ? (float)n2 : GMD_PAD_AUX;
-        if (row < N && stats) {
-            atomicMax(reinterpret_cast<int*>(stats), __float_as_int(__double2float_ru(n2)));
-            atomicMax(reinterpret_cast<int*>(stats) + 1, __float_as_int(__double2float_ru(n1)));
-        }
+        s_n2[threadIdx.x] = (float)n2;
     }
     __syncthreads();
-    const long long t = blockIdx.x, row0 = t * TM;
-    float* hi = reinterpret_cast<float*>(tiles + (size_t)t * TILE_B);
-    float* lo = hi + IMG_B / 4;
-    float* nrm = lo + IMG_B / 4;
-    bool bad = false;
+    __half* hi = reinterpret_cast<__half*>(tiles + (size_t)t * TILE_B);
+    __half* lo = hi + IMG_B / 2;
+    float* nrm = reinterpret_cast<float*>(tiles + (size_t)t * TILE_B + 2 * IMG_B);
     for (int e = threadIdx.x; e < TM * TK; e += blockDim.x) {
         const int r = e / TK, k = e - r * TK;
         const long long row = row0 + r;
         float v = 0.0f;
-        if (row < N && k < D) {
-            const double x = X[(size_t)row * D + k];
-            bad |= !isfinite(x);
-            v = (float)(x - (center ? center[k] : 0.0));
+        if (row < N) {
+            if (k < D)
+                v = (float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0)) * scale;   // exact: power of two
+            else if (k == D)
+                v = role == 0 ? QCOL : -s_n2[r] / (2.0f * QCOL);
         } else if (k == D) {
-            v = role == 0 ? 1.0f : -0.5f * s_n2[r];
+            v = role == 0 ? QCOL : PAD_COL;
         }
-        const float h = tf32_rn(v);
-        // shared-memory image: 8-row groups of 1024 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7)
-        const int off = ((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4) >> 2;
+        const __half h = __float2half_rn(v);
+        // shared-memory image: 8-row groups of 512 B, 16-byte chunk c (8 halves) of row r at c ^ ((r >> 1) & 3)
+        const int off = ((r >> 3) * 512 + (r & 7) * 64 + ((((k >> 3) ^ ((r >> 1) & 3)) & 3) << 4) + (k & 7) * 2) >> 1;
         hi[off] = h;
-        lo[off] = tf32_rn(v - h);
+        lo[off] = __float2half_rn(v - __half2float(h));
     }
-    if (bad) atomicExch(flags, 1);
-    if (threadIdx.x < TM) nrm[threadIdx.x] = s_n2[threadIdx.x];
+    if (threadIdx.x < TM) nrm[threadIdx.x] = (row0 + threadIdx.x) < N ? s_n2[threadIdx.x] : 0.0f;
 }
 
 // ------------------------------------------------------------------ the scan
@@ -157,6 +184,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                                                               const unsigned char* __restrict__ ctiles,
                                                               long long Nq, long long Nc, int ntiles_c, int kk,
                                                               long long c_index_offset, int dbg,
+                                                              const float* __restrict__ stats_c,
+                                                              const float* __restrict__ stats_q,
                                                               uint32_t* __restrict__ cand_idx,
                                                               float* __restrict__ cand_val,
                                                               float* __restrict__ cand_tau) {
@@ -219,7 +248,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         // ---- MMA issuer
         if (lane == 0) {
             mbar_wait(qbar, 0);
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            // FP32 accumulator, FP16 A and B (format 0), both K-major, N = M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             // descriptors differ only in the 16-byte-granular start address: build them once and add
             const uint64_t a_hi = umma_desc(smem_u32(Aimg)), a_lo = a_hi + (IMG_B >> 4);
             const uint64_t b_base = umma_desc(smem_u32(Bst));
@@ -230,12 +260,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint64_t b_hi = b_base + (uint64_t)s * (TILE_B >> 4), b_lo = b_hi + (IMG_B >> 4);
                 const uint32_t acc = tmem + (uint32_t)(s * TM);
+                // hi.hi + hi.lo + lo.hi, K = 16 halves (32 bytes) per MMA
 #pragma unroll
                 for (int p = 0; p < 3; ++p)
 #pragma unroll
-                    for (int k = 0; k < TK / 8; ++k)
-                        umma_tf32(acc, (p == 2 ? a_lo : a_hi) + 2 * k, (p == 1 ? b_lo : b_hi) + 2 * k, idesc,
-                                  (p | k) ? 1u : 0u);
+                    for (int k = 0; k < TK / 16; ++k)
+                        umma_f16(acc, (p == 2 ? a_lo : a_hi) + 2 * k, (p == 1 ? b_lo : b_hi) + 2 * k, idesc,
+                                 (p | k) ? 1u : 0u);
                 umma_commit(&done[s]);   // one commit: accumulator stage written, shared-memory stage readable again
             }
         }
@@ -315,6 +346,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         // ---- write this query's proposals
         const long long q = qt * TM + row;
         if (q < Nq) {
+            // back to the caller's units: everything above ran on rows scaled by 2^e
+            const float unscale = ldexpf(1.0f, -2 * gmd_tc_exponent(stats_c[0], stats_q[0]));
             const float qnv = reinterpret_cast<const float*>(Aimg + 2 * IMG_B)[row];
             const size_t ob = (size_t)q * kk;
             for (int x = 0; x < kk; ++x) {
@@ -324,7 +357,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                 uint32_t oi = GMD_EMPTY_IDX;
                 if (key != GMD_EMPTY_KEY && (long long)li < Nc) {
                     oi = li + (uint32_t)c_index_offset;
-                    vv = fmaxf(vv + qnv, 0.0f);
+                    vv = fmaxf(vv + qnv, 0.0f) * unscale;
                 } else {
                     vv = __int_as_float(0x7f800000);
                 }
@@ -332,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                 cand_val[ob + x] = vv;
             }
             float tau = thr;
-            if (h[0] != GMD_EMPTY_KEY) tau = fmaxf(tau + qnv, 0.0f);
+            if (h[0] != GMD_EMPTY_KEY) tau = fmaxf(tau + qnv, 0.0f) * unscale;
             cand_tau[q] = tau;
         }
     }
@@ -353,21 +386,30 @@ extern "C" size_t gmd_tc_tiles_bytes(int64_t N) {
     return (size_t)((N + gmd_tc::TM - 1) / gmd_tc::TM) * gmd_tc::TILE_B;
 }
 
-extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role, void* tiles,
-                               float* stats, int32_t* flags, void* stream) {
-    GMD_REQUIRE(X && tiles && flags && N > 0 && D >= 1 && D < gmd_tc::TK && (role == 0 || role == 1), GMD_ERR_BAD_ARG,
-                "prep_tc: bad arguments");
+extern "C" int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double* center, float* stats, int32_t* flags,
+                                void* stream) {
+    GMD_REQUIRE(X && stats && flags && N > 0 && D >= 1 && D < gmd_tc::TK, GMD_ERR_BAD_ARG, "tc_norms: bad arguments");
+    gmd_tc::tc_norms_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, N, D, center, stats, flags);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role,
+                               const float* stats_c, const float* stats_q, void* tiles, void* stream) {
+    GMD_REQUIRE(X && tiles && stats_c && stats_q && N > 0 && D >= 1 && D < gmd_tc::TK && (role == 0 || role == 1),
+                GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
     const unsigned grid = (unsigned)((N + gmd_tc::TM - 1) / gmd_tc::TM);
-    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, center, role, (unsigned char*)tiles, stats,
-                                                                  flags);
+    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, center, role, stats_c, stats_q,
+                                                                  (unsigned char*)tiles);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }
 
 extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
-                               int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
-                               void* stream) {
-    GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG, "scan_tc: null pointer");
+                               int64_t c_index_offset, const float* stats_c, const float* stats_q, uint32_t* cand_idx,
+                               float* cand_val, float* cand_tau, void* stream) {
+    GMD_REQUIRE(qtiles && ctiles && stats_c && stats_q && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG,
+                "scan_tc: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan_tc: bad sizes");
     GMD_REQUIRE(D >= 1 && D < gmd_tc::TK && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
     using namespace gmd_tc;
@@ -382,7 +424,7 @@ extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctile
         GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>((const unsigned char*)qtiles, (const unsigned char*)ctiles,
                                                            Nq, Nc, (int)((Nc + TM - 1) / TM), kk, c_index_offset, dbg,
-                                                           cand_idx, cand_val, cand_tau);
+                                                           stats_c, stats_q, cand_idx, cand_val, cand_tau);
         return GMD_OK;
     };
     const int rc = nst == 4 ? launch(scan_tc_kernel<4>) : nst == 3 ? launch(scan_tc_kernel<3>) : launch(scan_tc_kernel<2>);

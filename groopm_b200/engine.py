@@ -137,16 +137,27 @@ class KnnPipeline:
 
     def prep_candidates(self, c: torch.Tensor):
         if self.tc:
-            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(c), self.nc, self.d, _ptr(self.center), 1, _ptr(self.ctiles),
-                                                _ptr(self.stats), _ptr(self.flags), _stream_ptr()))
+            # pass 1 of the tensor-core staging: the largest centred row norm fixes the power-of-two scale
+            _lib.check(self.lib.gmd_tc_norms_f64(_ptr(c), self.nc, self.d, _ptr(self.center), _ptr(self.stats),
+                                                 _ptr(self.flags), _stream_ptr()))
+            self._tc_c = c
             return
         _lib.check(self.lib.gmd_prep_f64(_ptr(c), self.nc, self.d, _ptr(self.center), self.form,
                                          _ptr(self.ctiles), _ptr(self.stats), _ptr(self.flags), _stream_ptr()))
 
     def prep_queries(self, q: torch.Tensor):
         if self.tc:
-            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(q), self.nq, self.d, _ptr(self.center), 0, _ptr(self.qtiles),
-                                                _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))
+            sq = _ptr(self.stats) + 8
+            if not self.same:
+                _lib.check(self.lib.gmd_tc_norms_f64(_ptr(q), self.nq, self.d, _ptr(self.center), sq, _ptr(self.flags),
+                                                     _stream_ptr()))
+            # pass 2 for both roles, now that both sets' norms are known
+            c = self._tc_c
+            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(c), self.nc, self.d, _ptr(self.center), 1, _ptr(self.stats), sq,
+                                                _ptr(self.ctiles), _stream_ptr()))
+            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(q), self.nq, self.d, _ptr(self.center), 0, _ptr(self.stats), sq,
+                                                _ptr(self.qtiles), _stream_ptr()))
+            self._tc_c = None
             return
         if self.same:
             return
@@ -156,8 +167,8 @@ class KnnPipeline:
     def scan(self):
         if self.tc:
             _lib.check(self.lib.gmd_scan_tc_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, self.kk,
-                                                0, _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau),
-                                                _stream_ptr()))
+                                                0, _ptr(self.stats), _ptr(self.stats) + 8, _ptr(self.cand_idx),
+                                                _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))
             return
         if self.bmu:
             _lib.check(self.lib.gmd_scan_bmu_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, 0,
@@ -204,7 +215,9 @@ class KnnPipeline:
     # launches of the engine's own kernels in one run() (col_mean, prep x1/2, scan, refine, exact)
     @property
     def launches_per_run(self) -> int:
-        return 5 if (self.same and not self.tc) else 6
+        if self.tc:
+            return 7 if self.same else 8      # col_mean, norms x1/2, prep x2, scan, refine, exact
+        return 5 if self.same else 6
 
 
 def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, device=None,

@@ -57,7 +57,7 @@ enum { GMD_L2 = 0, GMD_L1 = 1 };
  *   0 expanded  ||c||^2 - 2 q.c   (L2 only; D FFMA per pair)
  *   1 direct L2 sum (q-c)^2       (2D instr per pair; for ill-conditioned / tiny D)
  *   2 direct L1 sum |q-c|         (2D instr per pair)
- *   3 tensor cores: ||c||^2 - 2 q.c with q.c as a 3 x TF32 (hi/lo split) tcgen05 contraction
+ *   3 tensor cores: ||c||^2 - 2 q.c with q.c as a 3 x FP16 (hi/lo split) tcgen05 contraction
  *     (L2 only, D <= 32; its own tile format, see gmd_scan_tc_f32)                    */
 enum { GMD_FORM_EXPANDED = 0, GMD_FORM_DIRECT_L2 = 1, GMD_FORM_DIRECT_L1 = 2, GMD_FORM_TC = 3, GMD_FORM_AUTO = -1 };
 
@@ -128,23 +128,28 @@ GMD_API int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctile
                      void* stream);
 
 /* Tensor-core scan (form GMD_FORM_TC): the dot products of a 128-query x 128-candidate tile
- * are one tcgen05.mma kind::tf32 contraction, every FP32 value split hi + lo and the
- * contraction issued three times (hi.hi + hi.lo + lo.hi: FP32-class accuracy, measured
- * 2^-20.9 |q||c|); selection threads read the accumulators from tensor memory and keep the
- * per-query heaps.  Its operands are "TC tiles" (128 profiles: hi image, lo image, norms;
- * gmd_tc_tiles_bytes / gmd_prep_tc_f64).  Outputs as gmd_scan_topk_f32 with nsplit = 1, to be
- * finished by gmd_refine_topk_f64(form = GMD_FORM_TC) / gmd_exact_rows_f64.
- * Query and candidate tiles differ (column D carries 1 resp. -||c||^2/2, so the norm rides in
- * the contraction): the same rows must be staged once per role.
- * gmd_tc_supported(k, metric, D): Euclidean, 2 <= k <= 64, 4 <= D <= 31.                  */
+ * are one tcgen05.mma kind::f16 contraction (FP32 accumulation in tensor memory), every centred
+ * FP32 value -- scaled by a power of two that brings the largest row norm into (128, 256] --
+ * split hi + lo (both FP16) and the contraction issued three times (hi.hi + hi.lo + lo.hi:
+ * FP32-class accuracy, measured 2^-21.9 |q||c|); the norm rides in the contraction (column D);
+ * selection threads read the accumulators from tensor memory and keep the per-query heaps.
+ * Operands are "TC tiles" (128 profiles: hi image, lo image, norms), staged per ROLE
+ * (0 queries, 1 candidates) in two passes: gmd_tc_norms_f64 on each set (stats[0] <- max
+ * ||x - center||^2, zero the slot first; flags[0] <- 1 on NaN/Inf), then gmd_prep_tc_f64 on each
+ * set with BOTH sets' stats slots (the same slot twice when queries == candidates).
+ * Outputs as gmd_scan_topk_f32 with nsplit = 1, in the caller's units, to be finished by
+ * gmd_refine_topk_f64(form = GMD_FORM_TC, stats = candidate slot, stats + 2 = query slot) /
+ * gmd_exact_rows_f64.  gmd_tc_supported(k, metric, D): Euclidean, 2 <= k <= 64, 4 <= D <= 31. */
 GMD_API int gmd_tc_supported(int k, int metric, int D);
 GMD_API int gmd_use_tc_scan(int64_t Nq, int64_t Nc, int k, int metric, int D);  /* the size policy of gmd_knn_f64 */
 GMD_API size_t gmd_tc_tiles_bytes(int64_t N);
-GMD_API int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role /* 0 queries, 1 candidates */,
-                    void* tiles, float* stats, int32_t* flags, void* stream);
+GMD_API int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double* center, float* stats, int32_t* flags,
+                     void* stream);
+GMD_API int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role,
+                    const float* stats_c, const float* stats_q, void* tiles, void* stream);
 GMD_API int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
-                    int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
-                    void* stream);
+                    int64_t c_index_offset, const float* stats_c, const float* stats_q, uint32_t* cand_idx,
+                    float* cand_val, float* cand_tau, void* stream);
 
 /* float64 re-rank of the proposed candidates from the ORIGINAL rows, lowest-index tie
  * rule, plus the per-row certificate; uncertified rows are appended to fail_rows
