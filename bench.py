@@ -147,7 +147,7 @@ def secondary_workloads(engine, synth, torch, peak):
         tf = 2.0 * qd.shape[1] * pairs / (scan_ms * 1e-3) / 1e12
         pk = peak if metric == "euclidean" else peak / 2       # L1 has no FMA form: FADD rate
         rec = {"workload": name, "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "scan_ms": scan_ms,
-               "scan_kernel": "tensor-core 3xTF32" if pipe.form == 3 else ("k=1 BMU scan" if pipe.bmu else "FP32 scan"),
+               "scan_kernel": "tensor-core 3xFP16" if pipe.form == 3 else ("k=1 BMU scan" if pipe.bmu else "FP32 scan"),
                "scan_tflops_algorithmic": tf, "exact_rows": pipe.exact_row_count()}
         # fraction of the FP32 CUDA-core peak the ALGORITHMIC flops amount to (> 1 is possible on the tensor path)
         rec["vs_fp32_pipe_peak"] = tf / pk
@@ -349,20 +349,20 @@ def engine_arm(args):
                 traffic = None
         tc = pipe.form == 3                                    # GMD_FORM_TC: the tensor-core scan
         if tc:
-            # executed tensor work: K padded to 32, three TF32 passes (hi.hi + hi.lo + lo.hi)
+            # executed tensor work: K padded to 32, three FP16 passes (hi.hi + hi.lo + lo.hi)
             executed = 2.0 * 32 * 3 * float(n_local) * float(n) / (scan_avg_ms * 1e-3) / 1e12
-            tf32_peak, tf32_src = None, "MEASURED_PEAKS.json absent: nominal 1130 TFLOP/s dense TF32"
+            tc_peak, tc_src = 1590.0, "MEASURED_PEAKS.json absent: fallback 1590 TFLOP/s (B200_PROFILING.md)"
             try:
                 mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-                tf32_peak = float(mp["bf16_tflops"]) / 2.0
-                tf32_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate), burst figure"
+                tc_peak = float(mp["bf16_tflops"])
+                tc_src = "MEASURED_PEAKS.json bf16_tflops (FP16 tensor rate = bf16 rate), burst figure"
             except (OSError, ValueError, KeyError):
-                tf32_peak = 1130.0
+                pass
             roofline = {"bound": "tensor", "kernel": "gmd_tc::scan_tc_kernel", "achieved": achieved,
-                        "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "peak_source": tf32_src,
+                        "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "peak_source": tc_src,
                         "note": "achieved = ALGORITHMIC flops (2*D per pair); the kernel executes 2*32*3 per pair "
-                                "(K padded to 32, 3 x TF32 split for FP32-class accuracy)",
-                        "executed_tflops": executed, "frac_executed": executed / tf32_peak,
+                                "(K padded to 32, 3 x FP16 hi/lo split for FP32-class accuracy)",
+                        "executed_tflops": executed, "frac_executed": executed / tc_peak,
                         "fp32_pipe_peak": peak_probe, "vs_fp32_pipe_peak": achieved / peak_probe,
                         "scan_ms_per_launch": scan_avg_ms_max, "flop_per_launch": launch_flop, "traffic": traffic}
         else:
@@ -376,13 +376,13 @@ def engine_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "tf32x3" if tc else "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16x3" if tc else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "contigs": n, "dim": d, "k": k, "metric": metric,
                        "parallelism": f"query rows block-sharded over {world} GPU(s); one NCCL all-gather of the "
                                       f"float64 rows per step" if world > 1 else "single GPU",
                        "l2": "inputs exceed L2 (float64 profiles %d MB, FP32 tiles %d MB)" %
                              (n * d * 8 // 2**20, pipe.ctiles.numel() * 4 // 2**20),
-                       "arithmetic": ("tcgen05 3xTF32 (FP32-class) " if pipe.form == 3 else "FP32 ") +
+                       "arithmetic": ("tcgen05 3xFP16 hi/lo split (FP32-class) " if pipe.form == 3 else "FP32 ") +
                                      "fused distance+top-k scan proposes k+8 candidates; float64 re-rank "
                                      "and certificate make the result exact",
                        "form": pipe.form, "kk": pipe.kk, "nsplit": pipe.nsplit, "exact_rows_last_step": exact_rows},
