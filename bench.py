@@ -68,6 +68,18 @@ def _ref_chunk(args):
 
 _REF_X = None
 _REF_ROWS = None
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's original stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
 
 
 def reference_arm(args):
@@ -241,8 +253,12 @@ def engine_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its own lines (e.g. "NCCL version ...") on file descriptor 1: point that at
+        # stderr for the whole run and keep the real stdout for the ONE JSON line
+        sys.stdout.flush()
+        global _REAL_STDOUT
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         tdist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -397,7 +413,7 @@ def engine_arm(args):
             line["secondary"] = secondary_workloads(engine, synth, torch, peak_probe)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(x, k, metric)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         tdist.destroy_process_group()
     return 0
