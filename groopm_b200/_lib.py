@@ -36,13 +36,14 @@ SIGNATURES = {
     "gmd_scan_bmu_f32": (_int, [_vp, _i64, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
     "gmd_tc_supported": (_int, [_int, _int, _int]),
     "gmd_use_tc_scan": (_int, [_i64, _i64, _int, _int, _int]),
-    "gmd_tc_tiles_bytes": (_sz, [_i64]),
+    "gmd_tc_tiles_bytes": (_sz, [_i64, _int]),
     "gmd_tc_norms_f64": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "gmd_prep_tc_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp]),
     "gmd_scan_tc_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_refine_topk_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gmd_exact_rows_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_exact_workspace_bytes": (_sz, [_i64]),
+    "gmd_exact_rows_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gmd_knn_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "gmd_knn_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gmd_cdist_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp]),

@@ -150,6 +150,8 @@ struct Workspace {
     float* cand_val;
     float* cand_tau;
     int32_t* fail_rows;
+    void* exact_ws;     // hit lists of the batched exact pass
+    size_t exact_bytes;
     size_t bytes;
 };
 
@@ -167,12 +169,14 @@ Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, b
     w.center = (double*)take(sizeof(double) * GMD_MAX_D);
     w.stats = (float*)take(sizeof(float) * 4);
     w.flags = (int32_t*)take(sizeof(int32_t) * 4);
-    w.ctiles = (float*)take(tc ? gmd_tc_tiles_bytes(Nc) : gmd_tiles_bytes(Nc, D));
-    w.qtiles = (same && !tc) ? w.ctiles : (float*)take(tc ? gmd_tc_tiles_bytes(Nq) : gmd_tiles_bytes(Nq, D));
+    w.ctiles = (float*)take(tc ? gmd_tc_tiles_bytes(Nc, D) : gmd_tiles_bytes(Nc, D));
+    w.qtiles = (same && !tc) ? w.ctiles : (float*)take(tc ? gmd_tc_tiles_bytes(Nq, D) : gmd_tiles_bytes(Nq, D));
     w.cand_idx = (uint32_t*)take((size_t)Nq * nsplit * kk * sizeof(uint32_t));
     w.cand_val = (float*)take((size_t)Nq * nsplit * kk * sizeof(float));
     w.cand_tau = (float*)take((size_t)Nq * nsplit * sizeof(float));
     w.fail_rows = (int32_t*)take((size_t)Nq * sizeof(int32_t));
+    w.exact_bytes = gmd_exact_workspace_bytes(Nq);
+    w.exact_ws = take(w.exact_bytes);
     w.bytes = off;
     return w;
 }
@@ -200,7 +204,7 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
                 "knn: form %d does not compute metric %d", form, metric);
     const bool tc = form == GMD_FORM_TC;
     GMD_REQUIRE(!tc || gmd_tc_supported(k, metric, D), GMD_ERR_UNSUPPORTED,
-                "knn: the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 31");
+                "knn: the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 136");
     const bool bmu = form == GMD_FORM_EXPANDED && gmd_use_bmu_scan(k, metric, D);
     const int kk = bmu ? gmd_scan::BMU_KK : gmd_pick_kk(k);
     const int nsplit = (bmu || tc) ? 1 : gmd_pick_nsplit(Nq, Nc, D, kk);
@@ -232,8 +236,8 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     if ((rc = gmd_refine_topk_f64(Q, Nq, C, Nc, D, w.center, k, kk, nsplit, metric, form, w.cand_idx, w.cand_val,
                                   w.cand_tau, w.stats, out_idx, out_dist, w.flags + 1, w.fail_rows, stream)) != GMD_OK)
         return rc;
-    if ((rc = gmd_exact_rows_f64(Q, Nq, C, Nc, D, k, metric, w.flags + 1, w.fail_rows, out_idx, out_dist, stream)) !=
-        GMD_OK)
+    if ((rc = gmd_exact_rows_f64(Q, Nq, C, Nc, D, k, metric, w.flags + 1, w.fail_rows, out_idx, out_dist, w.exact_ws,
+                                 w.exact_bytes, stream)) != GMD_OK)
         return rc;
     if (info) {
         // info[0] = rows finished by the exact scan, info[1] = non-finite input seen

@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include <math_constants.h>
 
+#include <algorithm>
+
 namespace {
 
 constexpr double U32 = 5.9604644775390625e-08;  // 2^-24
@@ -122,10 +124,12 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
             // error measured at 2^-21.9 |q||c| (tools/tc_probe16.cu); bounded here by 2^-18 |q||c| <=
             // 2^-20 nn^2, doubled by the factor -2, plus the norm column (hi + lo: 2^-22 ||c||^2) and the
             // FP32 roundings of the write-out: 64 x 2^-24 nn^2 in all.  FP16 subnormals add an absolute
-            // 2^-25 per element in scaled units: 2^-24 sqrt(D) nn 2^-e on the value ranked by.
+            // 2^-25 per element in scaled units: 2^-24 sqrt(D) nn 2^-e on the value ranked by.  With
+            // nkb = ceil((D + 1) / 32) K blocks the accumulator takes 6 nkb partial sums: the bound
+            // scales with nkb.
             const double nn = (sqrt(n2) + sqrt((double)fmaxf(stats[0], stats[2]))) * 1.000001;
             const double floor_term = ldexp(sqrt((double)D) * nn, -24 - gmd_tc_exponent(stats[0], stats[2]));
-            const double e2 = 64.0 * U32 * nn * nn + floor_term;
+            const double e2 = 64.0 * ((D + 32) / 32) * U32 * nn * nn + floor_term;
             lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
         } else if (form == GMD_FORM_DIRECT_L2) {
             const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;
@@ -169,11 +173,131 @@ __device__ __forceinline__ KeyD block_min_key(KeyD v, KeyD* red) {
     return r;
 }
 
+// Batched form of the exact scan: one block per chunk of EXB_CH candidates (staged once, coalesced),
+// every rejected row visits it, EXB_RB rows at a time.  The re-ranked k-th distance of a row is an
+// upper bound on its true k-th distance, so only candidates within it are kept: they go to the row's
+// hit list in global memory, which exact_finish_kernel ranks.  The candidate set is read once per
+// launch instead of once per rejected row; rows whose list overflows (tie masses) and rows beyond
+// the workspace's capacity are left to exact_rows_kernel.
+constexpr int EXB_CH = 128;       // candidates per block
+constexpr int EXB_RB = 8;         // rejected rows per pass: 4 per thread
+constexpr int EXB_THREADS = 256;  // (candidate, half of the row group)
+constexpr int EXB_HC = 256;       // hit list capacity per row
+constexpr int EXB_FCAP = 4096;    // most rows taken by the batched pass
+
+__global__ void __launch_bounds__(EXB_THREADS) exact_batch_kernel(const double* __restrict__ Q,
+                                                                 const double* __restrict__ C, long long Nc, int D,
+                                                                 int k, int metric,
+                                                                 const int32_t* __restrict__ fail_count,
+                                                                 const int32_t* __restrict__ fail_rows, int fcap,
+                                                                 const double* __restrict__ out_dist,
+                                                                 int32_t* __restrict__ hit_cnt,
+                                                                 double* __restrict__ hit_d,
+                                                                 uint32_t* __restrict__ hit_i) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int nfail = min(*fail_count, fcap);
+    if (nfail == 0) return;
+    const int Dp = D | 1;                                  // odd row pitch: conflict-free column walks
+    double* cs = reinterpret_cast<double*>(sm_raw);        // [EXB_CH][Dp]
+    double* qs = cs + (size_t)EXB_CH * Dp;                 // [EXB_RB][D]
+    double* ubs = qs + (size_t)EXB_RB * D;                 // [EXB_RB]
+    const int tid = threadIdx.x;
+    const long long c0 = (long long)blockIdx.x * EXB_CH;
+    const int n = (int)min((long long)EXB_CH, Nc - c0);
+    const double* cg = C + (size_t)c0 * D;
+    for (int e = tid; e < n * D; e += EXB_THREADS) {
+        const int r = e / D;
+        cs[r * Dp + (e - r * D)] = cg[e];
+    }
+    const int c = tid & (EXB_CH - 1), rh = tid / EXB_CH;   // rows rh * 4 .. rh * 4 + 3 of the group
+    const double* cr = cs + (size_t)c * Dp;
+    const double* q0 = qs + (size_t)(rh * 4) * D;
+    for (int w0 = 0; w0 < nfail; w0 += EXB_RB) {
+        __syncthreads();
+        for (int e = tid; e < EXB_RB * D; e += EXB_THREADS) {
+            const int r = e / D, w = w0 + r;
+            qs[e] = w < nfail ? Q[(size_t)fail_rows[w] * D + (e - r * D)] : 0.0;
+        }
+        if (tid < EXB_RB) ubs[tid] = (w0 + tid) < nfail ? out_dist[(size_t)fail_rows[w0 + tid] * k + k - 1] : -1.0;
+        __syncthreads();
+        if (c >= n) continue;
+        // scipy's arithmetic (dist64), four rows side by side
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (metric == GMD_L2) {
+            for (int d = 0; d < D; ++d) {
+                const double v = cr[d];
+                const double t0 = __dsub_rn(q0[d], v), t1 = __dsub_rn(q0[D + d], v);
+                const double t2 = __dsub_rn(q0[2 * D + d], v), t3 = __dsub_rn(q0[3 * D + d], v);
+                s0 = __dadd_rn(s0, __dmul_rn(t0, t0));
+                s1 = __dadd_rn(s1, __dmul_rn(t1, t1));
+                s2 = __dadd_rn(s2, __dmul_rn(t2, t2));
+                s3 = __dadd_rn(s3, __dmul_rn(t3, t3));
+            }
+            s0 = sqrt(s0), s1 = sqrt(s1), s2 = sqrt(s2), s3 = sqrt(s3);
+        } else {
+            for (int d = 0; d < D; ++d) {
+                const double v = cr[d];
+                s0 = __dadd_rn(s0, fabs(__dsub_rn(q0[d], v)));
+                s1 = __dadd_rn(s1, fabs(__dsub_rn(q0[D + d], v)));
+                s2 = __dadd_rn(s2, fabs(__dsub_rn(q0[2 * D + d], v)));
+                s3 = __dadd_rn(s3, fabs(__dsub_rn(q0[3 * D + d], v)));
+            }
+        }
+        const double sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int w = w0 + rh * 4 + j;
+            if (w < nfail && sv[j] <= ubs[rh * 4 + j]) {
+                const int slot = atomicAdd(&hit_cnt[w], 1);
+                if (slot < EXB_HC) {
+                    hit_d[(size_t)w * EXB_HC + slot] = sv[j];
+                    hit_i[(size_t)w * EXB_HC + slot] = (uint32_t)(c0 + c);
+                }
+            }
+        }
+    }
+}
+
+// ranks a row's hit list by (distance, index) and writes its k best
+__global__ void __launch_bounds__(EXB_HC) exact_finish_kernel(int k, const int32_t* __restrict__ fail_count,
+                                                             const int32_t* __restrict__ fail_rows, int fcap,
+                                                             const int32_t* __restrict__ hit_cnt,
+                                                             const double* __restrict__ hit_d,
+                                                             const uint32_t* __restrict__ hit_i,
+                                                             int32_t* __restrict__ out_idx,
+                                                             double* __restrict__ out_dist) {
+    __shared__ double bd[EXB_HC];
+    __shared__ uint32_t bi[EXB_HC];
+    const int nfail = min(*fail_count, fcap);
+    for (int w = blockIdx.x; w < nfail; w += gridDim.x) {
+        const int n = hit_cnt[w];
+        if (n > EXB_HC) continue;
+        const long long q = fail_rows[w];
+        __syncthreads();
+        if ((int)threadIdx.x < n) {
+            bd[threadIdx.x] = hit_d[(size_t)w * EXB_HC + threadIdx.x];
+            bi[threadIdx.x] = hit_i[(size_t)w * EXB_HC + threadIdx.x];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < n) {
+            const double d = bd[threadIdx.x];
+            const uint32_t idx = bi[threadIdx.x];
+            int r = 0;
+            for (int y = 0; y < n; ++y) r += key_less(bd[y], bi[y], d, idx) ? 1 : 0;
+            if (r < k) {
+                out_idx[(size_t)q * k + r] = (int32_t)idx;
+                out_dist[(size_t)q * k + r] = d;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(EX_THREADS) exact_rows_kernel(const double* __restrict__ Q,
                                                                const double* __restrict__ C, long long Nc, int D,
                                                                int k, int metric,
                                                                const int32_t* __restrict__ fail_count,
                                                                const int32_t* __restrict__ fail_rows,
+                                                               const int32_t* __restrict__ hit_cnt, int fcap,
                                                                int32_t* __restrict__ out_idx,
                                                                double* __restrict__ out_dist) {
     __shared__ double qs[GMD_MAX_D];
@@ -183,6 +307,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_rows_kernel(const double* __
     __shared__ int cnt;
     const int nfail = *fail_count;
     for (int w = blockIdx.x; w < nfail; w += gridDim.x) {
+        if (hit_cnt && w < fcap && hit_cnt[w] <= EXB_HC) continue;   // finished by the batched pass
         const long long q = fail_rows[w];
         __syncthreads();
         for (int d = threadIdx.x; d < D; d += EX_THREADS) qs[d] = Q[(size_t)q * D + d];
@@ -264,17 +389,42 @@ extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C,
     return GMD_OK;
 }
 
+extern "C" size_t gmd_exact_workspace_bytes(int64_t Nq) {
+    const size_t rows = (size_t)std::min<int64_t>(std::max<int64_t>(Nq, 0), EXB_FCAP);
+    return rows * (sizeof(int32_t) + (size_t)EXB_HC * (sizeof(double) + sizeof(uint32_t)));
+}
+
 extern "C" int gmd_exact_rows_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
                                   const int32_t* fail_count, const int32_t* fail_rows, int32_t* out_idx,
-                                  double* out_dist, void* stream) {
+                                  double* out_dist, void* workspace, size_t workspace_bytes, void* stream) {
     GMD_REQUIRE(Q && C && fail_count && fail_rows && out_idx && out_dist, GMD_ERR_BAD_ARG, "exact_rows: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1 && D <= GMD_MAX_D && k >= 1 && k <= Nc, GMD_ERR_BAD_ARG,
                 "exact_rows: bad sizes");
     int dev = 0, sms = 0;
     GMD_CUDA_CHECK(cudaGetDevice(&dev));
     GMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    exact_rows_kernel<<<sms * 2, EX_THREADS, 0, (cudaStream_t)stream>>>(Q, C, Nc, D, k, metric, fail_count, fail_rows,
-                                                                       out_idx, out_dist);
+    cudaStream_t st = (cudaStream_t)stream;
+    // batched pass over as many rejected rows as the workspace holds hit lists for
+    const size_t per_row = sizeof(int32_t) + (size_t)EXB_HC * (sizeof(double) + sizeof(uint32_t));
+    const int fcap = workspace ? (int)std::min<size_t>(std::min<int64_t>(Nq, EXB_FCAP), workspace_bytes / per_row) : 0;
+    int32_t* hit_cnt = nullptr;
+    if (fcap > 0) {
+        double* hit_d = (double*)workspace;                                  // [fcap][EXB_HC]
+        uint32_t* hit_i = (uint32_t*)(hit_d + (size_t)fcap * EXB_HC);        // [fcap][EXB_HC]
+        hit_cnt = (int32_t*)(hit_i + (size_t)fcap * EXB_HC);                 // [fcap]
+        GMD_CUDA_CHECK(cudaMemsetAsync(hit_cnt, 0, sizeof(int32_t) * fcap, st));
+        const size_t smem = ((size_t)EXB_CH * (D | 1) + (size_t)EXB_RB * D + EXB_RB) * sizeof(double);
+        GMD_CUDA_CHECK(cudaFuncSetAttribute(exact_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)((Nc + EXB_CH - 1) / EXB_CH);
+        exact_batch_kernel<<<grid, EXB_THREADS, smem, st>>>(Q, C, Nc, D, k, metric, fail_count, fail_rows, fcap,
+                                                            out_dist, hit_cnt, hit_d, hit_i);
+        GMD_CUDA_CHECK(cudaGetLastError());
+        exact_finish_kernel<<<sms * 2, EXB_HC, 0, st>>>(k, fail_count, fail_rows, fcap, hit_cnt, hit_d, hit_i, out_idx,
+                                                       out_dist);
+        GMD_CUDA_CHECK(cudaGetLastError());
+    }
+    exact_rows_kernel<<<sms * 2, EX_THREADS, 0, st>>>(Q, C, Nc, D, k, metric, fail_count, fail_rows, hit_cnt, fcap,
+                                                      out_idx, out_dist);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }

@@ -30,15 +30,21 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "scan_impl.cuh"
 
 namespace gmd_tc {
 using namespace gmd_scan;
 
 constexpr int TM = 128;                  // profiles per TC tile (UMMA M and N)
-constexpr int TK = 32;                   // contraction length (padded D)
-constexpr int IMG_B = TM * TK * 2;       // one FP16 image: 8 KB
-constexpr int TILE_B = 2 * IMG_B + 1024; // hi, lo, norms (512 B used)
+constexpr int TK = 32;                   // contraction length of one K block (64-byte rows of halves)
+constexpr int IMG_B = TM * TK * 2;       // one FP16 image of one K block: 8 KB
+constexpr int KB_B = 2 * IMG_B;          // hi + lo images of one K block: 16 KB = one ring stage
+constexpr int MAX_KB = 5;                // K blocks per tile: D + 1 <= 160 covers the 136-d signatures
+constexpr int NS_MAX = 8;                // most ring stages
+constexpr int NACC = 4;                  // accumulator stages in tensor memory (4 x 128 of the 512 columns)
+__host__ __device__ constexpr int tile_bytes(int nkb) { return nkb * KB_B + 1024; }  // K blocks, then norms
 constexpr float QCOL = 8.0f;             // column D of a query row; a candidate row holds -||c||^2 / (2 QCOL)
 constexpr float PAD_COL = -60000.0f;     // column D of a padding candidate: u = -480000, below any real value
 constexpr int NTHREADS = 192;
@@ -116,9 +122,10 @@ __global__ void __launch_bounds__(256) tc_norms_kernel(const double* __restrict_
     if (bad) atomicExch(flags, 1);
 }
 
-// pass 2: scaled FP16 hi / lo images.  role 0: query tile (column D = QCOL), role 1: candidate tile
-// (column D = -||x||^2 / (2 QCOL), in scaled units).  stats_c / stats_q: max ||x||^2 of the two sets.
-__global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long N, int D,
+// pass 2: scaled FP16 hi / lo images, nkb K blocks of 32 columns.  role 0: query tile (column D =
+// QCOL), role 1: candidate tile (column D = -||x||^2 / (2 QCOL), in scaled units).
+// stats_c / stats_q: max ||x||^2 of the two sets.
+__global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long N, int D, int nkb,
                                                       const double* __restrict__ center, int role,
                                                       const float* __restrict__ stats_c, const float* __restrict__ stats_q,
                                                       unsigned char* __restrict__ tiles) {
@@ -137,11 +144,10 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
         s_n2[threadIdx.x] = (float)n2;
     }
     __syncthreads();
-    __half* hi = reinterpret_cast<__half*>(tiles + (size_t)t * TILE_B);
-    __half* lo = hi + IMG_B / 2;
-    float* nrm = reinterpret_cast<float*>(tiles + (size_t)t * TILE_B + 2 * IMG_B);
-    for (int e = threadIdx.x; e < TM * TK; e += blockDim.x) {
-        const int r = e / TK, k = e - r * TK;
+    unsigned char* tile = tiles + (size_t)t * tile_bytes(nkb);
+    const int KT = TK * nkb;
+    for (int e = threadIdx.x; e < TM * KT; e += blockDim.x) {
+        const int r = e / KT, k = e - r * KT;
         const long long row = row0 + r;
         float v = 0.0f;
         if (row < N) {
@@ -153,11 +159,15 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
             v = role == 0 ? QCOL : PAD_COL;
         }
         const __half h = __float2half_rn(v);
-        // shared-memory image: 8-row groups of 512 B, 16-byte chunk c (8 halves) of row r at c ^ ((r >> 1) & 3)
-        const int off = ((r >> 3) * 512 + (r & 7) * 64 + ((((k >> 3) ^ ((r >> 1) & 3)) & 3) << 4) + (k & 7) * 2) >> 1;
+        // K block kb = k / 32; inside it the shared-memory image: 8-row groups of 512 B, 16-byte chunk c
+        // (8 halves) of row r at c ^ ((r >> 1) & 3)
+        const int kb = k >> 5, kk = k & 31;
+        const int off = ((r >> 3) * 512 + (r & 7) * 64 + ((((kk >> 3) ^ ((r >> 1) & 3)) & 3) << 4) + (kk & 7) * 2) >> 1;
+        __half* hi = reinterpret_cast<__half*>(tile + (size_t)kb * KB_B);
         hi[off] = h;
-        lo[off] = __float2half_rn(v - __half2float(h));
+        hi[IMG_B / 2 + off] = __float2half_rn(v - __half2float(h));
     }
+    float* nrm = reinterpret_cast<float*>(tile + (size_t)nkb * KB_B);
     if (threadIdx.x < TM) nrm[threadIdx.x] = (row0 + threadIdx.x) < N ? s_n2[threadIdx.x] : 0.0f;
 }
 
@@ -177,12 +187,14 @@ static __device__ __noinline__ float drain_own(uint64_t* h, int kk, const uint2*
     return (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
 }
 
-// NSTB: pipeline depth = candidate stages in shared memory = accumulator stages in tensor memory
-// (4 when the heaps leave room in shared memory, else 3 or 2)
-template <int NSTB>
+// nkb: K blocks per tile (1 for D <= 31 ... 5 for D = 136); ns: ring stages of one K block each.
+// NKB is a template parameter: with a run-time K-block loop the issuing thread falls behind the tensor
+// pipe (1M x 30: 196 ms instead of 159 ms with selection off).
+template <int NKB>
 __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned char* __restrict__ qtiles,
                                                               const unsigned char* __restrict__ ctiles,
                                                               long long Nq, long long Nc, int ntiles_c, int kk,
+                                                              int ns,
                                                               long long c_index_offset, int dbg,
                                                               const float* __restrict__ stats_c,
                                                               const float* __restrict__ stats_q,
@@ -191,16 +203,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                                                               float* __restrict__ cand_tau) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* Aimg = base;                          // hi, lo images + norms of the CTA's queries (one TC tile)
-    unsigned char* Bst = base + TILE_B;                  // NSTB candidate stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + (size_t)NSTB * TILE_B);
-    uint64_t* full = bars;                               // [NSTB] candidate tile landed in shared memory
-    uint64_t* done = bars + NSTB;                        // [NSTB] the tile's MMAs are complete: the accumulator
-                                                         //        stage is written and the smem stage is free
-    uint64_t* tempty = bars + 2 * NSTB;                  // [NSTB] accumulator stage read back by the selection warps
-    uint64_t* qbar = bars + 3 * NSTB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NSTB + 2);
-    uint2* queues = reinterpret_cast<uint2*>(bars + 3 * NSTB + 4);        // [TQ][128] parked (index, value bits)
+    constexpr int nkb = NKB;
+    constexpr int TILE_B = tile_bytes(nkb);
+    unsigned char* Aimg = base;                          // the CTA's query tile: nkb x (hi, lo) + norms
+    unsigned char* Bst = base + TILE_B;                  // ns ring stages: one K block (hi, lo) of a candidate tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + (size_t)ns * KB_B);
+    uint64_t* full = bars;                               // [NS_MAX] K block landed in shared memory
+    uint64_t* sfree = bars + NS_MAX;                     // [NS_MAX] the MMAs that read the stage are complete
+    uint64_t* tdone = bars + 2 * NS_MAX;                 // [NACC] all MMAs of a tile complete: accumulator stage written
+    uint64_t* tempty = bars + 2 * NS_MAX + NACC;         // [NACC] accumulator stage read back by the selection warps
+    uint64_t* qbar = bars + 2 * NS_MAX + 2 * NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS_MAX + 2 * NACC + 2);
+    uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NS_MAX + 2 * NACC + 4);  // [TQ][128] parked (index, value bits)
     uint64_t* lists = reinterpret_cast<uint64_t*>(queues + TQ * TM);      // [128][kkp] heaps
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -208,10 +222,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     const long long qt = blockIdx.x;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTB; ++s) {
+        for (int s = 0; s < ns; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&done[s], 1);
-            mbar_init(&tempty[s], 4);
+            mbar_init(&sfree[s], 1);
+        }
+        for (int a = 0; a < NACC; ++a) {
+            mbar_init(&tdone[a], 1);
+            mbar_init(&tempty[a], 4);
         }
         mbar_init(qbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -230,18 +247,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ---- producer
+        // ---- producer: ring item `it` = K block it % nkb of candidate tile it / nkb
         if (lane == 0) {
-            for (int t = 0; t < ntiles_c; ++t) {
-                const int s = t % NSTB;
-                if (t >= NSTB) mbar_wait_backoff(&done[s], ((t / NSTB) - 1) & 1, 64);
-                if (dbg == 2) {  // developer probe: no candidate traffic (1 KB per tile), MMAs on stale data
-                    mbar_expect_tx(&full[s], 1024);
-                    bulk_g2s(Bst + (size_t)s * TILE_B, ctiles + (size_t)t * TILE_B, 1024, &full[s]);
-                    continue;
+            // A stage that held the last K block of a tile is free when the tile's accumulator is
+            // complete (tdone), any other when the MMAs of its K block are (sfree): one commit per block.
+            // ns <= NACC * nkb keeps the tdone parity unambiguous (tile pt + NACC is not loaded yet).
+            const long long nit = (long long)ntiles_c * nkb;
+            int s = 0, kb = 0, t = 0, pkb = 0, pt = 0;
+            uint32_t sph = 0;                              // bit s: parity of the next sfree[s] phase
+            for (long long it = 0; it < nit; ++it) {
+                if (it >= ns) {
+                    if (pkb == nkb - 1) {
+                        mbar_wait_backoff(&tdone[pt % NACC], (uint32_t)(pt / NACC) & 1u, 64);
+                    } else {
+                        mbar_wait_backoff(&sfree[s], (sph >> s) & 1u, 64);
+                        sph ^= 1u << s;
+                    }
+                    if (++pkb == nkb) pkb = 0, ++pt;
                 }
-                mbar_expect_tx(&full[s], TILE_B);
-                bulk_g2s(Bst + (size_t)s * TILE_B, ctiles + (size_t)t * TILE_B, TILE_B, &full[s]);
+                const uint32_t bytes = dbg == 2 ? 1024u : (uint32_t)KB_B;  // (2: developer probe, no candidate traffic)
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(Bst + (size_t)s * KB_B, ctiles + (size_t)t * TILE_B + (size_t)kb * KB_B, bytes, &full[s]);
+                if (++kb == nkb) kb = 0, ++t;
+                if (++s == ns) s = 0;
             }
         }
     } else if (warp == 1) {
@@ -251,23 +279,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             // FP32 accumulator, FP16 A and B (format 0), both K-major, N = M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             // descriptors differ only in the 16-byte-granular start address: build them once and add
-            const uint64_t a_hi = umma_desc(smem_u32(Aimg)), a_lo = a_hi + (IMG_B >> 4);
+            const uint64_t a_base = umma_desc(smem_u32(Aimg));
             const uint64_t b_base = umma_desc(smem_u32(Bst));
+            int s = 0;
+            uint32_t ph = 0;
             for (int t = 0; t < ntiles_c; ++t) {
-                const int s = t % NSTB;
-                mbar_wait(&full[s], (t / NSTB) & 1);
-                if (t >= NSTB) mbar_wait(&tempty[s], ((t / NSTB) - 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint64_t b_hi = b_base + (uint64_t)s * (TILE_B >> 4), b_lo = b_hi + (IMG_B >> 4);
-                const uint32_t acc = tmem + (uint32_t)(s * TM);
-                // hi.hi + hi.lo + lo.hi, K = 16 halves (32 bytes) per MMA
+                const int a = t % NACC;
+                if (t >= NACC) mbar_wait(&tempty[a], ((t / NACC) - 1) & 1);
+                const uint32_t acc = tmem + (uint32_t)(a * TM);
 #pragma unroll
-                for (int p = 0; p < 3; ++p)
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint64_t a_hi = a_base + (uint64_t)kb * (KB_B >> 4), a_lo = a_hi + (IMG_B >> 4);
+                    const uint64_t b_hi = b_base + (uint64_t)s * (KB_B >> 4), b_lo = b_hi + (IMG_B >> 4);
+                    // hi.hi + hi.lo + lo.hi, K = 16 halves (32 bytes) per MMA
 #pragma unroll
-                    for (int k = 0; k < TK / 16; ++k)
-                        umma_f16(acc, (p == 2 ? a_lo : a_hi) + 2 * k, (p == 1 ? b_lo : b_hi) + 2 * k, idesc,
-                                 (p | k) ? 1u : 0u);
-                umma_commit(&done[s]);   // one commit: accumulator stage written, shared-memory stage readable again
+                    for (int p = 0; p < 3; ++p)
+#pragma unroll
+                        for (int k = 0; k < TK / 16; ++k)
+                            umma_f16(acc, (p == 2 ? a_lo : a_hi) + 2 * k, (p == 1 ? b_lo : b_hi) + 2 * k, idesc,
+                                     (kb | p | k) ? 1u : 0u);
+                    // one commit per K block: the last one of a tile signals the accumulator stage (and
+                    // frees its ring stage with it), the others only their ring stage
+                    umma_commit(kb + 1 < nkb ? &sfree[s] : &tdone[a]);
+                    if (++s == ns) s = 0, ph ^= 1;
+                }
             }
         }
     } else {
@@ -282,8 +319,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         float uthr = __int_as_float(0xff800000);            // -thr / 2: the accumulators are u = -s/2
         if (dbg == 4) uthr = __int_as_float(0x7f800000);    // developer probe: nothing ever hits
         for (int t = 0; t < ntiles_c; ++t) {
-            const int a = t % NSTB;
-            mbar_wait(&done[a], (t / NSTB) & 1);
+            const int a = t % NACC;
+            mbar_wait(&tdone[a], (t / NACC) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t cbase = (uint32_t)t * TM;
             const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TM);
@@ -348,7 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         if (q < Nq) {
             // back to the caller's units: everything above ran on rows scaled by 2^e
             const float unscale = ldexpf(1.0f, -2 * gmd_tc_exponent(stats_c[0], stats_q[0]));
-            const float qnv = reinterpret_cast<const float*>(Aimg + 2 * IMG_B)[row];
+            const float qnv = reinterpret_cast<const float*>(Aimg + (size_t)nkb * KB_B)[row];
             const size_t ob = (size_t)q * kk;
             for (int x = 0; x < kk; ++x) {
                 const uint64_t key = h[x];
@@ -376,19 +413,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
 
 }  // namespace gmd_tc
 
+static int tc_nkb(int D) { return (D + 1 + gmd_tc::TK - 1) / gmd_tc::TK; }
+
 extern "C" int gmd_tc_supported(int k, int metric, int D) {
-    // one column of the K = 32 contraction carries the norm
-    return metric == GMD_L2 && k >= 2 && k <= GMD_MAX_K && D >= 4 && D < gmd_tc::TK;
+    // one column of the contraction carries the norm; up to MAX_KB blocks of 32 columns
+    return metric == GMD_L2 && k >= 2 && k <= GMD_MAX_K && D >= 4 && D <= GMD_MAX_D && tc_nkb(D) <= gmd_tc::MAX_KB;
 }
 
-extern "C" size_t gmd_tc_tiles_bytes(int64_t N) {
-    if (N < 0) return 0;
-    return (size_t)((N + gmd_tc::TM - 1) / gmd_tc::TM) * gmd_tc::TILE_B;
+extern "C" size_t gmd_tc_tiles_bytes(int64_t N, int D) {
+    if (N < 0 || D < 1 || tc_nkb(D) > gmd_tc::MAX_KB) return 0;
+    return (size_t)((N + gmd_tc::TM - 1) / gmd_tc::TM) * gmd_tc::tile_bytes(tc_nkb(D));
 }
 
 extern "C" int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double* center, float* stats, int32_t* flags,
                                 void* stream) {
-    GMD_REQUIRE(X && stats && flags && N > 0 && D >= 1 && D < gmd_tc::TK, GMD_ERR_BAD_ARG, "tc_norms: bad arguments");
+    GMD_REQUIRE(X && stats && flags && N > 0 && D >= 1 && tc_nkb(D) <= gmd_tc::MAX_KB, GMD_ERR_BAD_ARG,
+                "tc_norms: bad arguments");
     gmd_tc::tc_norms_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, N, D, center, stats, flags);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
@@ -396,10 +436,11 @@ extern "C" int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double*
 
 extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role,
                                const float* stats_c, const float* stats_q, void* tiles, void* stream) {
-    GMD_REQUIRE(X && tiles && stats_c && stats_q && N > 0 && D >= 1 && D < gmd_tc::TK && (role == 0 || role == 1),
+    GMD_REQUIRE(X && tiles && stats_c && stats_q && N > 0 && D >= 1 && tc_nkb(D) <= gmd_tc::MAX_KB &&
+                    (role == 0 || role == 1),
                 GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
     const unsigned grid = (unsigned)((N + gmd_tc::TM - 1) / gmd_tc::TM);
-    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, center, role, stats_c, stats_q,
+    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, tc_nkb(D), center, role, stats_c, stats_q,
                                                                   (unsigned char*)tiles);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
@@ -411,23 +452,32 @@ extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctile
     GMD_REQUIRE(qtiles && ctiles && stats_c && stats_q && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG,
                 "scan_tc: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan_tc: bad sizes");
-    GMD_REQUIRE(D >= 1 && D < gmd_tc::TK && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
     using namespace gmd_tc;
-    const size_t fixed = 1024 + (size_t)TILE_B + 512 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8;
-    int nst = 4;
-    while (nst > 2 && fixed + (size_t)nst * TILE_B > GMD_SMEM_LIMIT) --nst;
-    const size_t smem = fixed + (size_t)nst * TILE_B;
-    GMD_REQUIRE(smem <= GMD_SMEM_LIMIT, GMD_ERR_UNSUPPORTED, "scan_tc: kk=%d needs %zu B of shared memory", kk, smem);
+    const int nkb = tc_nkb(D);
+    GMD_REQUIRE(D >= 1 && nkb <= MAX_KB && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
+    const size_t fixed = 1024 + (size_t)tile_bytes(nkb) + 512 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8;
+    GMD_REQUIRE(fixed + 2 * (size_t)KB_B <= GMD_SMEM_LIMIT, GMD_ERR_UNSUPPORTED,
+                "scan_tc: D=%d kk=%d needs more than 227 KB of shared memory", D, kk);
+    const int ns = (int)std::min<size_t>(std::min(NS_MAX, NACC * nkb), (GMD_SMEM_LIMIT - fixed) / KB_B);
+    const size_t smem = fixed + (size_t)ns * KB_B;
     const unsigned grid = (unsigned)((Nq + TM - 1) / TM);
     const int dbg = getenv("GMD_TC_DBG") ? atoi(getenv("GMD_TC_DBG")) : 0;  // developer probe
+    const int ntiles_c = (int)((Nc + TM - 1) / TM);
     auto launch = [&](auto kern) -> int {
         GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>((const unsigned char*)qtiles, (const unsigned char*)ctiles,
-                                                           Nq, Nc, (int)((Nc + TM - 1) / TM), kk, c_index_offset, dbg,
-                                                           stats_c, stats_q, cand_idx, cand_val, cand_tau);
+                                                           Nq, Nc, ntiles_c, kk, ns, c_index_offset, dbg, stats_c,
+                                                           stats_q, cand_idx, cand_val, cand_tau);
         return GMD_OK;
     };
-    const int rc = nst == 4 ? launch(scan_tc_kernel<4>) : nst == 3 ? launch(scan_tc_kernel<3>) : launch(scan_tc_kernel<2>);
+    int rc;
+    switch (nkb) {
+        case 1: rc = launch(scan_tc_kernel<1>); break;
+        case 2: rc = launch(scan_tc_kernel<2>); break;
+        case 3: rc = launch(scan_tc_kernel<3>); break;
+        case 4: rc = launch(scan_tc_kernel<4>); break;
+        default: rc = launch(scan_tc_kernel<5>); break;
+    }
     if (rc != GMD_OK) return rc;
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;

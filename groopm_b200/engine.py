@@ -96,7 +96,7 @@ class KnnPipeline:
         self.form = int(form)
         self.tc = self.form == _lib.FORM_TC
         if self.tc and not self.lib.gmd_tc_supported(self.k, self.metric, self.d):
-            raise ValueError("the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 31")
+            raise ValueError("the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 136")
         self.same = bool(same)
         # k = 1 on short profiles (BMU search) has its own heap-free scan
         self.bmu = bool(auto and self.lib.gmd_use_bmu_scan(self.k, self.metric, self.d))
@@ -114,7 +114,8 @@ class KnnPipeline:
         self.center = torch.zeros(_lib.MAX_D, dtype=torch.float64, **e)
         self.stats = torch.zeros(4, dtype=torch.float32, **e)
         self.flags = torch.zeros(4, dtype=torch.int32, **e)
-        tiles_bytes = self.lib.gmd_tc_tiles_bytes if self.tc else (lambda n: self.lib.gmd_tiles_bytes(n, self.d))
+        tiles_bytes = ((lambda n: self.lib.gmd_tc_tiles_bytes(n, self.d)) if self.tc
+                       else (lambda n: self.lib.gmd_tiles_bytes(n, self.d)))
         self.ctiles = torch.empty(tiles_bytes(self.nc) // 4, dtype=torch.float32, **e)
         # tensor-core tiles differ by role (column D), so queries are always staged separately there
         self.qtiles = self.ctiles if (same and not self.tc) else torch.empty(
@@ -124,6 +125,7 @@ class KnnPipeline:
         self.cand_val = torch.empty(m, dtype=torch.float32, **e)
         self.cand_tau = torch.empty(self.nq * self.nsplit, dtype=torch.float32, **e)
         self.fail_rows = torch.empty(self.nq, dtype=torch.int32, **e)
+        self.exact_ws = torch.empty(self.lib.gmd_exact_workspace_bytes(self.nq) // 4, dtype=torch.int32, **e)
         self.out_idx = torch.empty((self.nq, self.k), dtype=torch.int32, **e)
         self.out_dist = torch.empty((self.nq, self.k), dtype=torch.float64, **e)
 
@@ -188,7 +190,8 @@ class KnnPipeline:
     def exact_rows(self, q: torch.Tensor, c: torch.Tensor):
         _lib.check(self.lib.gmd_exact_rows_f64(
             _ptr(q), self.nq, _ptr(c), self.nc, self.d, self.k, self.metric, _ptr(self.flags) + 4,
-            _ptr(self.fail_rows), _ptr(self.out_idx), _ptr(self.out_dist), _stream_ptr()))
+            _ptr(self.fail_rows), _ptr(self.out_idx), _ptr(self.out_dist), _ptr(self.exact_ws),
+            self.exact_ws.numel() * 4, _stream_ptr()))
 
     def run(self, q: torch.Tensor, c: torch.Tensor):
         """q [Nq, D], c [Nc, D] float64 on this pipeline's device -> (out_idx, out_dist) device tensors."""
@@ -215,9 +218,10 @@ class KnnPipeline:
     # launches of the engine's own kernels in one run() (col_mean, prep x1/2, scan, refine, exact)
     @property
     def launches_per_run(self) -> int:
+        # the exact stage is three kernels: batched pass, its finish, one-row-per-block remainder
         if self.tc:
-            return 7 if self.same else 8      # col_mean, norms x1/2, prep x2, scan, refine, exact
-        return 5 if self.same else 6
+            return 9 if self.same else 10     # col_mean, norms x1/2, prep x2, scan, refine, exact x3
+        return 7 if self.same else 8
 
 
 def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, device=None,

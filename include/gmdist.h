@@ -139,10 +139,12 @@ GMD_API int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctile
  * set with BOTH sets' stats slots (the same slot twice when queries == candidates).
  * Outputs as gmd_scan_topk_f32 with nsplit = 1, in the caller's units, to be finished by
  * gmd_refine_topk_f64(form = GMD_FORM_TC, stats = candidate slot, stats + 2 = query slot) /
- * gmd_exact_rows_f64.  gmd_tc_supported(k, metric, D): Euclidean, 2 <= k <= 64, 4 <= D <= 31. */
+ * gmd_exact_rows_f64.  A tile holds ceil((D + 1) / 32) K blocks of 32 columns, streamed through the
+ * ring one block at a time and accumulated in tensor memory.
+ * gmd_tc_supported(k, metric, D): Euclidean, 2 <= k <= 64, 4 <= D <= 136.                  */
 GMD_API int gmd_tc_supported(int k, int metric, int D);
 GMD_API int gmd_use_tc_scan(int64_t Nq, int64_t Nc, int k, int metric, int D);  /* the size policy of gmd_knn_f64 */
-GMD_API size_t gmd_tc_tiles_bytes(int64_t N);
+GMD_API size_t gmd_tc_tiles_bytes(int64_t N, int D);
 GMD_API int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double* center, float* stats, int32_t* flags,
                      void* stream);
 GMD_API int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role,
@@ -161,11 +163,17 @@ GMD_API int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, in
                         double* out_dist,
                         int32_t* fail_count, int32_t* fail_rows, void* stream);
 
-/* exact float64 scan of all candidates for the listed rows (reads the count on device) */
+/* exact float64 scan of all candidates for the listed rows (reads the count on device).
+ * With a workspace of gmd_exact_workspace_bytes(Nq) the listed rows (up to 4096) share one
+ * pass over the candidates: each block stages 128 candidates once and every listed row
+ * visits them, keeping what lies within its re-ranked k-th distance; rows with more than
+ * 256 such candidates, rows beyond the capacity, and all rows when workspace is NULL are
+ * scanned one row per block.                                                              */
+GMD_API size_t gmd_exact_workspace_bytes(int64_t Nq);
 GMD_API int gmd_exact_rows_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
                        int k, int metric, const int32_t* fail_count,
                        const int32_t* fail_rows, int32_t* out_idx, double* out_dist,
-                       void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* whole pipeline on device pointers with a caller workspace (see
  * gmd_knn_workspace_bytes); form = GMD_FORM_AUTO picks by metric and D.

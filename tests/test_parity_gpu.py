@@ -391,7 +391,11 @@ def test_cfg4_raw_signatures_100k_d136(cuda):
     medians on 2000-row bins."""
     sigs = synth.quantise(synth.kmer_sigs(100_000, 4), 34)
     idx, dist, info = engine.knn(sigs, None, k=16, return_info=True)
+    assert info["form"] == _lib.FORM_TC            # five K blocks of the tensor-core scan
     _graph_properties(sigs, idx, dist, 16)
+    idx32, dist32, info32 = engine.knn(sigs, None, k=16, form=_lib.FORM_EXPANDED, return_info=True)
+    assert info32["form"] == _lib.FORM_EXPANDED    # the FP32 scan proposes, float64 decides: same answer
+    assert np.array_equal(idx, idx32) and np.array_equal(dist, dist32)
     rows = np.sort(np.random.default_rng(4).choice(len(sigs), 256, replace=False))
     od, oi = oracle.knn(sigs[rows], sigs, 16)
     assert_knn_parity(sigs[rows], sigs, idx[rows], dist[rows], oi, od)
@@ -464,6 +468,9 @@ def test_batched_medians_vs_oracle(cuda):
 @pytest.mark.parametrize("n,nq,d,k", [
     (5000, None, 4, 2), (3000, None, 31, 64), (9000, None, 10, 16), (4097, 1000, 17, 6),
     (129, None, 8, 32), (128, 77, 30, 5), (20000, None, 30, 32),
+    # more than one K block of 32 columns (D + 1 > 32): 2, 3, 4 and 5 blocks, block edges
+    (3000, None, 32, 8), (2500, 700, 63, 16), (4000, None, 64, 10), (3000, None, 95, 4), (2100, 500, 100, 64),
+    (6000, None, 136, 16), (300, None, 127, 3),
 ])
 def test_tensor_core_scan_vs_oracle(cuda, n, nq, d, k):
     """The tcgen05 3 x TF32 scan forced on (form=GMD_FORM_TC) at sizes the oracle finishes in
@@ -484,13 +491,16 @@ def test_tensor_core_scan_vs_oracle(cuda, n, nq, d, k):
 
 def test_tensor_core_scan_limits_and_policy(cuda):
     lib = _lib.lib()
-    assert lib.gmd_tc_supported(16, _lib.L2, 31) == 1 and lib.gmd_tc_supported(16, _lib.L2, 32) == 0
+    assert lib.gmd_tc_supported(16, _lib.L2, 31) == 1 and lib.gmd_tc_supported(16, _lib.L2, 32) == 1
+    assert lib.gmd_tc_supported(16, _lib.L2, 136) == 1 and lib.gmd_tc_supported(16, _lib.L2, 137) == 0
+    assert lib.gmd_tc_supported(16, _lib.L2, 3) == 0 and lib.gmd_tc_supported(65, _lib.L2, 30) == 0
+    assert lib.gmd_tc_tiles_bytes(129, 30) == 2 * (16384 + 1024) and lib.gmd_tc_tiles_bytes(128, 136) == 5 * 16384 + 1024
     assert lib.gmd_tc_supported(16, _lib.L1, 10) == 0 and lib.gmd_tc_supported(1, _lib.L2, 10) == 0
     assert lib.gmd_use_tc_scan(100_000, 100_000, 16, _lib.L2, 10) == 1
     assert lib.gmd_use_tc_scan(2_000, 100_000, 16, _lib.L2, 10) == 0
     x = np.random.default_rng(0).random((500, 32))
     with pytest.raises(ValueError):
-        engine.knn(x, None, k=4, form=_lib.FORM_TC)
+        engine.knn(x[:, :3], None, k=4, form=_lib.FORM_TC)
     with pytest.raises(ValueError):
         engine.knn(x[:, :8], None, k=4, metric="cityblock", form=_lib.FORM_TC)
 
@@ -502,6 +512,21 @@ def test_tensor_core_scan_ill_conditioned_falls_back(cuda):
     x = centres[rng.integers(0, 30, size=5000)] + 0.01 * rng.standard_normal((5000, 4))
     idx, dist, info = engine.knn(x, None, k=6, form=_lib.FORM_TC, return_info=True)
     od, oi = oracle.knn(x, x, 6)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cityblock"])
+def test_exact_pass_tie_mass_and_capacity(cuda, metric):
+    """The batched exact pass keeps at most 256 candidates per rejected row: a mass of 700
+    identical rows (every one of them within the bound of every other) overflows it and is
+    finished one row per block; the answer is the lowest-index rule of a stable sort either way."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((3000, 12)) * 3.0
+    x[500:1200] = x[500]
+    x[2000:2100] = x[2000] + 1e-9 * rng.standard_normal((100, 12))      # a near-tie mass that fits
+    idx, dist, info = engine.knn(x, None, k=8, metric=metric, return_info=True)
+    assert info["exact_rows"] >= 700
+    od, oi = oracle.knn(x, x, 8, metric)
     assert np.array_equal(idx, oi) and np.array_equal(dist, od)
 
 
