@@ -1,32 +1,39 @@
-// Tensor-core variant of the fused distance + top-k scan (expanded form, D <= 31).
+// Tensor-core variant of the fused distance + top-k scan (expanded form, Euclidean, 4 <= D <= 136).
 //
-// The dot products q.c of a 128-query x 128-candidate tile are one K = 32 contraction on the
+// The dot products q.c of a 128-query x 128-candidate tile are a contraction on the
 // 5th-generation tensor cores: tcgen05.mma kind::f16 (FP16 operands, FP32 accumulation in
-// tensor memory), operands K-major SWIZZLE_64B images in shared memory.  One FP16 (11-bit
-// significand) is far too coarse for a neighbour search, so every centred FP32 value, scaled by
-// a power of two that brings the largest row norm into (128, 256], is split v = hi + lo (both
-// FP16) and the contraction is issued three times: hi.hi + hi.lo + lo.hi.  Measured against
-// float64 (tools/tc_probe16.cu): |error| <= 2^-21.9 |q||c|, i.e. FP32-class, inside the
-// certificate's bound (refine.cu, GMD_FORM_TC).  The same split with TF32 operands
-// (tools/tc_probe.cu, 2^-20.9) needs twice the tensor time and twice the bytes; it was the
-// first version of this kernel.
+// tensor memory), operands K-major SWIZZLE_64B images in shared memory, the D + 1 columns cut
+// into NKB = ceil((D + 1) / 32) K blocks of 32 that accumulate into the same tensor-memory
+// stage.  One FP16 (11-bit significand) is far too coarse for a neighbour search, so every
+// centred FP32 value, scaled by a power of two that brings the largest row norm into (128, 256],
+// is split v = hi + lo (both FP16) and the contraction is issued three times: hi.hi + hi.lo +
+// lo.hi.  Measured against float64 (tools/tc_probe16.cu): |error| <= 2^-21.9 |q||c|, i.e.
+// FP32-class, inside the certificate's bound (refine.cu, GMD_FORM_TC).  The same split with
+// TF32 operands (tools/tc_probe.cu, 2^-20.9) needs twice the tensor time and twice the bytes;
+// it was the first version of this kernel.
 //
 // The norm rides in the contraction: column D of a QUERY image holds 8, column D of a
 // CANDIDATE image holds -||c||^2 / 16, so the accumulator is  u = q.c - ||c||^2/2 = -s/2  with
 // s = ||c||^2 - 2 q.c the value the FP32 scan ranks by; selection maximises u directly (no
 // per-pair FMA, no norm loads) and converts to s = -2u (exact) only for the few values it keeps.
 //
-// Roles (192 threads): warp 0 lane 0 streams candidate tiles HBM -> shared memory with bulk
-// async copies (mbarrier ring); warp 1 lane 0 issues the MMAs (6 per tile) into one of the
-// 128-column accumulator stages in tensor memory and commits completion to an mbarrier; warps
-// 2..5 are the selection warps: thread r owns query r of the CTA = TMEM lane r, reads its 128
-// accumulators with tcgen05.ld, and keeps the query's top-kk heap in shared memory all by
-// itself (no atomics: a thread sees every candidate of its query, in ascending index order).
+// Roles (224 threads).  Warps 0..3 are the selection warps: thread r owns query r of the CTA =
+// TMEM lane r, reads its 128 accumulators with tcgen05.ld, and keeps the query's top-kk heap in
+// shared memory all by itself (no atomics: a thread sees every candidate of its query, in
+// ascending index order).  Warp 4 lane 0 streams candidate K blocks HBM -> shared memory with
+// bulk async copies (mbarrier ring, one 16 KB K block per stage).  Warps 5 and 6, lane 0 each,
+// issue the MMAs (6 per K block) of the even and of the odd candidate tiles into one of the four
+// 128-column accumulator stages and commit completion to mbarriers.  Two issuers because the
+// barrier probes, fence and commit of a tile cost the issuing thread ~290 cycles in which it
+// feeds the tensor pipe nothing (tools/tc_smem.cu: 672 instead of 384 cycles per tile of 6
+// MMAs); with two threads one is always issuing (MMA + copy pipeline alone: 159 -> 134 ms on
+// 1M x 30).  The single-thread roles have the highest warp ids: a sub-partition's scheduler
+// picks the eligible warp with the highest id first.
 //
-// HBM tile format ("TC tile", 128 profiles): [hi image 8 KB][lo image 8 KB][scaled ||x||^2 128 f32]
-// [pad to 17 KB], images already in the swizzled shared-memory layout (8-row x 64 B atoms,
-// 16-byte chunk c of row r at c ^ ((r >> 1) & 3)) so that one bulk copy per tile is all the
-// producer does.  Query and candidate tiles differ in column D only.
+// HBM tile format ("TC tile", 128 profiles): NKB x [hi image 8 KB][lo image 8 KB], then
+// [scaled ||x||^2 128 f32][pad to 1 KB]; images already in the swizzled shared-memory layout
+// (8-row x 64 B atoms, 16-byte chunk c of row r at c ^ ((r >> 1) & 3)) so that one bulk copy
+// per K block is all the producer does.  Query and candidate tiles differ in column D only.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -47,7 +54,11 @@ constexpr int NACC = 4;                  // accumulator stages in tensor memory 
 __host__ __device__ constexpr int tile_bytes(int nkb) { return nkb * KB_B + 1024; }  // K blocks, then norms
 constexpr float QCOL = 8.0f;             // column D of a query row; a candidate row holds -||c||^2 / (2 QCOL)
 constexpr float PAD_COL = -60000.0f;     // column D of a padding candidate: u = -480000, below any real value
-constexpr int NTHREADS = 192;
+// Warp roles.  The scheduler of an SM sub-partition picks the eligible warp with the HIGHEST id first, so the
+// single-thread roles whose latency the whole pipeline waits on sit above the selection warps.
+constexpr int W_PROD = 4;                // warps 0..3: selection (TMEM lane quarter = warp id), 4: producer
+constexpr int W_ISSUE = 5;               // 5, 6: MMA issuers (even / odd candidate tiles)
+constexpr int NTHREADS = 224;
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     // K-major SWIZZLE_64B: LBO 1, SBO 512 B (8 rows x 64 B), descriptor version 1 (sm_100), layout type 4
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         bulk_g2s(Aimg, qtiles + (size_t)qt * TILE_B, TILE_B, qbar);
     }
     for (int e = tid; e < TM * kkp; e += NTHREADS) lists[e] = GMD_EMPTY_KEY;
-    if (warp == 1) {
+    if (warp == W_ISSUE) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ---- producer: ring item `it` = K block it % nkb of candidate tile it / nkb
         if (lane == 0) {
             // A stage that held the last K block of a tile is free when the tile's accumulator is
@@ -272,8 +283,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                 if (++s == ns) s = 0;
             }
         }
-    } else if (warp == 1) {
-        // ---- MMA issuer
+    } else if (warp >= W_ISSUE) {
+        // ---- MMA issuers: warp W_ISSUE takes the even candidate tiles, the next warp the odd ones.
+        // Tiles are independent (own accumulator stage, own ring stages) and tcgen05.commit tracks the
+        // committing thread's own MMAs.
         if (lane == 0) {
             mbar_wait(qbar, 0);
             // FP32 accumulator, FP16 A and B (format 0), both K-major, N = M = 128
@@ -281,9 +294,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             // descriptors differ only in the 16-byte-granular start address: build them once and add
             const uint64_t a_base = umma_desc(smem_u32(Aimg));
             const uint64_t b_base = umma_desc(smem_u32(Bst));
-            int s = 0;
+            // Two issuers need ns > nkb: an issuer only sees every other fill of a ring stage, and a parity
+            // wait is ambiguous if the fill before the awaited one may still be in flight.
+            const int nissue = (ns > nkb && !(dbg & 256)) ? 2 : 1;  // (dbg & 256: developer probe, one issuer)
+            const int first = warp - W_ISSUE;
+            int s = 0;                                     // ring stage and phase of item t * nkb
             uint32_t ph = 0;
-            for (int t = 0; t < ntiles_c; ++t) {
+            auto skip_tile = [&]() {
+                s += nkb;
+                while (s >= ns) s -= ns, ph ^= 1;
+            };
+            if (first) skip_tile();
+            if (first >= nissue) s = 0, ph = 0;
+            for (int t = first; t < (first < nissue ? ntiles_c : 0); t += nissue) {
                 const int a = t % NACC;
                 if (t >= NACC) mbar_wait(&tempty[a], ((t / NACC) - 1) & 1);
                 const uint32_t acc = tmem + (uint32_t)(a * TM);
@@ -305,6 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                     umma_commit(kb + 1 < nkb ? &sfree[s] : &tdone[a]);
                     if (++s == ns) s = 0, ph ^= 1;
                 }
+                if (nissue == 2) skip_tile();              // the other issuer's tile
             }
         }
     } else {
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
             auto process = [&](const uint32_t (&r)[32], int c0) {
-                if (dbg >= 1) return;  // developer probe: MMA + copy pipeline only
+                if (dbg >= 1 && dbg != 4) return;  // developer probe: MMA + copy pipeline only
                 // group maxima as trees (a chain of dependent ops is pure latency for the one
                 // selection warp of a scheduler), one vote per 32 columns
                 float gm[4];
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    if (warp == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 }  // namespace gmd_tc

@@ -8,7 +8,7 @@ x = synth.cfg_knn_rows(n, d, 5)
 xd = torch.from_numpy(x).cuda()
 pipe = engine.KnnPipeline(n, n, d, k, "euclidean", _lib.FORM_TC, same=True)
 pipe.reset(); pipe.col_mean(xd); pipe.prep_candidates(xd); pipe.prep_queries(xd)
-for dbg in ("0", "1", "2", "4"):
+for dbg in (sys.argv[4:] or ("0", "1", "2", "4")):
     os.environ["GMD_TC_DBG"] = dbg
     best = 1e9
     for r in range(3):
