@@ -42,6 +42,10 @@ SIGNATURES = {
     "gmd_scan_tc_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_refine_topk_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_prep_tc_perm_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_scan_tc_sweep_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "gmd_order_workspace_bytes": (_sz, [_int]),
+    "gmd_order_by_key": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "gmd_exact_workspace_bytes": (_sz, [_i64]),
     "gmd_exact_rows_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gmd_knn_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),

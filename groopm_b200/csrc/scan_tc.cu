@@ -137,18 +137,21 @@ __global__ void __launch_bounds__(256) tc_norms_kernel(const double* __restrict_
 // QCOL), role 1: candidate tile (column D = -||x||^2 / (2 QCOL), in scaled units).
 // stats_c / stats_q: max ||x||^2 of the two sets.
 __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long N, int D, int nkb,
+                                                      const uint32_t* __restrict__ perm,
                                                       const double* __restrict__ center, int role,
                                                       const float* __restrict__ stats_c, const float* __restrict__ stats_q,
                                                       unsigned char* __restrict__ tiles) {
     __shared__ float s_n2[TM];
     const float scale = ldexpf(1.0f, gmd_tc_exponent(stats_c[0], stats_q[0]));
     const long long t = blockIdx.x, row0 = t * TM;
+    // perm (nullable): tile position -> row of X, for profiles staged in a locality-preserving order
     if (threadIdx.x < TM) {
         const long long row = row0 + threadIdx.x;
         double n2 = 0.0;
         if (row < N) {
+            const size_t src = perm ? perm[row] : (size_t)row;
             for (int k = 0; k < D; ++k) {
-                const double v = (double)((float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0)) * scale);
+                const double v = (double)((float)(X[src * D + k] - (center ? center[k] : 0.0)) * scale);
                 n2 += v * v;
             }
         }
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
         float v = 0.0f;
         if (row < N) {
             if (k < D)
-                v = (float)(X[(size_t)row * D + k] - (center ? center[k] : 0.0)) * scale;   // exact: power of two
+                v = (float)(X[(perm ? (size_t)perm[row] : (size_t)row) * D + k] - (center ? center[k] : 0.0)) * scale;   // exact: power of two
             else if (k == D)
                 v = role == 0 ? QCOL : -s_n2[r] / (2.0f * QCOL);
         } else if (k == D) {
@@ -201,11 +204,17 @@ static __device__ __noinline__ float drain_own(uint64_t* h, int kk, const uint2*
 // nkb: K blocks per tile (1 for D <= 31 ... 5 for D = 136); ns: ring stages of one K block each.
 // NKB is a template parameter: with a run-time K-block loop the issuing thread falls behind the tensor
 // pipe (1M x 30: 196 ms instead of 159 ms with selection off).
-template <int NKB>
+// SWEEP: the profiles were staged in a locality-preserving order (perm[position] = original row, the
+// same for queries and candidates) and every CTA starts its sweep over the candidate tiles at its own
+// query tile, wrapping around: a query meets its neighbourhood first, its threshold is near-final after a
+// few tiles, and hits become rare (tools/sim_hits.py: a vote fires in ~20 instead of ~2960 of 7813
+// tiles).  The selection warps then use the variant that is fastest when nothing hits: all 16 group
+// maxima and ONE vote per tile.  Proposals are written under the ORIGINAL row numbers.
+template <int NKB, bool SWEEP>
 __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned char* __restrict__ qtiles,
                                                               const unsigned char* __restrict__ ctiles,
                                                               long long Nq, long long Nc, int ntiles_c, int kk,
-                                                              int ns,
+                                                              int ns, const uint32_t* __restrict__ perm,
                                                               long long c_index_offset, int dbg,
                                                               const float* __restrict__ stats_c,
                                                               const float* __restrict__ stats_q,
@@ -231,6 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kkp = kk | 1;
     const long long qt = blockIdx.x;
+    const int t_first = SWEEP ? (int)(qt % ntiles_c) : 0;   // sweep step t visits tile (t_first + t) mod ntiles_c
 
     if (tid == 0) {
         for (int s = 0; s < ns; ++s) {
@@ -276,9 +286,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                     }
                     if (++pkb == nkb) pkb = 0, ++pt;
                 }
-                const uint32_t bytes = dbg == 2 ? 1024u : (uint32_t)KB_B;  // (2: developer probe, no candidate traffic)
+                const uint32_t bytes = (dbg & 15) == 2 ? 1024u : (uint32_t)KB_B;  // (2: developer probe, no candidate traffic)
                 mbar_expect_tx(&full[s], bytes);
-                bulk_g2s(Bst + (size_t)s * KB_B, ctiles + (size_t)t * TILE_B + (size_t)kb * KB_B, bytes, &full[s]);
+                const int ta = t + t_first < ntiles_c ? t + t_first : t + t_first - ntiles_c;
+                bulk_g2s(Bst + (size_t)s * KB_B, ctiles + (size_t)ta * TILE_B + (size_t)kb * KB_B, bytes, &full[s]);
                 if (++kb == nkb) kb = 0, ++t;
                 if (++s == ns) s = 0;
             }
@@ -341,12 +352,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         float thr = __int_as_float(0x7f800000);
         constexpr unsigned FULLW = 0xFFFFFFFFu;
         float uthr = __int_as_float(0xff800000);            // -thr / 2: the accumulators are u = -s/2
-        if (dbg == 4) uthr = __int_as_float(0x7f800000);    // developer probe: nothing ever hits
+        if ((dbg & 15) == 4) uthr = __int_as_float(0x7f800000);    // developer probe: nothing ever hits
         for (int t = 0; t < ntiles_c; ++t) {
             const int a = t % NACC;
             mbar_wait(&tdone[a], (t / NACC) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t cbase = (uint32_t)t * TM;
+            const uint32_t cbase = (uint32_t)(t + t_first < ntiles_c ? t + t_first : t + t_first - ntiles_c) * TM;
             const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TM);
             // all 128 columns of the row in flight at once, then the accumulator stage goes back
             uint32_t r0[32], r1[32], r2[32], r3[32];
@@ -361,31 +372,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
-            auto process = [&](const uint32_t (&r)[32], int c0) {
-                if (dbg >= 1 && dbg != 4) return;  // developer probe: MMA + copy pipeline only
-                // group maxima as trees (a chain of dependent ops is pure latency for the one
-                // selection warp of a scheduler), one vote per 32 columns
-                float gm[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float m01 = fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
-                    const float m23 = fmaxf(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-                    const float m45 = fmaxf(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-                    const float m67 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-                    gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
-                }
-                const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-                if (__any_sync(FULLW, cm > uthr)) {
-                    // 8 values at a time: park what beats the (possibly stale) threshold, drain all
-                    // the warp's queues side by side when one of them is half full
+            if constexpr (SWEEP) {
+                if ((dbg & 15) >= 1 && (dbg & 15) != 4) continue;  // developer probe: MMA + copy pipeline only
+                // Maxima of the 16 groups of 8 columns first, as shallow trees with all 128 values in
+                // flight (a dependent chain or a vote-and-branch per 32 columns is pure latency for the one
+                // selection warp of a scheduler: 430 instead of ~200 cycles per tile), then ONE vote.
+                float gm[16];
+                auto tree = [&](const uint32_t (&r)[32], int b) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        if (__any_sync(FULLW, gm[g] > uthr)) {
+                        const float m0 = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
+                        const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4])), __uint_as_float(r[8 * g + 5]));
+                        const float m2 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                        gm[4 * b + g] = fmaxf(fmaxf(m0, m1), m2);
+                    }
+                };
+                tree(r0, 0);
+                tree(r1, 1);
+                tree(r2, 2);
+                tree(r3, 3);
+                float cm;
+                {
+                    const float a0 = fmaxf(fmaxf(gm[0], gm[1]), gm[2]), a1 = fmaxf(fmaxf(gm[3], gm[4]), gm[5]);
+                    const float a2 = fmaxf(fmaxf(gm[6], gm[7]), gm[8]), a3 = fmaxf(fmaxf(gm[9], gm[10]), gm[11]);
+                    const float a4 = fmaxf(fmaxf(gm[12], gm[13]), gm[14]);
+                    cm = fmaxf(fmaxf(fmaxf(a0, a1), a2), fmaxf(fmaxf(a3, a4), gm[15]));
+                }
+                if (!__any_sync(FULLW, cm > uthr)) continue;
+                // which groups hold a hit for any lane: one warp-wide OR instead of 16 votes
+                unsigned mine = 0;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
+                const unsigned hot = __reduce_or_sync(FULLW, mine);
+                // 8 values at a time: park what beats the (possibly stale) threshold, drain all the warp's
+                // queues side by side when one of them is half full
+                auto park = [&](const uint32_t (&r)[32], int b) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (hot & (1u << (4 * b + g))) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float u = __uint_as_float(r[8 * g + j]);
                                 if (u > uthr) {
-                                    myq[cnt * TM] = make_uint2(cbase + c0 + 8 * g + j, __float_as_uint(-2.0f * u));
+                                    myq[cnt * TM] = make_uint2(cbase + 32 * b + 8 * g + j, __float_as_uint(-2.0f * u));
                                     ++cnt;
                                 }
                             }
@@ -396,17 +425,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                             }
                         }
                     }
-                }
-            };
-            process(r0, 0);
-            process(r1, 32);
-            process(r2, 64);
-            process(r3, 96);
+                };
+                park(r0, 0);
+                park(r1, 1);
+                park(r2, 2);
+                park(r3, 3);
+            } else {
+                auto process = [&](const uint32_t (&r)[32], int c0) {
+                    if ((dbg & 15) >= 1 && (dbg & 15) != 4) return;  // developer probe: MMA + copy pipeline only
+                    // group maxima as trees (a chain of dependent ops is pure latency for the one
+                    // selection warp of a scheduler), one vote per 32 columns
+                    float gm[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float m01 = fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
+                        const float m23 = fmaxf(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+                        const float m45 = fmaxf(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+                        const float m67 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                        gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+                    }
+                    const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+                    if (__any_sync(FULLW, cm > uthr)) {
+                        // 8 values at a time: park what beats the (possibly stale) threshold, drain all
+                        // the warp's queues side by side when one of them is half full
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (__any_sync(FULLW, gm[g] > uthr)) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float u = __uint_as_float(r[8 * g + j]);
+                                    if (u > uthr) {
+                                        myq[cnt * TM] = make_uint2(cbase + c0 + 8 * g + j, __float_as_uint(-2.0f * u));
+                                        ++cnt;
+                                    }
+                                }
+                                if (__any_sync(FULLW, cnt > TQ - 8)) {
+                                    thr = drain_own(h, kk, myq, cnt);
+                                    uthr = -0.5f * thr;
+                                    cnt = 0;
+                                }
+                            }
+                        }
+                    }
+                };
+                process(r0, 0);
+                process(r1, 32);
+                process(r2, 64);
+                process(r3, 96);
+            }
         }
         thr = drain_own(h, kk, myq, cnt);
         // ---- write this query's proposals
-        const long long q = qt * TM + row;
-        if (q < Nq) {
+        const long long qpos = qt * TM + row;
+        if (qpos < Nq) {
+            const long long q = (SWEEP && perm) ? (long long)perm[qpos] : qpos;
             // back to the caller's units: everything above ran on rows scaled by 2^e
             const float unscale = ldexpf(1.0f, -2 * gmd_tc_exponent(stats_c[0], stats_q[0]));
             const float qnv = reinterpret_cast<const float*>(Aimg + (size_t)nkb * KB_B)[row];
@@ -417,7 +489,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                 float vv = gmd_unflip((uint32_t)(key >> 32));
                 uint32_t oi = GMD_EMPTY_IDX;
                 if (key != GMD_EMPTY_KEY && (long long)li < Nc) {
-                    oi = li + (uint32_t)c_index_offset;
+                    oi = ((SWEEP && perm) ? perm[li] : li) + (uint32_t)c_index_offset;
                     vv = fmaxf(vv + qnv, 0.0f) * unscale;
                 } else {
                     vv = __int_as_float(0x7f800000);
@@ -458,24 +530,32 @@ extern "C" int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double*
     return GMD_OK;
 }
 
-extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role,
-                               const float* stats_c, const float* stats_q, void* tiles, void* stream) {
+extern "C" int gmd_prep_tc_perm_f64(const double* X, int64_t N, int D, const double* center, int role,
+                                    const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
+                                    void* stream) {
     GMD_REQUIRE(X && tiles && stats_c && stats_q && N > 0 && D >= 1 && tc_nkb(D) <= gmd_tc::MAX_KB &&
                     (role == 0 || role == 1),
                 GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
     const unsigned grid = (unsigned)((N + gmd_tc::TM - 1) / gmd_tc::TM);
-    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, tc_nkb(D), center, role, stats_c, stats_q,
-                                                                  (unsigned char*)tiles);
+    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, tc_nkb(D), perm, center, role, stats_c,
+                                                                  stats_q, (unsigned char*)tiles);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }
 
-extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
-                               int64_t c_index_offset, const float* stats_c, const float* stats_q, uint32_t* cand_idx,
-                               float* cand_val, float* cand_tau, void* stream) {
+extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role,
+                               const float* stats_c, const float* stats_q, void* tiles, void* stream) {
+    return gmd_prep_tc_perm_f64(X, N, D, center, role, stats_c, stats_q, nullptr, tiles, stream);
+}
+
+extern "C" int gmd_scan_tc_sweep_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
+                                     int64_t c_index_offset, const float* stats_c, const float* stats_q,
+                                     const uint32_t* perm, int sweep, uint32_t* cand_idx, float* cand_val,
+                                     float* cand_tau, void* stream) {
     GMD_REQUIRE(qtiles && ctiles && stats_c && stats_q && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG,
                 "scan_tc: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll, GMD_ERR_BAD_ARG, "scan_tc: bad sizes");
+    GMD_REQUIRE(!sweep || !perm || Nq == Nc, GMD_ERR_BAD_ARG, "scan_tc: one permutation serves queries and candidates");
     using namespace gmd_tc;
     const int nkb = tc_nkb(D);
     GMD_REQUIRE(D >= 1 && nkb <= MAX_KB && kk >= 1 && kk <= 96, GMD_ERR_UNSUPPORTED, "scan_tc: D=%d kk=%d", D, kk);
@@ -490,19 +570,31 @@ extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctile
     auto launch = [&](auto kern) -> int {
         GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>((const unsigned char*)qtiles, (const unsigned char*)ctiles,
-                                                           Nq, Nc, ntiles_c, kk, ns, c_index_offset, dbg, stats_c,
-                                                           stats_q, cand_idx, cand_val, cand_tau);
+                                                           Nq, Nc, ntiles_c, kk, ns, perm, c_index_offset, dbg,
+                                                           stats_c, stats_q, cand_idx, cand_val, cand_tau);
         return GMD_OK;
     };
     int rc;
-    switch (nkb) {
-        case 1: rc = launch(scan_tc_kernel<1>); break;
-        case 2: rc = launch(scan_tc_kernel<2>); break;
-        case 3: rc = launch(scan_tc_kernel<3>); break;
-        case 4: rc = launch(scan_tc_kernel<4>); break;
-        default: rc = launch(scan_tc_kernel<5>); break;
+    switch (nkb * 2 + (sweep ? 1 : 0)) {
+        case 2: rc = launch(scan_tc_kernel<1, false>); break;
+        case 3: rc = launch(scan_tc_kernel<1, true>); break;
+        case 4: rc = launch(scan_tc_kernel<2, false>); break;
+        case 5: rc = launch(scan_tc_kernel<2, true>); break;
+        case 6: rc = launch(scan_tc_kernel<3, false>); break;
+        case 7: rc = launch(scan_tc_kernel<3, true>); break;
+        case 8: rc = launch(scan_tc_kernel<4, false>); break;
+        case 9: rc = launch(scan_tc_kernel<4, true>); break;
+        case 10: rc = launch(scan_tc_kernel<5, false>); break;
+        default: rc = launch(scan_tc_kernel<5, true>); break;
     }
     if (rc != GMD_OK) return rc;
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
+}
+
+extern "C" int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
+                               int64_t c_index_offset, const float* stats_c, const float* stats_q, uint32_t* cand_idx,
+                               float* cand_val, float* cand_tau, void* stream) {
+    return gmd_scan_tc_sweep_f32(qtiles, Nq, ctiles, Nc, D, kk, c_index_offset, stats_c, stats_q, nullptr, 0, cand_idx,
+                                 cand_val, cand_tau, stream);
 }

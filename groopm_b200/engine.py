@@ -7,6 +7,8 @@ reached through the C ABI of ``libgmdist.so`` with raw device pointers.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional
 
@@ -73,7 +75,7 @@ class KnnPipeline:
     """
 
     def __init__(self, nq: int, nc: int, d: int, k: int, metric="euclidean", form: Optional[int] = None,
-                 same: bool = False, device=None):
+                 same: bool = False, device=None, order: Optional[bool] = None):
         self.lib = _lib.lib()
         self.dev = _device(device)
         self.nq, self.nc, self.d, self.k = int(nq), int(nc), int(d), int(k)
@@ -126,6 +128,22 @@ class KnnPipeline:
         self.cand_tau = torch.empty(self.nq * self.nsplit, dtype=torch.float32, **e)
         self.fail_rows = torch.empty(self.nq, dtype=torch.int32, **e)
         self.exact_ws = torch.empty(self.lib.gmd_exact_workspace_bytes(self.nq) // 4, dtype=torch.int32, **e)
+        # Locality-ordered sweep of the tensor-core scan (all-pairs only; opt-in: order=True or
+        # GMD_TC_ORDER=1).  Profiles are grouped by their nearest of ~N/1024 sampled profiles (an
+        # inner k = 1 pipeline of this engine), staged in that order, and every query tile starts
+        # its sweep at its own position; proposals come back under the original row numbers.
+        if order is None:
+            order = os.environ.get("GMD_TC_ORDER", "0") == "1"
+        self.order = bool(order and self.tc and self.same and self.nc >= 4096)
+        if self.order:
+            ncl = 64
+            while ncl < 4096 and ncl * 1024 < self.nc:
+                ncl *= 2
+            self.order_ncl = ncl
+            self.key_pipe = KnnPipeline(self.nc, ncl, self.d, 1, "euclidean", None, same=False, device=self.dev,
+                                        order=False)
+            self.perm = torch.empty(self.nc, dtype=torch.int32, **e)
+            self.order_ws = torch.empty(self.lib.gmd_order_workspace_bytes(ncl) // 4, dtype=torch.int32, **e)
         self.out_idx = torch.empty((self.nq, self.k), dtype=torch.int32, **e)
         self.out_dist = torch.empty((self.nq, self.k), dtype=torch.float64, **e)
 
@@ -155,10 +173,19 @@ class KnnPipeline:
                                                      _stream_ptr()))
             # pass 2 for both roles, now that both sets' norms are known
             c = self._tc_c
-            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(c), self.nc, self.d, _ptr(self.center), 1, _ptr(self.stats), sq,
-                                                _ptr(self.ctiles), _stream_ptr()))
-            _lib.check(self.lib.gmd_prep_tc_f64(_ptr(q), self.nq, self.d, _ptr(self.center), 0, _ptr(self.stats), sq,
-                                                _ptr(self.qtiles), _stream_ptr()))
+            perm = 0
+            if self.order:
+                # staging order: nearest sampled profile as the key, counting sort by key
+                stride = self.nc // self.order_ncl
+                cent = c[::stride][:self.order_ncl].contiguous()
+                key, _ = self.key_pipe.run(c, cent)
+                _lib.check(self.lib.gmd_order_by_key(_ptr(key), self.nc, self.order_ncl, _ptr(self.perm),
+                                                     _ptr(self.order_ws), self.order_ws.numel() * 4, _stream_ptr()))
+                perm = _ptr(self.perm)
+            _lib.check(self.lib.gmd_prep_tc_perm_f64(_ptr(c), self.nc, self.d, _ptr(self.center), 1, _ptr(self.stats),
+                                                     sq, perm, _ptr(self.ctiles), _stream_ptr()))
+            _lib.check(self.lib.gmd_prep_tc_perm_f64(_ptr(q), self.nq, self.d, _ptr(self.center), 0, _ptr(self.stats),
+                                                     sq, perm, _ptr(self.qtiles), _stream_ptr()))
             self._tc_c = None
             return
         if self.same:
@@ -168,9 +195,10 @@ class KnnPipeline:
 
     def scan(self):
         if self.tc:
-            _lib.check(self.lib.gmd_scan_tc_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, self.kk,
-                                                0, _ptr(self.stats), _ptr(self.stats) + 8, _ptr(self.cand_idx),
-                                                _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))
+            _lib.check(self.lib.gmd_scan_tc_sweep_f32(
+                _ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, self.kk, 0, _ptr(self.stats),
+                _ptr(self.stats) + 8, _ptr(self.perm) if self.order else 0, 1 if self.order else 0,
+                _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))
             return
         if self.bmu:
             _lib.check(self.lib.gmd_scan_bmu_f32(_ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, 0,
@@ -220,12 +248,14 @@ class KnnPipeline:
     def launches_per_run(self) -> int:
         # the exact stage is three kernels: batched pass, its finish, one-row-per-block remainder
         if self.tc:
-            return 9 if self.same else 10     # col_mean, norms x1/2, prep x2, scan, refine, exact x3
+            # col_mean, norms x1/2, prep x2, scan, refine, exact x3 (+ the key pipeline and 3 sort kernels)
+            extra = (self.key_pipe.launches_per_run + 3) if self.order else 0
+            return (9 if self.same else 10) + extra
         return 7 if self.same else 8
 
 
 def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, device=None,
-        return_info: bool = False):
+        return_info: bool = False, order: Optional[bool] = None):
     """k nearest rows of ``c`` for every row of ``q``; ascending (distance, index).
 
     ``c=None`` means all-pairs within ``q`` (self included at rank 0, as in
@@ -245,7 +275,8 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
     with torch.cuda.device(dev):
         qd = qt.to(dev, non_blocking=True)
         cd = qd if same else ct.to(dev, non_blocking=True)
-        pipe = KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, form, same=same, device=dev)
+        pipe = KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, form, same=same, device=dev,
+                           order=order)
         idx, dist = pipe.run(qd, cd)
         if q_np:
             idx_h, dist_h = idx.cpu().numpy(), dist.cpu().numpy()  # synchronises
@@ -258,7 +289,7 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
             out = (idx, dist)
         if return_info:
             return out + ({"exact_rows": pipe.exact_row_count(), "form": pipe.form, "kk": pipe.kk,
-                           "nsplit": pipe.nsplit},)
+                           "nsplit": pipe.nsplit, "ordered": pipe.order},)
         return out
 
 

@@ -153,6 +153,26 @@ GMD_API int gmd_scan_tc_f32(const void* qtiles, int64_t Nq, const void* ctiles, 
                     int64_t c_index_offset, const float* stats_c, const float* stats_q, uint32_t* cand_idx,
                     float* cand_val, float* cand_tau, void* stream);
 
+/* Locality-ordered sweep of the tensor-core scan (all-pairs: queries == candidates).
+ * gmd_order_by_key: counting sort of the rows by a small integer key (0 <= key < nkeys; the
+ * engine uses the nearest of ~N/1024 sampled profiles): perm[position] = row.
+ * gmd_prep_tc_perm_f64 stages tiles in that order (perm NULL: as gmd_prep_tc_f64).
+ * gmd_scan_tc_sweep_f32 with sweep != 0: the CTA of query tile t visits the candidate tiles
+ * t, t+1, ... wrapping around, so a query meets its neighbourhood first and few later
+ * candidates beat its threshold; proposals (cand_idx rows and values) are written under the
+ * ORIGINAL row numbers (perm NULL: positions are row numbers).  Everything downstream
+ * (gmd_refine_topk_f64 / gmd_exact_rows_f64) is unchanged, and so are the results.        */
+GMD_API size_t gmd_order_workspace_bytes(int nkeys);
+GMD_API int gmd_order_by_key(const int32_t* key, int64_t N, int nkeys, uint32_t* perm, void* workspace,
+                     size_t workspace_bytes, void* stream);
+GMD_API int gmd_prep_tc_perm_f64(const double* X, int64_t N, int D, const double* center, int role,
+                     const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
+                     void* stream);
+GMD_API int gmd_scan_tc_sweep_f32(const void* qtiles, int64_t Nq, const void* ctiles, int64_t Nc, int D, int kk,
+                     int64_t c_index_offset, const float* stats_c, const float* stats_q,
+                     const uint32_t* perm, int sweep, uint32_t* cand_idx, float* cand_val,
+                     float* cand_tau, void* stream);
+
 /* float64 re-rank of the proposed candidates from the ORIGINAL rows, lowest-index tie
  * rule, plus the per-row certificate; uncertified rows are appended to fail_rows
  * (count in fail_count[0]) and finished by gmd_exact_rows_f64.                        */

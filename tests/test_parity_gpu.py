@@ -489,6 +489,40 @@ def test_tensor_core_scan_vs_oracle(cuda, n, nq, d, k):
     assert np.array_equal(dist, od)
 
 
+@pytest.mark.parametrize("n,d,k", [(6000, 10, 16), (20000, 30, 32), (5000, 100, 8), (4097, 4, 2), (9000, 136, 5)])
+def test_tensor_core_ordered_sweep_vs_oracle(cuda, n, d, k):
+    """The locality-ordered sweep (profiles staged by nearest sampled profile, every query tile starts at
+    its own position, proposals mapped back to the original rows) must not change a single index or
+    distance -- clustered rows, duplicates and a tie mass included."""
+    rng = np.random.default_rng(31 * n + d)
+    centres = rng.standard_normal((23, d)) * 6.0
+    c = centres[rng.integers(0, 23, size=n)] + rng.standard_normal((n, d)) * rng.uniform(0.05, 1.0, size=d)
+    synth.add_duplicates(c, rng, 0.01)
+    c[100:160] = c[100]                                   # 60 identical rows: lowest-index rule under a permutation
+    idx, dist, info = engine.knn(c, None, k=k, form=_lib.FORM_TC, order=True, return_info=True)
+    assert info["form"] == _lib.FORM_TC and info["ordered"]
+    od, oi = oracle.knn(c, c, k)
+    assert_knn_parity(c, c, idx, dist, oi, od)
+    assert np.array_equal(dist, od)
+    idx0, dist0 = engine.knn(c, None, k=k, form=_lib.FORM_TC, order=False)
+    assert np.array_equal(idx, idx0) and np.array_equal(dist, dist0)
+
+
+def test_order_by_key_is_a_grouping_permutation(cuda):
+    import torch
+    lib = _lib.lib()
+    n, nkeys = 100_003, 257
+    key = torch.randint(0, nkeys, (n,), dtype=torch.int32, device="cuda")
+    perm = torch.empty(n, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.gmd_order_workspace_bytes(nkeys) // 4, dtype=torch.int32, device="cuda")
+    _lib.check(lib.gmd_order_by_key(key.data_ptr(), n, nkeys, perm.data_ptr(), ws.data_ptr(), ws.numel() * 4, None))
+    torch.cuda.synchronize()
+    p = perm.cpu().numpy().astype(np.int64)
+    assert np.array_equal(np.sort(p), np.arange(n))        # a permutation
+    ks = key.cpu().numpy()[p]
+    assert np.all(np.diff(ks) >= 0)                         # rows of a key are contiguous, keys ascending
+
+
 def test_tensor_core_scan_limits_and_policy(cuda):
     lib = _lib.lib()
     assert lib.gmd_tc_supported(16, _lib.L2, 31) == 1 and lib.gmd_tc_supported(16, _lib.L2, 32) == 1
