@@ -141,6 +141,45 @@ def c_dist_between(cov1, cov2):
     return float(np.median(v)) if len(v) else float("nan")
 
 
+def evenly_spaced_pts_z(transformed_cp, row_indices, sample_size: int):
+    """RefineEngine.getEvenlySpacedPtsZ (refine.py:1505-1516): ``sample_size`` of the rows, spread
+    evenly along the Z axis (last column) of the transformed coverage space.  Host logic; the
+    positions are the truncations of the reference's RUNNING float sum (0, s, s+s, ...), which
+    is not always ``int(i * s)``."""
+    row_indices = np.asarray(row_indices)
+    by_z = np.argsort(np.asarray(transformed_cp)[row_indices, -1])
+    step = float(len(row_indices)) / sample_size
+    pos, acc = [], 0.0
+    for _ in range(sample_size):
+        pos.append(int(acc))
+        acc += step
+    return row_indices[by_z[np.array(pos, dtype=np.int64)]]
+
+
+def _c_pick(transformed_cp, row_indices, max_in_bin: int = 100):
+    row_indices = np.asarray(row_indices)
+    if len(row_indices) > max_in_bin:
+        return evenly_spaced_pts_z(transformed_cp, row_indices, max_in_bin)
+    return row_indices
+
+
+def c_dist_rows(cov_profiles, transformed_cp, row_indices):
+    """RefineEngine.cDist (refine.py:1528-1551) from a bin's row indices: at most 100 rows, picked
+    evenly along Z when the bin is larger, then the median angle over the pairs."""
+    return c_dist(np.asarray(cov_profiles)[_c_pick(transformed_cp, row_indices)])
+
+
+def c_dist_between_rows(cov_profiles, transformed_cp, rows1, rows2):
+    """RefineEngine.cDistBetweenBins (refine.py:1557-1583) from two bins' row indices."""
+    cov = np.asarray(cov_profiles)
+    return c_dist_between(cov[_c_pick(transformed_cp, rows1)], cov[_c_pick(transformed_cp, rows2)])
+
+
+def c_dist_merged_rows(cov_profiles, transformed_cp, rows1, rows2):
+    """RefineEngine.cDistMergedBins (refine.py:1553-1555)."""
+    return c_dist_rows(cov_profiles, transformed_cp, np.concatenate((np.asarray(rows1), np.asarray(rows2))))
+
+
 # ------------------------------------------------------------------ binManager.py
 
 def vq(obs, code_book):

@@ -14,7 +14,8 @@ __all__ = [
     "best_match", "bmu_batch", "classify_contigs", "som_train_bmus",
     "whiten", "allpairs_cityblock", "kth_neighbour_radius", "radius_neighbours",
     "contraction_weights", "two_way_contraction_step", "kdtree_knn", "knn",
-    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal", "som_stamp", "som_train", "c_dist", "c_dist_between", "vq",
+    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal", "som_stamp", "som_train", "c_dist", "c_dist_between", "evenly_spaced_pts_z", "c_dist_rows", "c_dist_between_rows",
+    "c_dist_merged_rows", "vq",
 ]
 
 
@@ -361,6 +362,44 @@ def c_dist_between(cov1: np.ndarray, cov2: np.ndarray):
             if a is not None:
                 angles.append(a)
     return float(np.median(angles)) if angles else float("nan")
+
+
+def evenly_spaced_pts_z(transformed_cp: np.ndarray, row_indices, sample_size: int):
+    """RefineEngine.getEvenlySpacedPtsZ, refine.py:1505-1516: ``sample_size`` rows spread evenly
+    along the Z axis (last column) of the transformed coverage space."""
+    row_indices = np.asarray(row_indices)
+    sorted_indices = np.argsort(transformed_cp[row_indices, -1])
+    step_size = float(len(row_indices)) / sample_size
+    si = []
+    index = 0.0
+    for _ in range(sample_size):
+        si.append(row_indices[sorted_indices[int(index)]])
+        index += step_size
+    return np.array(si)
+
+
+def _c_pick(transformed_cp, row_indices, max_in_bin=100):
+    """The row selection at the head of cDist / cDistBetweenBins (refine.py:1529-1536, 1558-1568)."""
+    row_indices = np.asarray(row_indices)
+    if len(row_indices) > max_in_bin:
+        return evenly_spaced_pts_z(transformed_cp, row_indices, max_in_bin)
+    return row_indices
+
+
+def c_dist_rows(cov_profiles, transformed_cp, row_indices):
+    """RefineEngine.cDist (refine.py:1528-1551) from the row indices of a bin."""
+    return c_dist(np.asarray(cov_profiles)[_c_pick(transformed_cp, row_indices)])
+
+
+def c_dist_between_rows(cov_profiles, transformed_cp, rows1, rows2):
+    """RefineEngine.cDistBetweenBins (refine.py:1557-1583) from the row indices of two bins."""
+    cov = np.asarray(cov_profiles)
+    return c_dist_between(cov[_c_pick(transformed_cp, rows1)], cov[_c_pick(transformed_cp, rows2)])
+
+
+def c_dist_merged_rows(cov_profiles, transformed_cp, rows1, rows2):
+    """RefineEngine.cDistMergedBins (refine.py:1553-1555)."""
+    return c_dist_rows(cov_profiles, transformed_cp, np.concatenate((rows1, rows2)))
 
 
 def vq(obs: np.ndarray, code_book: np.ndarray):

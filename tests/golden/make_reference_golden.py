@@ -23,6 +23,9 @@ straight from ``/root/reference/groopm`` (nothing is copied into this repository
                                        sys.settrace at the first line after the two
                                        contraction loops, then aborted before the Hough code)
         RefineEngine.kDist / kDistBetweenBins / kDistMergedBins  refine.py:1490-1503
+        RefineEngine.getEvenlySpacedPtsZ / cDist / cDistBetweenBins / cDistMergedBins
+                                       refine.py:1505-1583 (bins below and above the 100-row
+                                       sampling limit, a zero-coverage row for the dropped pairs)
 
 Outputs: ``tests/golden/ref_*.npz`` (inputs + the reference's outputs).  The CPU tests
 check ``oracle/`` against them, the GPU tests check the engine against them, so parity is
@@ -258,6 +261,48 @@ def gen_kdist(mods, rng):
     print("ref_kdist:", kd, kb[:3])
 
 
+def gen_cdist(mods, rng):
+    sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
+    from groopm_b200 import synth
+
+    RE = mods["refine"].RefineEngine
+    n, s_ = 3000, 6
+    with np.errstate(divide='warn', over='warn', under='ignore', invalid='warn'):
+        cov = synth.coverage_profiles(n, s_, 9)
+        cov[17] = 0.0                                      # a contig without coverage: its pairs raise and are dropped
+        cov[1200] = cov[40]                                # identical profiles: arccos of (almost) 1
+        tcp = synth.transform_cp(np.where(cov.sum(axis=1, keepdims=True) > 0, cov, 1.0))
+        norms = np.array([np.linalg.norm(r) for r in cov])
+    eng = object.__new__(RE)
+    eng.PM = types.SimpleNamespace(covProfiles=cov, normCoverages=norms, transformedCP=tcp)
+    rows = [np.sort(rng.choice(n, m, replace=False)) for m in (2, 57, 100, 101, 350)]
+    rows.append(np.array([17, 40, 1200, 5, 900]))          # holds the zero row and the identical pair
+    rows.append(np.array([17, 3]))                          # every pair dropped -> median of nothing
+    B = lambda r: types.SimpleNamespace(rowIndices=r)       # noqa: E731
+    old = np.seterr(all='raise')                            # the reference's global setting (torusMesh.py:57)
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                 # np.median([]) warns and returns nan
+            cd = []
+            for r in rows:
+                try:
+                    cd.append(float(eng.cDist(r)))
+                except FloatingPointError:                  # np.median([]) under seterr(all='raise')
+                    cd.append(np.nan)
+            picks = [np.array(eng.getEvenlySpacedPtsZ(r, 100)) if len(r) > 100 else np.array(r) for r in rows]
+            pairs = [(0, 1), (1, 2), (3, 4), (4, 1), (5, 1), (2, 2)]
+            cb = [float(eng.cDistBetweenBins(B(rows[a]), B(rows[b]))) for a, b in pairs]
+            cm = [float(eng.cDistMergedBins(B(rows[a]), B(rows[b]))) for a, b in pairs[:3]]
+    finally:
+        np.seterr(**old)
+    arrs = {f"rows{i}": r for i, r in enumerate(rows)}
+    arrs.update({f"pick{i}": p for i, p in enumerate(picks)})
+    np.savez_compressed(OUT / "ref_cdist.npz", cov=cov, tcp=tcp, n_sets=len(rows), c_dist=np.array(cd),
+                        pairs=np.array(pairs), c_dist_between=np.array(cb), c_dist_merged=np.array(cm), **arrs)
+    print("ref_cdist:", cd, cb[:3], cm)
+
+
 def main():
     if not REF.exists():
         raise SystemExit("the reference is not mounted here; the committed ref_*.npz files are the product of this script")
@@ -270,6 +315,7 @@ def main():
     gen_som_train(mods, rng)
     gen_contraction(mods, rng)
     gen_kdist(mods, rng)
+    gen_cdist(mods, np.random.default_rng(20261020))
 
 
 if __name__ == "__main__":

@@ -4,7 +4,8 @@
 which executes the reference's own ``TorusMesh.bestMatch`` (torusMesh.py:123-130),
 ``SOM.classifyContig`` (som.py:572-575), ``ClusterEngine.twoWayContraction``
 (cluster.py:411-600) and ``RefineEngine.kDist`` / ``kDistBetweenBins`` / ``kDistMergedBins``
-(refine.py:1490-1503) from /root/reference under Python 3.  Inputs travel inside the
+(refine.py:1490-1503) and ``getEvenlySpacedPtsZ`` / ``cDist`` / ``cDistBetweenBins`` / ``cDistMergedBins``
+(refine.py:1505-1583) from /root/reference under Python 3.  Inputs travel inside the
 fixtures, so nothing here depends on regenerating them or on /root/reference."""
 import numpy as np
 import pytest
@@ -180,3 +181,65 @@ def test_engine_som_train_equals_oracle_larger(cuda):
     np.random.seed(4)
     got = engine.som_train(None, block[:700], weights=w0, iterations=8, radius=5.0, influence_rate=0.2)
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- f4: cDist family (refine.py:1505-1583)
+
+def _cdist_sets(g):
+    return [g[f"rows{i}"] for i in range(int(g["n_sets"]))], [g[f"pick{i}"] for i in range(int(g["n_sets"]))]
+
+
+def _same_or_both_nan(a, b, atol=0.0):
+    return (np.isnan(a) and np.isnan(b)) or abs(a - b) <= atol
+
+
+def test_oracle_cdist_equals_reference(golden):
+    """getEvenlySpacedPtsZ, cDist, cDistBetweenBins and cDistMergedBins of the reference, run unmodified
+    on bins below and above the 100-row sampling limit, with a zero-coverage row (its pairs raise
+    FloatingPointError in the reference and are dropped) and a bin whose every pair is dropped."""
+    g = golden("ref_cdist.npz")
+    cov, tcp = g["cov"], g["tcp"]
+    rows, picks = _cdist_sets(g)
+    for r, pick, want in zip(rows, picks, g["c_dist"]):
+        if len(r) > 100:
+            assert np.array_equal(oracle.evenly_spaced_pts_z(tcp, r, 100), pick)
+        assert _same_or_both_nan(oracle.c_dist_rows(cov, tcp, r), float(want))
+    for (a, b), want in zip(g["pairs"], g["c_dist_between"]):
+        assert _same_or_both_nan(oracle.c_dist_between_rows(cov, tcp, rows[a], rows[b]), float(want))
+    for (a, b), want in zip(g["pairs"][:3], g["c_dist_merged"]):
+        assert _same_or_both_nan(oracle.c_dist_merged_rows(cov, tcp, rows[a], rows[b]), float(want))
+
+
+def test_host_row_selection_equals_reference(golden):
+    from groopm_b200 import dropin
+    g = golden("ref_cdist.npz")
+    rows, picks = _cdist_sets(g)
+    for r, pick in zip(rows, picks):
+        if len(r) > 100:
+            assert np.array_equal(dropin.evenly_spaced_pts_z(g["tcp"], r, 100), pick)
+    rng = np.random.default_rng(5)
+    z = rng.random((5000, 3))
+    for m, size in ((101, 100), (333, 100), (4999, 100), (250, 7), (1000, 999)):
+        r = np.sort(rng.choice(5000, m, replace=False))
+        assert np.array_equal(dropin.evenly_spaced_pts_z(z, r, size), oracle.evenly_spaced_pts_z(z, r, size))
+
+
+@pytest.mark.gpu
+def test_engine_cdist_equals_reference(cuda, golden):
+    """Set 5 holds two IDENTICAL profiles: whether their cosine rounds to 1 (angle 0, kept) or just
+    above it (arccos invalid, pair dropped by the reference) is decided by the summation order of
+    BLAS' dot product, which no other implementation reproduces -- it stays a CPU-only case."""
+    from groopm_b200 import dropin
+    g = golden("ref_cdist.npz")
+    cov, tcp = g["cov"], g["tcp"]
+    rows, _ = _cdist_sets(g)
+    atol = 1e-12                                             # radians; np.dot goes through BLAS (see test_next_rows)
+    for i, (r, want) in enumerate(zip(rows, g["c_dist"])):
+        if i != 5:
+            assert _same_or_both_nan(dropin.c_dist_rows(cov, tcp, r), float(want), atol)
+    for (a, b), want in zip(g["pairs"], g["c_dist_between"]):
+        if 5 in (a, b):
+            continue
+        assert _same_or_both_nan(dropin.c_dist_between_rows(cov, tcp, rows[a], rows[b]), float(want), atol)
+    for (a, b), want in zip(g["pairs"][:3], g["c_dist_merged"]):
+        assert _same_or_both_nan(dropin.c_dist_merged_rows(cov, tcp, rows[a], rows[b]), float(want), atol)
