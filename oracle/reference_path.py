@@ -366,16 +366,16 @@ def c_dist_between(cov1: np.ndarray, cov2: np.ndarray):
 
 def evenly_spaced_pts_z(transformed_cp: np.ndarray, row_indices, sample_size: int):
     """RefineEngine.getEvenlySpacedPtsZ, refine.py:1505-1516: ``sample_size`` rows spread evenly
-    along the Z axis (last column) of the transformed coverage space."""
-    row_indices = np.asarray(row_indices)
-    sorted_indices = np.argsort(transformed_cp[row_indices, -1])
-    step_size = float(len(row_indices)) / sample_size
-    si = []
-    index = 0.0
+    along the Z axis (last column) of the transformed coverage space.  The positions are the
+    truncations of a RUNNING float sum of len/sample_size, as in the reference."""
+    rows = np.asarray(row_indices)
+    z_rank = np.argsort(transformed_cp[rows, -1])
+    stride = float(len(rows)) / sample_size
+    chosen, cursor = [], 0.0
     for _ in range(sample_size):
-        si.append(row_indices[sorted_indices[int(index)]])
-        index += step_size
-    return np.array(si)
+        chosen.append(rows[z_rank[int(cursor)]])
+        cursor += stride
+    return np.array(chosen)
 
 
 def _c_pick(transformed_cp, row_indices, max_in_bin=100):
