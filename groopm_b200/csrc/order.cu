@@ -10,10 +10,10 @@ __global__ void __launch_bounds__(256) key_hist_kernel(const int32_t* __restrict
                                                        int32_t* __restrict__ count, int32_t* __restrict__ bad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const int k = key[i];
-    if (k < 0 || k >= nkeys) {
+    int k = key[i];
+    if (k < 0 || k >= nkeys) {                         // (a row without a valid key, e.g. a non-finite profile)
         *bad = 1;
-        return;
+        k = min(max(k, 0), nkeys - 1);                 // still placed: perm must stay a permutation
     }
     atomicAdd(&count[k], 1);
 }
@@ -48,8 +48,7 @@ __global__ void __launch_bounds__(256) key_scatter_kernel(const int32_t* __restr
                                                           int32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const int k = key[i];
-    if (k < 0 || k >= nkeys) return;
+    const int k = min(max(key[i], 0), nkeys - 1);
     perm[atomicAdd(&cursor[k], 1)] = (uint32_t)i;      // order inside a key group is arbitrary (and irrelevant)
 }
 
