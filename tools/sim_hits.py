@@ -42,7 +42,7 @@ def assign(x, cent, chunk=20000):
     return out
 
 
-def replay(q, c, kk, start_tile=0, prune=True):
+def replay(q, c, kk, start_tile=0, prune=True, check=False):
     """q [128, D], c [Nc, D] in the sweep's order -> hits per query, firing tiles per warp, skipped tiles."""
     tm = 128
     nt = (len(c) + tm - 1) // tm
@@ -74,6 +74,11 @@ def replay(q, c, kk, start_tile=0, prune=True):
             merged.partition(kk - 1, axis=1)
             best[rows] = merged[:, :kk]
             thr[rows] = best[rows].max(1)
+    if check:
+        # the bound is only sound if the kept top-kk is the brute-force one
+        d_all = q2[:, None] - 2.0 * q @ c.T + (c * c).sum(1)[None, :]
+        want = np.sort(np.partition(d_all, kk - 1, axis=1)[:, :kk], axis=1)
+        assert np.allclose(np.sort(best, axis=1), want, rtol=0, atol=1e-9 * max(1.0, np.abs(want).max())), "pruning lost a neighbour"
     return hits, fire, skipped, nt
 
 
@@ -101,7 +106,7 @@ def main():
     for qt in rng.choice(n // 128, 6, replace=False):
         q = xs[qt * 128:(qt + 1) * 128]
         for prune in (False, True):
-            hits, fire, skipped, nt = replay(q, xs, kk, qt, prune=prune)
+            hits, fire, skipped, nt = replay(q, xs, kk, qt, prune=prune, check=prune)
             print(f"cluster order, sweep from own tile {qt}, prune={prune}: hits per query mean {hits.mean():.0f} max {hits.max()}, "
                   f"tiles with a hit per warp {fire.mean():.0f}, tiles skipped by the bound {skipped} of {nt}", flush=True)
 
