@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box pass.  Usage (repo root, under gpurun): bash tools/gpu_round.sh <tag> [steps...]
-# steps: test perf bench ref launches full1m fullcfg2
+# steps: test perf bench ref launches full1m full1m_order fullcfg2
 set -u
 TAG=${1:-r1}; shift
 STEPS=${*:-test perf bench ref}
@@ -19,6 +19,9 @@ launches) python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary 
 full1m) python tools/ncu_case.py 1000000 30 32 > $OUT/plain_case_$TAG.log 2>&1 &&
    ncu --set full --clock-control none --import-source on -k regex:scan_tc -s 1 -c 1 -f -o $OUT/scan_1m_d30_$TAG \
     python tools/ncu_case.py 1000000 30 32 > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full 1M rc=$?";;
+full1m_order) GMD_TC_ORDER=1 python tools/ncu_case.py 1000000 30 32 > $OUT/plain_case_order_$TAG.log 2>&1 &&
+   GMD_TC_ORDER=1 ncu --set full --clock-control none --import-source on -k regex:scan_tc -s 1 -c 1 -f -o $OUT/scan_1m_d30_order_$TAG \
+    python tools/ncu_case.py 1000000 30 32 > $OUT/ncu_full_order_$TAG.log 2>&1; echo "ncu full 1M ordered rc=$?";;
 fullcfg2) python tools/ncu_case.py 100000 10 16 > $OUT/plain_case2_$TAG.log 2>&1 &&
    ncu --set full --clock-control none --import-source on -k regex:scan_tc -s 1 -c 1 -f -o $OUT/scan_100k_d10_$TAG \
     python tools/ncu_case.py 100000 10 16 > $OUT/ncu_full2_$TAG.log 2>&1; echo "ncu full cfg2 rc=$?";;

@@ -1,4 +1,5 @@
-"""One short pipeline run for ncu captures: python tools/ncu_case.py N D k [metric] [nq]."""
+"""One short pipeline run for ncu captures: python tools/ncu_case.py N D k [metric] [nq]
+(GMD_TC_ORDER=1 in the environment selects the locality-ordered sweep of an all-pairs problem)."""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
