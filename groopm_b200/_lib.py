@@ -44,6 +44,24 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_prep_tc_perm_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "gmd_scan_tc_sweep_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "gmd_group_shells": (_int, []),
+    "gmd_group_params": (None, [_i64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gmd_group_positions": (_i64, [_i64, _int, _int]),
+    "gmd_group_leaders_workspace_bytes": (_sz, [_int, _int]),
+    "gmd_group_leaders_f64": (_int, [_vp, _i64, _int, _vp, _int, _int, C.c_float, _vp, _vp, _vp, _vp, _vp, _sz,
+                                     C.POINTER(C.c_int32), _vp]),
+    "gmd_group_order_workspace_bytes": (_sz, [_int]),
+    "gmd_group_order": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "gmd_prep_tc_grouped_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "gmd_tc_group_meta": (_int, [_vp, _int, _vp, _int, _int, _vp, _vp, _vp, _int, _vp]),
+    "gmd_use_tc_prune": (_int, [_i64, _i64, _int, _int, _int]),
+    "gmd_tc_prune_max_tiles": (_sz, [_int, _int]),
+    "gmd_tc_grouped_tiles_bytes": (_sz, [_i64, _i64, _int]),
+    "gmd_tc_grouped_workspace_bytes": (_sz, [_i64, _i64, _int]),
+    "gmd_tc_stage_grouped_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "gmd_scan_tc_prune_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp,
+                                     _int, _vp, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_scan_tc_grouped_f32": (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_order_workspace_bytes": (_sz, [_int]),
     "gmd_order_by_key": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "gmd_exact_workspace_bytes": (_sz, [_i64]),
@@ -51,7 +69,7 @@ SIGNATURES = {
     "gmd_knn_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "gmd_knn_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gmd_cdist_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp]),
-    "gmd_angle_block_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "gmd_angle_block_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     "gmd_pdist_f64": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
     "gmd_radius_count_f64": (_int, [_vp, _i64, _int, _int, C.c_double, _vp, _vp]),
     "gmd_radius_fill_f64": (_int, [_vp, _i64, _int, _int, C.c_double, _vp, _vp, _vp, _vp]),
@@ -65,6 +83,14 @@ SIGNATURES = {
     "gmd_pick_nsplit": (_int, [_i64, _i64, _int, _int]),
     "gmd_fp32_peak_probe": (_int, [_int, _vp, C.POINTER(C.c_double), _vp]),
 }
+
+
+class Grouped(C.Structure):
+    """gmd_grouped (include/gmdist.h): what the pruned tensor-core scan needs from its staging."""
+    _fields_ = [("npos_q", C.c_int64), ("npos_c", C.c_int64), ("ngroups", C.c_int32), ("ng_alloc", C.c_int32),
+                ("nt_alloc_q", C.c_int32), ("nt_alloc_c", C.c_int32), ("same", C.c_int32), ("reserved", C.c_int32),
+                ("perm_q", _vp), ("perm_c", _vp), ("tgroup_q", _vp), ("gstart_c", _vp), ("gmeta", _vp),
+                ("tmeta_q", _vp), ("tmeta_c", _vp), ("counters", _vp)]
 
 
 class GmdistError(RuntimeError):

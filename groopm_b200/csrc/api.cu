@@ -152,12 +152,15 @@ struct Workspace {
     int32_t* fail_rows;
     void* exact_ws;     // hit lists of the batched exact pass
     size_t exact_bytes;
+    void* grouped_ws;   // staging of the pruned tensor-core scan (grouped.cu)
+    size_t grouped_bytes;
     size_t bytes;
 };
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, bool same, bool tc = false) {
+Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, bool same, bool tc = false,
+                bool prune = false) {
     Workspace w;
     char* p = (char*)base;
     size_t off = 0;
@@ -169,14 +172,19 @@ Workspace carve(void* base, int64_t Nq, int64_t Nc, int D, int kk, int nsplit, b
     w.center = (double*)take(sizeof(double) * GMD_MAX_D);
     w.stats = (float*)take(sizeof(float) * 4);
     w.flags = (int32_t*)take(sizeof(int32_t) * 4);
-    w.ctiles = (float*)take(tc ? gmd_tc_tiles_bytes(Nc, D) : gmd_tiles_bytes(Nc, D));
-    w.qtiles = (same && !tc) ? w.ctiles : (float*)take(tc ? gmd_tc_tiles_bytes(Nq, D) : gmd_tiles_bytes(Nq, D));
+    w.ctiles = (float*)take(prune ? gmd_tc_grouped_tiles_bytes(Nc, Nc, D) : tc ? gmd_tc_tiles_bytes(Nc, D) : gmd_tiles_bytes(Nc, D));
+    w.qtiles = (same && !tc) ? w.ctiles
+                             : (float*)take(prune ? gmd_tc_grouped_tiles_bytes(Nq, Nc, D)
+                                            : tc  ? gmd_tc_tiles_bytes(Nq, D)
+                                                  : gmd_tiles_bytes(Nq, D));
     w.cand_idx = (uint32_t*)take((size_t)Nq * nsplit * kk * sizeof(uint32_t));
     w.cand_val = (float*)take((size_t)Nq * nsplit * kk * sizeof(float));
     w.cand_tau = (float*)take((size_t)Nq * nsplit * sizeof(float));
     w.fail_rows = (int32_t*)take((size_t)Nq * sizeof(int32_t));
     w.exact_bytes = gmd_exact_workspace_bytes(Nq);
     w.exact_ws = take(w.exact_bytes);
+    w.grouped_bytes = prune ? gmd_tc_grouped_workspace_bytes(Nq, Nc, D) : 0;
+    w.grouped_ws = take(w.grouped_bytes);
     w.bytes = off;
     return w;
 }
@@ -187,7 +195,8 @@ extern "C" size_t gmd_knn_workspace_bytes(int64_t Nq, int64_t Nc, int D, int k) 
     const int kk = std::max(gmd_pick_kk(k), k == 1 ? gmd_scan::BMU_KK : 0);
     const size_t plain = carve(nullptr, Nq, Nc, D, kk, gmd_pick_nsplit(Nq, Nc, D, kk), false).bytes;
     const size_t tc = gmd_tc_supported(k, GMD_L2, D) ? carve(nullptr, Nq, Nc, D, kk, 1, false, true).bytes : 0;
-    return std::max(plain, tc);
+    const size_t pr = gmd_use_tc_prune(Nq, Nc, k, GMD_L2, D) ? carve(nullptr, Nq, Nc, D, kk, 1, false, true, true).bytes : 0;
+    return std::max(plain, std::max(tc, pr));
 }
 
 extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
@@ -209,9 +218,12 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     const int kk = bmu ? gmd_scan::BMU_KK : gmd_pick_kk(k);
     const int nsplit = (bmu || tc) ? 1 : gmd_pick_nsplit(Nq, Nc, D, kk);
     const bool same = (Q == C && Nq == Nc);
-    Workspace w = carve(workspace, Nq, Nc, D, kk, nsplit, same, tc);
+    // large tensor-core problems go through the grouped order and the pruned scan
+    const bool prune = tc && gmd_use_tc_prune(Nq, Nc, k, metric, D);
+    Workspace w = carve(workspace, Nq, Nc, D, kk, nsplit, same, tc, prune);
     GMD_REQUIRE(w.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "knn: workspace %zu B < required %zu B",
                 workspace_bytes, w.bytes);
+    gmd_grouped grouped;
     cudaStream_t st = (cudaStream_t)stream;
     GMD_CUDA_CHECK(cudaMemsetAsync(w.stats, 0, sizeof(float) * 4, st));
     GMD_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, sizeof(int32_t) * 4, st));
@@ -220,14 +232,22 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
     if (tc) {
         if ((rc = gmd_tc_norms_f64(C, Nc, D, w.center, w.stats, w.flags, stream)) != GMD_OK) return rc;
         if (!same && (rc = gmd_tc_norms_f64(Q, Nq, D, w.center, w.stats + 2, w.flags, stream)) != GMD_OK) return rc;
-        if ((rc = gmd_prep_tc_f64(C, Nc, D, w.center, 1, w.stats, w.stats + 2, w.ctiles, stream)) != GMD_OK) return rc;
-        if ((rc = gmd_prep_tc_f64(Q, Nq, D, w.center, 0, w.stats, w.stats + 2, w.qtiles, stream)) != GMD_OK) return rc;
+        if (prune) {
+            if ((rc = gmd_tc_stage_grouped_f64(Q, Nq, C, Nc, D, w.center, w.stats, w.stats + 2, w.qtiles, w.ctiles,
+                                               w.grouped_ws, w.grouped_bytes, &grouped, stream)) != GMD_OK)
+                return rc;
+        } else {
+            if ((rc = gmd_prep_tc_f64(C, Nc, D, w.center, 1, w.stats, w.stats + 2, w.ctiles, stream)) != GMD_OK) return rc;
+            if ((rc = gmd_prep_tc_f64(Q, Nq, D, w.center, 0, w.stats, w.stats + 2, w.qtiles, stream)) != GMD_OK) return rc;
+        }
     } else {
         if ((rc = gmd_prep_f64(C, Nc, D, w.center, form, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
         if (!same && (rc = gmd_prep_f64(Q, Nq, D, w.center, form, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK)
             return rc;
     }
-    rc = tc ? gmd_scan_tc_f32(w.qtiles, Nq, w.ctiles, Nc, D, kk, 0, w.stats, w.stats + 2, w.cand_idx, w.cand_val,
+    rc = prune ? gmd_scan_tc_grouped_f32(w.qtiles, w.ctiles, D, kk, 0, w.stats, w.stats + 2, &grouped, w.cand_idx,
+                                         w.cand_val, w.cand_tau, stream) :
+         tc ? gmd_scan_tc_f32(w.qtiles, Nq, w.ctiles, Nc, D, kk, 0, w.stats, w.stats + 2, w.cand_idx, w.cand_val,
                               w.cand_tau, stream) :
          bmu ? gmd_scan_bmu_f32(w.qtiles, Nq, w.ctiles, Nc, D, 0, w.cand_idx, w.cand_val, w.cand_tau, stream)
              : gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,

@@ -258,34 +258,45 @@ __global__ void select_finish_kernel(const unsigned long long* __restrict__ stat
 
 }  // namespace
 
-// ---- angle between coverage profiles (refine.py:1545, 1577): arccos(a.b / (|a| |b|)) for a
-// small block of pairs; pairs the reference drops with a FloatingPointError (argument outside
-// [-1, 1], zero norm) come back as NaN.
+// ---- angle between coverage profiles (refine.py:1545-1546, 1577-1578):
+//   arccos(np.dot(cov[r1], cov[r2]) / (normCoverages[r1] * normCoverages[r2]))
+// for a small block of pairs.  The denominator is the product of the caller's normCoverages (the
+// reference loads them from its database, profileManager.py:205; they are NOT recomputed from the
+// rows), rounded once; the dot product is the sequential fused-multiply-add chain that OpenBLAS'
+// ddot runs on rows shorter than its SIMD block (the 3..10-sample rows this path sees).  Pairs the
+// reference drops with a FloatingPointError (argument outside [-1, 1], 0/0 or x/0 for a zero norm)
+// come back as NaN.  normA / normB null: norms of the rows themselves (sqrt of the same chain).
 namespace {
+__device__ __forceinline__ double fma_dot(const double* __restrict__ a, const double* __restrict__ b, int D) {
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) s = __fma_rn(a[d], b[d], s);
+    return s;
+}
 __global__ void __launch_bounds__(256) angle_block_kernel(const double* __restrict__ A, long long mA,
                                                           const double* __restrict__ B, long long mB, int D,
+                                                          const double* __restrict__ normA,
+                                                          const double* __restrict__ normB,
                                                           double* __restrict__ out) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= mA * mB) return;
-    const double* a = A + (size_t)(e / mB) * D;
-    const double* b = B + (size_t)(e % mB) * D;
-    double dot = 0.0, na = 0.0, nb = 0.0;
-    for (int d = 0; d < D; ++d) {
-        dot = __dadd_rn(dot, __dmul_rn(a[d], b[d]));
-        na = __dadd_rn(na, __dmul_rn(a[d], a[d]));
-        nb = __dadd_rn(nb, __dmul_rn(b[d], b[d]));
-    }
-    const double den = __dmul_rn(sqrt(na), sqrt(nb));
-    const double arg = dot / den;
-    out[e] = (den > 0.0 && arg >= -1.0 && arg <= 1.0) ? acos(arg) : CUDART_NAN;
+    const long long i = e / mB, j = e % mB;
+    const double* a = A + (size_t)i * D;
+    const double* b = B + (size_t)j * D;
+    const double na = normA ? normA[i] : sqrt(fma_dot(a, a, D));
+    const double nb = normB ? normB[j] : sqrt(fma_dot(b, b, D));
+    const double den = __dmul_rn(na, nb);
+    const double arg = __ddiv_rn(fma_dot(a, b, D), den);
+    // den == 0: divide-by-zero / invalid in the reference; |arg| > 1: invalid in arccos; NaN compares false
+    out[e] = (den != 0.0 && arg >= -1.0 && arg <= 1.0) ? acos(arg) : CUDART_NAN;
 }
 }  // namespace
 
-extern "C" int gmd_angle_block_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, double* out,
-                                   void* stream) {
+extern "C" int gmd_angle_block_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D,
+                                   const double* normA, const double* normB, double* out, void* stream) {
     GMD_REQUIRE(A && B && out && mA > 0 && mB > 0 && D > 0, GMD_ERR_BAD_ARG, "angle_block: bad arguments");
     const long long n = (long long)mA * mB;
-    angle_block_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A, mA, B, mB, D, out);
+    angle_block_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A, mA, B, mB, D, normA, normB,
+                                                                                      out);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }

@@ -638,7 +638,7 @@ static int scan_dispatch(const ScanParams& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // k = 1 (best-matching unit, torusMesh.py:127): no heaps, no thresholds, no hit path.
 //
-// Same CTA shape, ring and register tile as scan_topk_kernel (expanded form only, D <= 16,
+// Same CTA shape, ring and register tile as scan_topk_kernel (expanded form only, D <= 32,
 // straight-line d-steps).  A "cell" is the 8 candidates one lane holds of one tile.  Every
 // (lane, row) keeps, branch-free, the smallest cell minimum it has seen, the tile it came
 // from (strict <, so the earliest tile wins ties) and the second smallest cell minimum.
@@ -808,8 +808,8 @@ static int bmu_launch(const ScanParams& p, cudaStream_t st) {
     X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(20) X(24) X(28) X(30) X(32) X(40) X(48) X(64) X(96) X(136)
 
 // padded dimensions of the k = 1 kernel
-#define GMD_BMU_DIMS(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16)
-#define GMD_BMU_MAX_D 16
+#define GMD_BMU_DIMS(X) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(20) X(24) X(28) X(30) X(32)
+#define GMD_BMU_MAX_D 32
 
 int gmd_scan_pad_dim(int D);
 int gmd_bmu_launch(int DP, const gmd_scan::ScanParams& p, cudaStream_t st);

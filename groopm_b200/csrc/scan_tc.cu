@@ -34,73 +34,21 @@
 // [scaled ||x||^2 128 f32][pad to 1 KB]; images already in the swizzled shared-memory layout
 // (8-row x 64 B atoms, 16-byte chunk c of row r at c ^ ((r >> 1) & 3)) so that one bulk copy
 // per K block is all the producer does.  Query and candidate tiles differ in column D only.
-#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <algorithm>
 
-#include "scan_impl.cuh"
+#include "tc_common.cuh"
+
+// Developer probes of the scan (GMD_TC_DBG: pipeline without selection, no candidate traffic, one issuer ...)
+// exist only in builds made with -DGMD_TC_PROBES; the shipped kernel has none of their branches.
+#ifdef GMD_TC_PROBES
+#define TC_DBG(x) (x)
+#else
+#define TC_DBG(x) 0
+#endif
 
 namespace gmd_tc {
-using namespace gmd_scan;
-
-constexpr int TM = 128;                  // profiles per TC tile (UMMA M and N)
-constexpr int TK = 32;                   // contraction length of one K block (64-byte rows of halves)
-constexpr int IMG_B = TM * TK * 2;       // one FP16 image of one K block: 8 KB
-constexpr int KB_B = 2 * IMG_B;          // hi + lo images of one K block: 16 KB = one ring stage
-constexpr int MAX_KB = 5;                // K blocks per tile: D + 1 <= 160 covers the 136-d signatures
-constexpr int NS_MAX = 8;                // most ring stages
-constexpr int NACC = 4;                  // accumulator stages in tensor memory (4 x 128 of the 512 columns)
-__host__ __device__ constexpr int tile_bytes(int nkb) { return nkb * KB_B + 1024; }  // K blocks, then norms
-constexpr float QCOL = 8.0f;             // column D of a query row; a candidate row holds -||c||^2 / (2 QCOL)
-constexpr float PAD_COL = -60000.0f;     // column D of a padding candidate: u = -480000, below any real value
-// Warp roles.  The scheduler of an SM sub-partition picks the eligible warp with the HIGHEST id first, so the
-// single-thread roles whose latency the whole pipeline waits on sit above the selection warps.
-constexpr int W_PROD = 4;                // warps 0..3: selection (TMEM lane quarter = warp id), 4: producer
-constexpr int W_ISSUE = 5;               // 5, 6: MMA issuers (even / odd candidate tiles)
-constexpr int NTHREADS = 224;
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    // K-major SWIZZLE_64B: LBO 1, SBO 512 B (8 rows x 64 B), descriptor version 1 (sm_100), layout type 4
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem),
-        "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-// wait for the outstanding tcgen05.ld; the registers pass through the asm so that nothing that
-// reads them can be scheduled above the wait
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
 
 // ------------------------------------------------------------------ staging: float64 rows -> TC tiles
 // pass 1: largest centred row norm of a profile set (fixes the power-of-two scale)
@@ -136,22 +84,40 @@ __global__ void __launch_bounds__(256) tc_norms_kernel(const double* __restrict_
 // pass 2: scaled FP16 hi / lo images, nkb K blocks of 32 columns.  role 0: query tile (column D =
 // QCOL), role 1: candidate tile (column D = -||x||^2 / (2 QCOL), in scaled units).
 // stats_c / stats_q: max ||x||^2 of the two sets.
-__global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long N, int D, int nkb,
+// perm (nullable): tile position -> row of X, for profiles staged in a locality-preserving order;
+// GMD_EMPTY_IDX marks a padding position (grouped order of order.cu), Npos counts positions.
+// tmeta (nullable): [D + 1][nt_alloc] ball of the tile in scaled units -- centroid of its real rows and
+// the largest distance of one of them to it, rounded up (-1 for a tile of padding only).  Any centre
+// gives a valid ball; the radius is taken against the centre exactly as stored.
+__global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long Npos, int D, int nkb,
                                                       const uint32_t* __restrict__ perm,
                                                       const double* __restrict__ center, int role,
                                                       const float* __restrict__ stats_c, const float* __restrict__ stats_q,
-                                                      unsigned char* __restrict__ tiles) {
+                                                      unsigned char* __restrict__ tiles, float* __restrict__ tmeta,
+                                                      int nt_alloc) {
     __shared__ float s_n2[TM];
+    __shared__ long long s_src[TM];                      // row of X, -1 for padding
+    __shared__ float s_m[GMD_MAX_D];
+    __shared__ int s_cnt, s_rad;
     const float scale = ldexpf(1.0f, gmd_tc_exponent(stats_c[0], stats_q[0]));
     const long long t = blockIdx.x, row0 = t * TM;
-    // perm (nullable): tile position -> row of X, for profiles staged in a locality-preserving order
+    if (threadIdx.x == 0) s_cnt = 0, s_rad = 0;
     if (threadIdx.x < TM) {
-        const long long row = row0 + threadIdx.x;
+        const long long pos = row0 + threadIdx.x;
+        long long src = -1;
+        if (pos < Npos) {
+            if (perm) {
+                const uint32_t r = perm[pos];
+                if (r != GMD_EMPTY_IDX) src = (long long)r;
+            } else {
+                src = pos;
+            }
+        }
+        s_src[threadIdx.x] = src;
         double n2 = 0.0;
-        if (row < N) {
-            const size_t src = perm ? perm[row] : (size_t)row;
+        if (src >= 0) {
             for (int k = 0; k < D; ++k) {
-                const double v = (double)((float)(X[src * D + k] - (center ? center[k] : 0.0)) * scale);
+                const double v = (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale);
                 n2 += v * v;
             }
         }
@@ -162,11 +128,11 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
     const int KT = TK * nkb;
     for (int e = threadIdx.x; e < TM * KT; e += blockDim.x) {
         const int r = e / KT, k = e - r * KT;
-        const long long row = row0 + r;
+        const long long src = s_src[r];
         float v = 0.0f;
-        if (row < N) {
+        if (src >= 0) {
             if (k < D)
-                v = (float)(X[(perm ? (size_t)perm[row] : (size_t)row) * D + k] - (center ? center[k] : 0.0)) * scale;   // exact: power of two
+                v = (float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale;   // exact: power of two
             else if (k == D)
                 v = role == 0 ? QCOL : -s_n2[r] / (2.0f * QCOL);
         } else if (k == D) {
@@ -182,25 +148,37 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
         hi[IMG_B / 2 + off] = __float2half_rn(v - __half2float(h));
     }
     float* nrm = reinterpret_cast<float*>(tile + (size_t)nkb * KB_B);
-    if (threadIdx.x < TM) nrm[threadIdx.x] = (row0 + threadIdx.x) < N ? s_n2[threadIdx.x] : 0.0f;
+    if (threadIdx.x < TM) nrm[threadIdx.x] = s_src[threadIdx.x] >= 0 ? s_n2[threadIdx.x] : 0.0f;
+    if (!tmeta) return;
+    // ---- the tile's ball
+    if (threadIdx.x < TM && s_src[threadIdx.x] >= 0) atomicAdd(&s_cnt, 1);
+    __syncthreads();
+    const int cnt = s_cnt;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < TM; ++r) {
+            const long long src = s_src[r];
+            if (src >= 0) sum += (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale);
+        }
+        const float m = cnt ? (float)(sum / cnt) : 0.0f;
+        s_m[k] = m;
+        tmeta[(size_t)k * nt_alloc + t] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x < TM && s_src[threadIdx.x] >= 0) {
+        const long long src = s_src[threadIdx.x];
+        double d2 = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double u = (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale) - (double)s_m[k];
+            d2 += u * u;
+        }
+        atomicMax(&s_rad, __float_as_int(__double2float_ru(sqrt(d2) * (1.0 + 1e-9))));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) tmeta[(size_t)D * nt_alloc + t] = cnt ? __int_as_float(s_rad) : -1.0f;
 }
 
 // ------------------------------------------------------------------ the scan
-constexpr int TQ = 16;   // parked hits per selection thread (a thread owns its query's queue)
-
-// Every lane folds its own queue into its own heap (the lanes work side by side: this is
-// why hits are parked instead of being pushed the moment they are seen, which would
-// serialise 32 divergent heap updates per warp).  Returns the new threshold value.
-static __device__ __noinline__ float drain_own(uint64_t* h, int kk, const uint2* q, int n) {
-    for (int r = 0; r < n; ++r) {
-        const uint2 e = q[r * TM];
-        const uint64_t key = gmd_key(__uint_as_float(e.y), e.x);
-        if (key < h[0]) heap_replace_root(h, kk, key);
-    }
-    const uint64_t root = h[0];
-    return (root == GMD_EMPTY_KEY) ? __int_as_float(0x7f800000) : gmd_unflip((uint32_t)(root >> 32));
-}
-
 // nkb: K blocks per tile (1 for D <= 31 ... 5 for D = 136); ns: ring stages of one K block each.
 // NKB is a template parameter: with a run-time K-block loop the issuing thread falls behind the tensor
 // pipe (1M x 30: 196 ms instead of 159 ms with selection off).
@@ -286,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                     }
                     if (++pkb == nkb) pkb = 0, ++pt;
                 }
-                const uint32_t bytes = (dbg & 15) == 2 ? 1024u : (uint32_t)KB_B;  // (2: developer probe, no candidate traffic)
+                const uint32_t bytes = (TC_DBG(dbg) & 15) == 2 ? 1024u : (uint32_t)KB_B;  // (2: developer probe, no candidate traffic)
                 mbar_expect_tx(&full[s], bytes);
                 const int ta = t + t_first < ntiles_c ? t + t_first : t + t_first - ntiles_c;
                 bulk_g2s(Bst + (size_t)s * KB_B, ctiles + (size_t)ta * TILE_B + (size_t)kb * KB_B, bytes, &full[s]);
@@ -307,7 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             const uint64_t b_base = umma_desc(smem_u32(Bst));
             // Two issuers need ns > nkb: an issuer only sees every other fill of a ring stage, and a parity
             // wait is ambiguous if the fill before the awaited one may still be in flight.
-            const int nissue = (ns > nkb && !(dbg & 256)) ? 2 : 1;  // (dbg & 256: developer probe, one issuer)
+            const int nissue = (ns > nkb && !(TC_DBG(dbg) & 256)) ? 2 : 1;  // (dbg & 256: developer probe, one issuer)
             const int first = warp - W_ISSUE;
             int s = 0;                                     // ring stage and phase of item t * nkb
             uint32_t ph = 0;
@@ -352,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
         float thr = __int_as_float(0x7f800000);
         constexpr unsigned FULLW = 0xFFFFFFFFu;
         float uthr = __int_as_float(0xff800000);            // -thr / 2: the accumulators are u = -s/2
-        if ((dbg & 15) == 4) uthr = __int_as_float(0x7f800000);    // developer probe: nothing ever hits
+        if ((TC_DBG(dbg) & 15) == 4) uthr = __int_as_float(0x7f800000);    // developer probe: nothing ever hits
         for (int t = 0; t < ntiles_c; ++t) {
             const int a = t % NACC;
             mbar_wait(&tdone[a], (t / NACC) & 1);
@@ -373,7 +351,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
             if constexpr (SWEEP) {
-                if ((dbg & 15) >= 1 && (dbg & 15) != 4) continue;  // developer probe: MMA + copy pipeline only
+                if ((TC_DBG(dbg) & 15) >= 1 && (TC_DBG(dbg) & 15) != 4) continue;  // developer probe: MMA + copy pipeline only
                 // Maxima of the 16 groups of 8 columns first, as shallow trees with all 128 values in
                 // flight (a dependent chain or a vote-and-branch per 32 columns is pure latency for the one
                 // selection warp of a scheduler: 430 instead of ~200 cycles per tile), then ONE vote.
@@ -432,7 +410,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                 park(r3, 3);
             } else {
                 auto process = [&](const uint32_t (&r)[32], int c0) {
-                    if ((dbg & 15) >= 1 && (dbg & 15) != 4) return;  // developer probe: MMA + copy pipeline only
+                    if ((TC_DBG(dbg) & 15) >= 1 && (TC_DBG(dbg) & 15) != 4) return;  // developer probe: MMA + copy pipeline only
                     // group maxima as trees (a chain of dependent ops is pure latency for the one
                     // selection warp of a scheduler), one vote per 32 columns
                     float gm[4];
@@ -509,8 +487,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
 
 }  // namespace gmd_tc
 
-static int tc_nkb(int D) { return (D + 1 + gmd_tc::TK - 1) / gmd_tc::TK; }
-
 extern "C" int gmd_tc_supported(int k, int metric, int D) {
     // one column of the contraction carries the norm; up to MAX_KB blocks of 32 columns
     return metric == GMD_L2 && k >= 2 && k <= GMD_MAX_K && D >= 4 && D <= GMD_MAX_D && tc_nkb(D) <= gmd_tc::MAX_KB;
@@ -530,17 +506,24 @@ extern "C" int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double*
     return GMD_OK;
 }
 
+extern "C" int gmd_prep_tc_grouped_f64(const double* X, int64_t Npos, int D, const double* center, int role,
+                                       const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
+                                       float* tmeta, int nt_alloc, void* stream) {
+    GMD_REQUIRE(X && tiles && stats_c && stats_q && Npos > 0 && D >= 1 && tc_nkb(D) <= gmd_tc::MAX_KB &&
+                    (role == 0 || role == 1),
+                GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
+    const unsigned grid = (unsigned)((Npos + gmd_tc::TM - 1) / gmd_tc::TM);
+    GMD_REQUIRE(!tmeta || (int64_t)grid <= nt_alloc, GMD_ERR_BAD_ARG, "prep_tc: tile meta too small");
+    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, Npos, D, tc_nkb(D), perm, center, role, stats_c,
+                                                                  stats_q, (unsigned char*)tiles, tmeta, nt_alloc);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
 extern "C" int gmd_prep_tc_perm_f64(const double* X, int64_t N, int D, const double* center, int role,
                                     const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
                                     void* stream) {
-    GMD_REQUIRE(X && tiles && stats_c && stats_q && N > 0 && D >= 1 && tc_nkb(D) <= gmd_tc::MAX_KB &&
-                    (role == 0 || role == 1),
-                GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
-    const unsigned grid = (unsigned)((N + gmd_tc::TM - 1) / gmd_tc::TM);
-    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, tc_nkb(D), perm, center, role, stats_c,
-                                                                  stats_q, (unsigned char*)tiles);
-    GMD_CUDA_CHECK(cudaGetLastError());
-    return GMD_OK;
+    return gmd_prep_tc_grouped_f64(X, N, D, center, role, stats_c, stats_q, perm, tiles, nullptr, 0, stream);
 }
 
 extern "C" int gmd_prep_tc_f64(const double* X, int64_t N, int D, const double* center, int role,
@@ -565,7 +548,11 @@ extern "C" int gmd_scan_tc_sweep_f32(const void* qtiles, int64_t Nq, const void*
     const int ns = (int)std::min<size_t>(std::min(NS_MAX, NACC * nkb), (GMD_SMEM_LIMIT - fixed) / KB_B);
     const size_t smem = fixed + (size_t)ns * KB_B;
     const unsigned grid = (unsigned)((Nq + TM - 1) / TM);
-    const int dbg = getenv("GMD_TC_DBG") ? atoi(getenv("GMD_TC_DBG")) : 0;  // developer probe
+#ifdef GMD_TC_PROBES
+    const int dbg = getenv("GMD_TC_DBG") ? atoi(getenv("GMD_TC_DBG")) : 0;  // developer probe (tools/tc_time.py)
+#else
+    const int dbg = 0;
+#endif
     const int ntiles_c = (int)((Nc + TM - 1) / TM);
     auto launch = [&](auto kern) -> int {
         GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

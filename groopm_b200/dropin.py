@@ -123,20 +123,22 @@ def k_dist_between_many(kmer_pcs, bin_pairs):
     return engine.median_dist_batch(kmer_pcs, list(bin_pairs), "cityblock")
 
 
-def c_dist(cov_rows):
+def c_dist(cov_rows, norms=None):
     """RefineEngine.cDist (refine.py:1528-1551) on the already selected rows (<= 100 per
     bin, refine.py:1529-1536): median angle over the pairs i < j, pairs that raise a
-    FloatingPointError in the reference left out.  nan when no pair is left (np.median([]))."""
-    ang = engine.angle_block(cov_rows)
+    FloatingPointError in the reference left out.  ``norms`` = ``self.PM.normCoverages`` of
+    those rows (refine.py:1546 divides by the stored norms); None = norms of the rows.
+    nan when no pair is left (np.median([]))."""
+    ang = engine.angle_block(cov_rows, None, norms)
     iu = np.triu_indices(ang.shape[0], 1)
     v = ang[iu]
     v = v[~np.isnan(v)]
     return float(np.median(v)) if len(v) else float("nan")
 
 
-def c_dist_between(cov1, cov2):
+def c_dist_between(cov1, cov2, norms1=None, norms2=None):
     """RefineEngine.cDistBetweenBins (refine.py:1557-1583) on the selected rows."""
-    v = engine.angle_block(cov1, cov2).ravel()
+    v = engine.angle_block(cov1, cov2, norms1, norms2).ravel()
     v = v[~np.isnan(v)]
     return float(np.median(v)) if len(v) else float("nan")
 
@@ -163,21 +165,29 @@ def _c_pick(transformed_cp, row_indices, max_in_bin: int = 100):
     return row_indices
 
 
-def c_dist_rows(cov_profiles, transformed_cp, row_indices):
+def _norms_of(norm_coverages, pick):
+    return None if norm_coverages is None else np.asarray(norm_coverages, dtype=np.float64)[pick]
+
+
+def c_dist_rows(cov_profiles, transformed_cp, row_indices, norm_coverages=None):
     """RefineEngine.cDist (refine.py:1528-1551) from a bin's row indices: at most 100 rows, picked
-    evenly along Z when the bin is larger, then the median angle over the pairs."""
-    return c_dist(np.asarray(cov_profiles)[_c_pick(transformed_cp, row_indices)])
+    evenly along Z when the bin is larger, then the median angle over the pairs.
+    ``norm_coverages`` = ``self.PM.normCoverages`` (all contigs)."""
+    pick = _c_pick(transformed_cp, row_indices)
+    return c_dist(np.asarray(cov_profiles)[pick], _norms_of(norm_coverages, pick))
 
 
-def c_dist_between_rows(cov_profiles, transformed_cp, rows1, rows2):
+def c_dist_between_rows(cov_profiles, transformed_cp, rows1, rows2, norm_coverages=None):
     """RefineEngine.cDistBetweenBins (refine.py:1557-1583) from two bins' row indices."""
     cov = np.asarray(cov_profiles)
-    return c_dist_between(cov[_c_pick(transformed_cp, rows1)], cov[_c_pick(transformed_cp, rows2)])
+    p1, p2 = _c_pick(transformed_cp, rows1), _c_pick(transformed_cp, rows2)
+    return c_dist_between(cov[p1], cov[p2], _norms_of(norm_coverages, p1), _norms_of(norm_coverages, p2))
 
 
-def c_dist_merged_rows(cov_profiles, transformed_cp, rows1, rows2):
+def c_dist_merged_rows(cov_profiles, transformed_cp, rows1, rows2, norm_coverages=None):
     """RefineEngine.cDistMergedBins (refine.py:1553-1555)."""
-    return c_dist_rows(cov_profiles, transformed_cp, np.concatenate((np.asarray(rows1), np.asarray(rows2))))
+    return c_dist_rows(cov_profiles, transformed_cp, np.concatenate((np.asarray(rows1), np.asarray(rows2))),
+                       norm_coverages)
 
 
 # ------------------------------------------------------------------ binManager.py

@@ -75,7 +75,7 @@ class KnnPipeline:
     """
 
     def __init__(self, nq: int, nc: int, d: int, k: int, metric="euclidean", form: Optional[int] = None,
-                 same: bool = False, device=None, order: Optional[bool] = None):
+                 same: bool = False, device=None, order: Optional[bool] = None, prune: Optional[bool] = None):
         self.lib = _lib.lib()
         self.dev = _device(device)
         self.nq, self.nc, self.d, self.k = int(nq), int(nc), int(d), int(k)
@@ -116,7 +116,19 @@ class KnnPipeline:
         self.center = torch.zeros(_lib.MAX_D, dtype=torch.float64, **e)
         self.stats = torch.zeros(4, dtype=torch.float32, **e)
         self.flags = torch.zeros(4, dtype=torch.int32, **e)
-        tiles_bytes = ((lambda n: self.lib.gmd_tc_tiles_bytes(n, self.d)) if self.tc
+        # Pruned tensor-core scan (the default wherever gmd_knn_f64 uses it: both sets large): profiles
+        # staged in the grouped order (leaders from a sample, nearest-leader keys, groups padded to whole
+        # tiles), a ball per tile and group, and every query tile loads only the candidate tiles its
+        # running thresholds cannot rule out.  prune=False: the full sweep (plain or `order`ed).
+        if prune is None:
+            prune = bool(self.tc and auto and self.lib.gmd_use_tc_prune(self.nq, self.nc, self.k, self.metric, self.d))
+        self.prune = bool(prune and self.tc)
+        if self.prune and not self.lib.gmd_tc_prune_max_tiles(self.d, self.kk):
+            raise ValueError("the pruned tensor-core scan does not fit this (D, k)")
+        if self.prune:
+            order = False
+        tiles_bytes = ((lambda n: self.lib.gmd_tc_grouped_tiles_bytes(n, self.nc, self.d)) if self.prune
+                       else (lambda n: self.lib.gmd_tc_tiles_bytes(n, self.d)) if self.tc
                        else (lambda n: self.lib.gmd_tiles_bytes(n, self.d)))
         self.ctiles = torch.empty(tiles_bytes(self.nc) // 4, dtype=torch.float32, **e)
         # tensor-core tiles differ by role (column D), so queries are always staged separately there
@@ -144,6 +156,10 @@ class KnnPipeline:
                                         order=False)
             self.perm = torch.empty(self.nc, dtype=torch.int32, **e)
             self.order_ws = torch.empty(self.lib.gmd_order_workspace_bytes(ncl) // 4, dtype=torch.int32, **e)
+        if self.prune:
+            self.grouped_ws = torch.empty(self.lib.gmd_tc_grouped_workspace_bytes(self.nq, self.nc, self.d),
+                                          dtype=torch.uint8, **e)
+            self.grouped = _lib.Grouped()
         self.out_idx = torch.empty((self.nq, self.k), dtype=torch.int32, **e)
         self.out_dist = torch.empty((self.nq, self.k), dtype=torch.float64, **e)
 
@@ -173,6 +189,15 @@ class KnnPipeline:
                                                      _stream_ptr()))
             # pass 2 for both roles, now that both sets' norms are known
             c = self._tc_c
+            if self.prune:
+                # leaders, nearest-leader keys, padded counting sort, tiles + balls: one C call (it
+                # synchronises the stream once, to learn the number of leaders)
+                _lib.check(self.lib.gmd_tc_stage_grouped_f64(
+                    _ptr(q), self.nq, _ptr(c), self.nc, self.d, _ptr(self.center), _ptr(self.stats), sq,
+                    _ptr(self.qtiles), _ptr(self.ctiles), _ptr(self.grouped_ws), self.grouped_ws.numel(),
+                    C.byref(self.grouped), _stream_ptr()))
+                self._tc_c = None
+                return
             perm = 0
             if self.order:
                 # staging order: nearest sampled profile as the key, counting sort by key
@@ -194,6 +219,11 @@ class KnnPipeline:
                                          _ptr(self.qtiles), _ptr(self.stats) + 8, _ptr(self.flags), _stream_ptr()))
 
     def scan(self):
+        if self.prune:
+            _lib.check(self.lib.gmd_scan_tc_grouped_f32(
+                _ptr(self.qtiles), _ptr(self.ctiles), self.d, self.kk, 0, _ptr(self.stats), _ptr(self.stats) + 8,
+                C.byref(self.grouped), _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))
+            return
         if self.tc:
             _lib.check(self.lib.gmd_scan_tc_sweep_f32(
                 _ptr(self.qtiles), self.nq, _ptr(self.ctiles), self.nc, self.d, self.kk, 0, _ptr(self.stats),
@@ -243,10 +273,30 @@ class KnnPipeline:
     def saw_nonfinite(self) -> bool:
         return bool(self.flags[0].item())
 
+    def prune_stats(self) -> dict:
+        """Counters of the last pruned scan: candidate tiles loaded, over all query tiles, against the
+        full sweep's (synchronises)."""
+        if not self.prune:
+            return {}
+        torch.cuda.current_stream().synchronize()
+        g = self.grouped
+        off = g.counters - self.grouped_ws.data_ptr()
+        visited, ctas, groups, _ = (int(v) for v in self.grouped_ws[off:off + 32].view(torch.int64).tolist())
+        ntc = -(-g.npos_c // 128)
+        return {"tiles_visited": visited, "query_tiles": ctas, "groups": g.ngroups,
+                "candidate_tiles": ntc, "groups_surviving_per_query_tile": groups / max(ctas, 1),
+                "visited_fraction": visited / max(1, ctas * ntc)}
+
     # launches of the engine's own kernels in one run() (col_mean, prep x1/2, scan, refine, exact)
     @property
     def launches_per_run(self) -> int:
         # the exact stage is three kernels: batched pass, its finish, one-row-per-block remainder
+        if self.prune:
+            # col_mean, norms x1/2; leaders (samples, nearest sample, leader clustering, leader rows);
+            # nearest-leader search (col_mean, prep x2, scan, refine, exact x3); grouped sort (keys,
+            # histogram, padded scan, scatter, tile groups) once or twice; prep x2, group balls; scan,
+            # refine, exact x3.  (Queries that are no rows of the candidates add a second search: + 8.)
+            return (2 if self.same else 3) + 4 + 8 + 5 + 2 + 1 + 5 + (0 if self.same else 5)
         if self.tc:
             # col_mean, norms x1/2, prep x2, scan, refine, exact x3 (+ the key pipeline and 3 sort kernels)
             extra = (self.key_pipe.launches_per_run + 3) if self.order else 0
@@ -255,7 +305,7 @@ class KnnPipeline:
 
 
 def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, device=None,
-        return_info: bool = False, order: Optional[bool] = None):
+        return_info: bool = False, order: Optional[bool] = None, prune: Optional[bool] = None):
     """k nearest rows of ``c`` for every row of ``q``; ascending (distance, index).
 
     ``c=None`` means all-pairs within ``q`` (self included at rank 0, as in
@@ -276,7 +326,7 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
         qd = qt.to(dev, non_blocking=True)
         cd = qd if same else ct.to(dev, non_blocking=True)
         pipe = KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, form, same=same, device=dev,
-                           order=order)
+                           order=order, prune=prune)
         idx, dist = pipe.run(qd, cd)
         if q_np:
             idx_h, dist_h = idx.cpu().numpy(), dist.cpu().numpy()  # synchronises
@@ -289,7 +339,8 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
             out = (idx, dist)
         if return_info:
             return out + ({"exact_rows": pipe.exact_row_count(), "form": pipe.form, "kk": pipe.kk,
-                           "nsplit": pipe.nsplit, "ordered": pipe.order},)
+                           "nsplit": pipe.nsplit, "ordered": pipe.order, "pruned": pipe.prune,
+                           **({"prune": pipe.prune_stats()} if pipe.prune else {})},)
         return out
 
 
@@ -409,25 +460,40 @@ def pdist(x, metric="euclidean", device=None):
         return _out(out, x_np)
 
 
-def angle_block(xa, xb=None, device=None):
-    """``arccos(dot(a, b) / (|a| |b|))`` for every pair of rows of two small profile sets
-    (refine.py:1545, 1577) -> [mA, mB] float64; pairs the reference drops with a
-    FloatingPointError are NaN.  ``xb=None``: pairs within ``xa``."""
+def angle_block(xa, xb=None, norm_a=None, norm_b=None, device=None):
+    """``arccos(dot(a, b) / (norm_a[i] * norm_b[j]))`` for every pair of rows of two small profile
+    sets (refine.py:1545-1546, 1577-1578) -> [mA, mB] float64; pairs the reference drops with a
+    FloatingPointError are NaN.  ``norm_a`` / ``norm_b`` are the reference's ``normCoverages`` of
+    the rows (it divides by the stored norms, profileManager.py:205); None = the rows' own
+    Euclidean norms.  ``xb=None``: pairs within ``xa`` (``norm_b`` then defaults to ``norm_a``)."""
     at, a_np = _as_rows(xa, "XA")
     bt = at if xb is None else _as_rows(xb, "XB")[0]
     if at.shape[1] != bt.shape[1]:
         raise ValueError("XA and XB must have the same number of columns "
                          "(i.e. feature dimension.)")
     dev = at.device if at.is_cuda else _device(device)
+
+    def norms(v, m):
+        if v is None:
+            return None
+        t = torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64) if not isinstance(v, torch.Tensor) else v,
+                            dtype=torch.float64).reshape(-1)
+        if t.shape[0] != m:
+            raise ValueError("one norm per profile row is required")
+        return t.contiguous().to(dev)
+
     with torch.cuda.device(dev):
         if at.shape[0] == 0 or bt.shape[0] == 0:
             return _out(torch.empty((at.shape[0], bt.shape[0]), dtype=torch.float64, device=dev), a_np)
         ad = _to_dev(at, dev)
         bd = ad if xb is None else _to_dev(bt, dev)
-        _check_finite(ad, bd)
+        na = norms(norm_a, ad.shape[0])
+        nb = na if (xb is None and norm_b is None) else norms(norm_b, bd.shape[0])
         out = torch.empty((ad.shape[0], bd.shape[0]), dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().gmd_angle_block_f64(_ptr(ad), ad.shape[0], _ptr(bd), bd.shape[0], ad.shape[1],
-                                                  _ptr(out), _stream_ptr()))
+                                                  _ptr(na), _ptr(nb), _ptr(out), _stream_ptr()))
+        # a non-finite profile or norm gives a NaN pair, which is what the reference's
+        # FloatingPointError handler does with it too (refine.py:1548-1549)
         return _out(out, a_np)
 
 

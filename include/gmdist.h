@@ -173,6 +173,79 @@ GMD_API int gmd_scan_tc_sweep_f32(const void* qtiles, int64_t Nq, const void* ct
                      const uint32_t* perm, int sweep, uint32_t* cand_idx, float* cand_val,
                      float* cand_tau, void* stream);
 
+/* Pruned tensor-core scan (the default for large Euclidean problems; grouped.cu, order.cu,
+ * scan_tc_prune.cu).  The reference has no counterpart: KDTree.query (refine.py:653-665) is its only
+ * space-partitioning search; this is the same idea -- exact neighbours without looking at every pair --
+ * for the all-pairs / many-queries shapes.
+ *   Grouped order.  gmd_group_leaders_f64 picks "leaders" from a strided sample of ns rows by leader
+ * clustering (a sample becomes a leader unless an earlier leader lies within rfac x the median
+ * nearest-sample distance; at most cap); SYNCHRONISES the stream to return their number.  Outputs:
+ * Lt [D][cap] centred FP32 leader rows (dimension-major), lead_row [cap] their row numbers,
+ * lead_rows [cap][D] float64 copies (the candidate set of the nearest-leader search, which is this
+ * library's own k = 1 pipeline), info [2] = {leaders, float bits of the radius}.
+ * gmd_group_order: given every row's nearest leader and float64 distance to it, keys the rows by
+ * (leader, distance shell of width radius / 2; gmd_group_shells() shells), counting-sorts them with every
+ * leader's group padded to whole `tile`-row tiles:  perm[position] = row, 0xFFFFFFFF = padding
+ * (npos >= gmd_group_positions(N, ngroups, tile) positions), gstart [ngroups + 1] first tile of a group,
+ * tgroup [npos / tile] group of a tile (-1: padding only), grad [ngroups] (nullable) largest member
+ * distance of a group, rounded up; key [N] scratch.
+ *   gmd_prep_tc_grouped_f64 stages TC tiles through such a perm and records a ball per tile in
+ * tmeta [D + 1][nt_alloc] (scaled units: centroid, radius rounded up, -1 for a tile of padding).
+ *   gmd_tc_stage_grouped_f64 does all of it for a query and a candidate set (Q == C: all-pairs; Q a run
+ * of C's rows: the row-sharded path, keys are shared; otherwise Q is keyed by its own search) and fills
+ * the descriptor the scan takes; workspace from gmd_tc_grouped_workspace_bytes, tile buffers sized by
+ * gmd_tc_grouped_tiles_bytes(N rows, Nc, D).  stats_c / stats_q as for gmd_prep_tc_f64.
+ *   gmd_scan_tc_grouped_f32: the tcgen05 scan of gmd_scan_tc_f32, except that the CTA of a query tile
+ * first visits a window of its own group, takes T = its queries' largest k-th distance so far, and then
+ * loads only the candidate tiles whose ball bound |m_q - m_c| - r_q - r_c does not exceed T (bounds
+ * are evaluated with every rounding taken against them).  Outputs and the meaning of cand_tau are
+ * unchanged, so gmd_refine_topk_f64 / gmd_exact_rows_f64 finish it; results are identical to the full
+ * scan.  counters (device, in the descriptor): [0] tiles visited, [1] query tiles, [2] groups surviving. */
+typedef struct gmd_grouped {
+    int64_t npos_q, npos_c;               /* staged positions (rows + padding) */
+    int32_t ngroups, ng_alloc, nt_alloc_q, nt_alloc_c, same, reserved;
+    const uint32_t* perm_q;
+    const uint32_t* perm_c;
+    const int32_t* tgroup_q;
+    const int32_t* gstart_c;
+    const float* gmeta;                   /* [D + 1][ng_alloc] leaders + group radii, scaled units */
+    const float* tmeta_q;                 /* [D + 1][nt_alloc_q] */
+    const float* tmeta_c;                 /* [D + 1][nt_alloc_c] */
+    uint64_t* counters;                   /* [4] */
+} gmd_grouped;
+GMD_API int gmd_group_shells(void);
+GMD_API void gmd_group_params(int64_t N, int* ns, int* cap);
+GMD_API int64_t gmd_group_positions(int64_t N, int ngroups, int tile);
+GMD_API size_t gmd_group_leaders_workspace_bytes(int ns, int D);
+GMD_API int gmd_group_leaders_f64(const double* X, int64_t N, int D, const double* center, int ns, int cap, float rfac,
+                     float* Lt, int32_t* lead_row, double* lead_rows, int32_t* info, void* workspace,
+                     size_t workspace_bytes, int32_t* nlead_host, void* stream);
+GMD_API size_t gmd_group_order_workspace_bytes(int ngroups);
+GMD_API int gmd_group_order(const int32_t* lead, const double* dist, int64_t N, int ngroups, const int32_t* info,
+                     int tile, int32_t* key, float* grad, uint32_t* perm, int64_t npos, int32_t* gstart,
+                     int32_t* tgroup, void* workspace, size_t workspace_bytes, void* stream);
+GMD_API int gmd_prep_tc_grouped_f64(const double* X, int64_t Npos, int D, const double* center, int role,
+                     const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
+                     float* tmeta, int nt_alloc, void* stream);
+GMD_API int gmd_tc_group_meta(const float* Lt, int cap, const float* grad, int ngroups, int D, const float* stats_c,
+                     const float* stats_q, float* gmeta, int ng_alloc, void* stream);
+GMD_API int gmd_use_tc_prune(int64_t Nq, int64_t Nc, int k, int metric, int D);   /* the size policy of gmd_knn_f64 */
+GMD_API size_t gmd_tc_prune_max_tiles(int D, int kk);
+GMD_API size_t gmd_tc_grouped_tiles_bytes(int64_t N, int64_t Nc, int D);
+GMD_API size_t gmd_tc_grouped_workspace_bytes(int64_t Nq, int64_t Nc, int D);
+GMD_API int gmd_tc_stage_grouped_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                     const double* center, const float* stats_c, const float* stats_q, void* qtiles, void* ctiles,
+                     void* workspace, size_t workspace_bytes, gmd_grouped* out, void* stream);
+GMD_API int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const void* ctiles, int64_t Nc_pos, int D, int kk,
+                     int64_t c_index_offset, const float* stats_c, const float* stats_q,
+                     const uint32_t* perm_q, const uint32_t* perm_c, const int32_t* tgroup_q,
+                     const int32_t* gstart_c, int ngroups, const float* gmeta, int ng_alloc,
+                     const float* tmeta_q, int nt_alloc_q, const float* tmeta_c, int nt_alloc_c, int same,
+                     uint32_t* cand_idx, float* cand_val, float* cand_tau, uint64_t* counters, void* stream);
+GMD_API int gmd_scan_tc_grouped_f32(const void* qtiles, const void* ctiles, int D, int kk, int64_t c_index_offset,
+                     const float* stats_c, const float* stats_q, const gmd_grouped* g,
+                     uint32_t* cand_idx, float* cand_val, float* cand_tau, void* stream);
+
 /* float64 re-rank of the proposed candidates from the ORIGINAL rows, lowest-index tie
  * rule, plus the per-row certificate; uncertified rows are appended to fail_rows
  * (count in fail_count[0]) and finished by gmd_exact_rows_f64.                        */
@@ -213,11 +286,15 @@ GMD_API int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc
 GMD_API int gmd_cdist_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, int metric,
                   double* out, void* stream);
 
-/* Angles between coverage profiles, arccos(a.b / (|a| |b|)) for every pair of a small block
- * (RefineEngine.cDist / cDistBetweenBins, refine.py:1528-1583) -> out [mA, mB]; pairs the
- * reference skips (FloatingPointError: argument outside [-1, 1] or a zero norm) are NaN.  */
-GMD_API int gmd_angle_block_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D, double* out,
-                        void* stream);
+/* Angles between coverage profiles for every pair of a small block (RefineEngine.cDist /
+ * cDistBetweenBins, refine.py:1528-1583):
+ *     arccos(dot(A[i], B[j]) / (normA[i] * normB[j]))  -> out [mA, mB]
+ * normA / normB are the caller's normCoverages of the rows (refine.py:1546, 1578 divide by
+ * self.PM.normCoverages, loaded at profileManager.py:205, not by norms recomputed from the rows);
+ * null = the rows' own Euclidean norms.  Pairs the reference skips (FloatingPointError: argument
+ * outside [-1, 1], or a zero norm) are NaN.                                              */
+GMD_API int gmd_angle_block_f64(const double* A, int64_t mA, const double* B, int64_t mB, int D,
+                        const double* normA, const double* normB, double* out, void* stream);
 
 /* pdist(X, metric) -> condensed out [n(n-1)/2], scipy order (cluster.py:495, 497;
  * refine.py:1492; index map of mstore.py:1880-1888).                                  */

@@ -14,7 +14,7 @@ __all__ = [
     "best_match", "bmu_batch", "classify_contigs", "som_train_bmus",
     "whiten", "allpairs_cityblock", "kth_neighbour_radius", "radius_neighbours",
     "contraction_weights", "two_way_contraction_step", "kdtree_knn", "knn",
-    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal", "som_stamp", "som_train", "c_dist", "c_dist_between", "evenly_spaced_pts_z", "c_dist_rows", "c_dist_between_rows",
+    "k_dist", "k_dist_between", "small2indices", "knn_tie_aware_equal", "som_stamp", "som_train", "c_dist", "c_dist_between", "angle_pairs", "evenly_spaced_pts_z", "c_dist_rows", "c_dist_between_rows",
     "c_dist_merged_rows", "vq",
 ]
 
@@ -338,10 +338,34 @@ def _angle(a, b, na, nb):
             return None
 
 
-def c_dist(cov_rows: np.ndarray):
-    """RefineEngine.cDist, refine.py:1528-1551, on the selected rows; ``normCoverages`` is the
-    per-row Euclidean norm (profileManager.py)."""
-    norms = [np.linalg.norm(r) for r in cov_rows]
+def _row_norms(cov_rows, norms):
+    """``self.PM.normCoverages`` of the rows: an INPUT of the reference (loaded from its database,
+    profileManager.py:205).  None: the per-row Euclidean norm, which is how the fixtures make it."""
+    if norms is None:
+        return [np.linalg.norm(r) for r in cov_rows]
+    return list(np.asarray(norms, dtype=np.float64))
+
+
+def angle_pairs(cov1, cov2, norms1=None, norms2=None):
+    """Every pair of refine.py:1545-1546 / 1577-1578 -> (angle [m1, m2] with NaN where the reference
+    drops the pair, cosine argument [m1, m2] as the reference's arithmetic produced it)."""
+    n1, n2 = _row_norms(cov1, norms1), _row_norms(cov2, norms2)
+    ang = np.full((len(cov1), len(cov2)), np.nan)
+    arg = np.full((len(cov1), len(cov2)), np.nan)
+    for i in range(len(cov1)):
+        for j in range(len(cov2)):
+            with np.errstate(all='ignore'):
+                arg[i, j] = np.dot(cov1[i], cov2[j]) / (n1[i] * n2[j])
+            a = _angle(cov1[i], cov2[j], n1[i], n2[j])
+            if a is not None:
+                ang[i, j] = a
+    return ang, arg
+
+
+def c_dist(cov_rows: np.ndarray, norms=None):
+    """RefineEngine.cDist, refine.py:1528-1551, on the selected rows; ``norms`` =
+    ``normCoverages`` of those rows."""
+    norms = _row_norms(cov_rows, norms)
     angles = []
     for i in range(len(cov_rows)):
         for j in range(i + 1, len(cov_rows)):
@@ -351,10 +375,10 @@ def c_dist(cov_rows: np.ndarray):
     return float(np.median(angles)) if angles else float("nan")
 
 
-def c_dist_between(cov1: np.ndarray, cov2: np.ndarray):
+def c_dist_between(cov1: np.ndarray, cov2: np.ndarray, norms1=None, norms2=None):
     """RefineEngine.cDistBetweenBins, refine.py:1557-1583, on the selected rows."""
-    n1 = [np.linalg.norm(r) for r in cov1]
-    n2 = [np.linalg.norm(r) for r in cov2]
+    n1 = _row_norms(cov1, norms1)
+    n2 = _row_norms(cov2, norms2)
     angles = []
     for i in range(len(cov1)):
         for j in range(len(cov2)):
@@ -386,20 +410,26 @@ def _c_pick(transformed_cp, row_indices, max_in_bin=100):
     return row_indices
 
 
-def c_dist_rows(cov_profiles, transformed_cp, row_indices):
+def _pick_norms(norm_coverages, pick):
+    return None if norm_coverages is None else np.asarray(norm_coverages, dtype=np.float64)[pick]
+
+
+def c_dist_rows(cov_profiles, transformed_cp, row_indices, norm_coverages=None):
     """RefineEngine.cDist (refine.py:1528-1551) from the row indices of a bin."""
-    return c_dist(np.asarray(cov_profiles)[_c_pick(transformed_cp, row_indices)])
+    pick = _c_pick(transformed_cp, row_indices)
+    return c_dist(np.asarray(cov_profiles)[pick], _pick_norms(norm_coverages, pick))
 
 
-def c_dist_between_rows(cov_profiles, transformed_cp, rows1, rows2):
+def c_dist_between_rows(cov_profiles, transformed_cp, rows1, rows2, norm_coverages=None):
     """RefineEngine.cDistBetweenBins (refine.py:1557-1583) from the row indices of two bins."""
     cov = np.asarray(cov_profiles)
-    return c_dist_between(cov[_c_pick(transformed_cp, rows1)], cov[_c_pick(transformed_cp, rows2)])
+    p1, p2 = _c_pick(transformed_cp, rows1), _c_pick(transformed_cp, rows2)
+    return c_dist_between(cov[p1], cov[p2], _pick_norms(norm_coverages, p1), _pick_norms(norm_coverages, p2))
 
 
-def c_dist_merged_rows(cov_profiles, transformed_cp, rows1, rows2):
+def c_dist_merged_rows(cov_profiles, transformed_cp, rows1, rows2, norm_coverages=None):
     """RefineEngine.cDistMergedBins (refine.py:1553-1555)."""
-    return c_dist_rows(cov_profiles, transformed_cp, np.concatenate((rows1, rows2)))
+    return c_dist_rows(cov_profiles, transformed_cp, np.concatenate((rows1, rows2)), norm_coverages)
 
 
 def vq(obs: np.ndarray, code_book: np.ndarray):

@@ -298,7 +298,7 @@ def gen_cdist(mods, rng):
         np.seterr(**old)
     arrs = {f"rows{i}": r for i, r in enumerate(rows)}
     arrs.update({f"pick{i}": p for i, p in enumerate(picks)})
-    np.savez_compressed(OUT / "ref_cdist.npz", cov=cov, tcp=tcp, n_sets=len(rows), c_dist=np.array(cd),
+    np.savez_compressed(OUT / "ref_cdist.npz", cov=cov, tcp=tcp, norms=norms, n_sets=len(rows), c_dist=np.array(cd),
                         pairs=np.array(pairs), c_dist_between=np.array(cb), c_dist_merged=np.array(cm), **arrs)
     print("ref_cdist:", cd, cb[:3], cm)
 
@@ -311,11 +311,17 @@ def main():
     print("numpy", np.__version__, "scipy", scipy.__version__)
     mods = load_reference()
     rng = np.random.default_rng(20261019)
-    gen_bestmatch(mods, rng)
-    gen_som_train(mods, rng)
-    gen_contraction(mods, rng)
-    gen_kdist(mods, rng)
-    gen_cdist(mods, np.random.default_rng(20261020))
+    only = set(sys.argv[1:])                                # e.g. `make_reference_golden.py cdist`
+    if not only or "bestmatch" in only:
+        gen_bestmatch(mods, rng)
+    if not only or "som_train" in only:
+        gen_som_train(mods, rng)
+    if not only or "contraction" in only:
+        gen_contraction(mods, rng)
+    if not only or "kdist" in only:
+        gen_kdist(mods, rng)
+    if not only or "cdist" in only:
+        gen_cdist(mods, np.random.default_rng(20261020))
 
 
 if __name__ == "__main__":
