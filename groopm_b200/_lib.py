@@ -42,6 +42,8 @@ SIGNATURES = {
     "gmd_scan_tc_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmd_refine_topk_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gmd_refine_topk_order_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _int, _int, _int, _int, _int,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gmd_prep_tc_perm_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "gmd_scan_tc_sweep_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "gmd_group_shells": (_int, []),
@@ -53,7 +55,7 @@ SIGNATURES = {
     "gmd_group_order_workspace_bytes": (_sz, [_int]),
     "gmd_group_order": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "gmd_prep_tc_grouped_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
-    "gmd_tc_group_meta": (_int, [_vp, _int, _vp, _int, _int, _vp, _vp, _vp, _int, _vp]),
+    "gmd_tc_group_meta": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "gmd_use_tc_prune": (_int, [_i64, _i64, _int, _int, _int]),
     "gmd_tc_prune_max_tiles": (_sz, [_int, _int]),
     "gmd_tc_grouped_tiles_bytes": (_sz, [_i64, _i64, _int]),

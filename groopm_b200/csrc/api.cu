@@ -253,8 +253,9 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
              : gmd_scan_topk_f32(w.qtiles, Nq, w.ctiles, Nc, D, form, kk, nsplit, 0, w.cand_idx, w.cand_val,
                                  w.cand_tau, stream);
     if (rc != GMD_OK) return rc;
-    if ((rc = gmd_refine_topk_f64(Q, Nq, C, Nc, D, w.center, k, kk, nsplit, metric, form, w.cand_idx, w.cand_val,
-                                  w.cand_tau, w.stats, out_idx, out_dist, w.flags + 1, w.fail_rows, stream)) != GMD_OK)
+    if ((rc = gmd_refine_topk_order_f64(Q, Nq, C, Nc, D, w.center, k, kk, nsplit, metric, form, w.cand_idx, w.cand_val,
+                                        w.cand_tau, w.stats, out_idx, out_dist, w.flags + 1, w.fail_rows,
+                                        prune ? grouped.perm_q : nullptr, prune ? grouped.npos_q : 0, stream)) != GMD_OK)
         return rc;
     if ((rc = gmd_exact_rows_f64(Q, Nq, C, Nc, D, k, metric, w.flags + 1, w.fail_rows, out_idx, out_dist, w.exact_ws,
                                  w.exact_bytes, stream)) != GMD_OK)

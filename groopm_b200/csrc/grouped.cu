@@ -192,7 +192,7 @@ extern "C" int gmd_tc_stage_grouped_f64(const double* Q, int64_t Nq, const doubl
     if ((rc = gmd_prep_tc_grouped_f64(Q, npos_q, D, center, 0, stats_c, stats_q, perm_q, qtiles, L.tmeta_q, nt_q,
                                       stream)) != GMD_OK)
         return rc;
-    if ((rc = gmd_tc_group_meta(L.Lt, L.cap, L.grad, nlead, D, stats_c, stats_q, L.gmeta, L.cap, stream)) != GMD_OK)
+    if ((rc = gmd_tc_group_meta(L.Lt, L.grad, nlead, D, stats_c, stats_q, L.gmeta, L.cap, stream)) != GMD_OK)
         return rc;
     GMD_CUDA_CHECK(cudaMemsetAsync(L.counters, 0, 4 * sizeof(uint64_t), st));
     out->npos_q = npos_q;

@@ -66,7 +66,6 @@ __global__ void __launch_bounds__(256) key_scatter_kernel(const int32_t* __restr
 
 // ---------------------------------------------------------------- leader clustering of a row sample
 constexpr int LEAD_THREADS = 1024;
-constexpr int LEAD_BATCH = 8;          // samples tested against the leaders per step
 constexpr int LEAD_PROBES = 256;       // samples whose nearest-sample distance fixes the radius
 
 // sample i = row i * stride of X, centred, FP32 -> S[ns][D]
@@ -80,15 +79,15 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const double* __res
     S[e] = (float)(X[(size_t)(i * stride) * D + d] - (center ? center[d] : 0.0));
 }
 
-// distance from probe p (sample p * (ns / nprobe)) to its nearest DISTINCT sample; one warp per probe
+// distance from probe p (sample p * (ns / nprobe)) to its nearest DISTINCT sample; one block per probe
 __global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict__ S, int ns, int D, int nprobe,
                                                        float* __restrict__ nn) {
-    const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (w >= nprobe) return;
+    __shared__ float part[8];
+    const int w = blockIdx.x;
     const int p = w * (ns / nprobe);
     const float* a = S + (size_t)p * D;
     float best = __int_as_float(0x7f800000);
-    for (int j = lane; j < ns; j += 32) {
+    for (int j = threadIdx.x; j < ns; j += blockDim.x) {
         const float* b = S + (size_t)j * D;
         float d2 = 0.0f;
         for (int d = 0; d < D; ++d) {
@@ -98,24 +97,34 @@ __global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict_
         if (d2 > 0.0f) best = fminf(best, d2);
     }
     for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-    if (lane == 0) nn[w] = sqrtf(best);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int x = 1; x < 8; ++x) best = fminf(best, part[x]);
+        nn[w] = sqrtf(best);
+    }
 }
 
 // One block.  R = rfac x median(nn); then the samples in order: a sample farther than R from every
-// leader so far becomes a leader (at most cap).  Leaders are kept dimension-major, Lt[d][cap], so that
-// thread j's walk over "its" leader is coalesced across the block.
-// out: Lt, lead_row[cap] (row of X), info[0] = leaders, info[1] = float bits of R.
+// leader so far becomes a leader (at most cap).  The samples go through in batches of B: all threads
+// test the batch against the leaders that exist (thread = one sample x a share of the leaders; the batch
+// sits dimension-major in shared memory, the leader rows are warp-wide broadcasts), then warp 0 walks the
+// uncovered samples in order and tests each against the leaders the batch itself has produced so far.
+// out: L [cap][D] centred FP32 leader rows, lead_row[cap] (row of X), info[0] = leaders,
+// info[1] = float bits of R.
 __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __restrict__ S, int ns, long long stride,
                                                              int D, const float* __restrict__ nn, int nprobe,
-                                                             float rfac, int cap, float* __restrict__ Lt,
+                                                             float rfac, int cap, int B, float* __restrict__ L,
                                                              int32_t* __restrict__ lead_row,
                                                              int32_t* __restrict__ info) {
+    extern __shared__ float lsm[];
+    float* sT = lsm;                                   // [D][B] the batch, dimension-major
+    int* cov = reinterpret_cast<int*>(sT + (size_t)D * B);   // [B]
+    int* fresh = cov + B;                              // [B] batch members that became leaders (batch index)
     __shared__ float vals[LEAD_PROBES];
-    __shared__ float srow[LEAD_BATCH][GMD_MAX_D];
-    __shared__ unsigned covered;
     __shared__ int nlead_s;
     __shared__ float R2_s;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     // ---- median of the finite nearest-sample distances, by rank counting
     const bool probe = tid < nprobe;
     const float v = probe ? nn[tid] : __int_as_float(0x7f800000);
@@ -135,53 +144,57 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
     }
     __syncthreads();
     const float R2 = R2_s;
-    for (int i0 = 0; i0 < ns; i0 += LEAD_BATCH) {
-        const int nb = min(LEAD_BATCH, ns - i0);
-        for (int e = tid; e < nb * D; e += LEAD_THREADS) srow[e / D][e % D] = S[(size_t)i0 * D + e];
-        if (tid == 0) covered = 0u;
+    const int shares = LEAD_THREADS / B;               // threads per sample, each takes every shares-th leader
+    const int b = tid % B, share = tid / B;
+    for (int i0 = 0; i0 < ns; i0 += B) {
+        const int nb = min(B, ns - i0);
+        for (int e = tid; e < nb * D; e += LEAD_THREADS) {
+            const int r = e / D, d = e - r * D;
+            sT[(size_t)d * B + r] = S[(size_t)i0 * D + e];
+        }
+        for (int e = tid; e < B; e += LEAD_THREADS) cov[e] = 0;
         __syncthreads();
         const int nl = nlead_s;
-        unsigned mine = 0u;
-        for (int j = tid; j < nl; j += LEAD_THREADS) {
-            float d2[LEAD_BATCH];
-#pragma unroll
-            for (int b = 0; b < LEAD_BATCH; ++b) d2[b] = 0.0f;
-            for (int d = 0; d < D; ++d) {
-                const float lv = Lt[(size_t)d * cap + j];
-#pragma unroll
-                for (int b = 0; b < LEAD_BATCH; ++b) {
-                    const float t = srow[b][d] - lv;
-                    d2[b] = fmaf(t, t, d2[b]);
+        if (b < nb) {
+            bool hit = false;
+            for (int j = share; j < nl && !hit; j += shares) {
+                const float* l = L + (size_t)j * D;    // the same row for the whole warp: broadcast
+                float d2 = 0.0f;
+                for (int d = 0; d < D; ++d) {
+                    const float t = sT[(size_t)d * B + b] - l[d];
+                    d2 = fmaf(t, t, d2);
                 }
+                hit = d2 <= R2;
             }
-#pragma unroll
-            for (int b = 0; b < LEAD_BATCH; ++b) mine |= (d2[b] <= R2) ? (1u << b) : 0u;
+            if (hit) cov[b] = 1;
         }
-        mine = __reduce_or_sync(0xFFFFFFFFu, mine);
-        if ((tid & 31) == 0 && mine) atomicOr(&covered, mine);
         __syncthreads();
-        if (tid == 0) {
-            const unsigned cov = covered;
-            int added[LEAD_BATCH], na = 0;
-            for (int b = 0; b < nb; ++b) {
-                if ((cov >> b) & 1u) continue;
-                if (nlead_s >= cap) break;
-                bool ok = true;
-                for (int x = 0; x < na && ok; ++x) {          // leaders added earlier in this batch
+        if (tid < 32) {
+            int nf = 0;                                // leaders this batch has produced (warp-uniform)
+            for (int r = 0; r < nb; ++r) {
+                if (cov[r]) continue;
+                if (nlead_s + nf >= cap) break;
+                bool near = false;
+                for (int x = lane; x < nf; x += 32) {
+                    const int o = fresh[x];
                     float d2 = 0.0f;
                     for (int d = 0; d < D; ++d) {
-                        const float t = srow[b][d] - srow[added[x]][d];
+                        const float t = sT[(size_t)d * B + r] - sT[(size_t)d * B + o];
                         d2 = fmaf(t, t, d2);
                     }
-                    ok = d2 > R2;
+                    near |= d2 <= R2;
                 }
-                if (!ok) continue;
-                const int j = nlead_s;
-                for (int d = 0; d < D; ++d) Lt[(size_t)d * cap + j] = srow[b][d];
-                lead_row[j] = (int32_t)((long long)(i0 + b) * stride);
-                added[na++] = b;
-                nlead_s = j + 1;
+                if (__any_sync(0xFFFFFFFFu, near)) continue;
+                const int j = nlead_s + nf;
+                for (int d = lane; d < D; d += 32) L[(size_t)j * D + d] = sT[(size_t)d * B + r];
+                if (lane == 0) {
+                    lead_row[j] = (int32_t)((long long)(i0 + r) * stride);
+                    fresh[nf] = r;
+                }
+                __syncwarp();
+                ++nf;
             }
+            if (lane == 0) nlead_s += nf;
         }
         __syncthreads();
     }
@@ -314,9 +327,9 @@ extern "C" size_t gmd_group_leaders_workspace_bytes(int ns, int D) {
 }
 
 extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const double* center, int ns, int cap, float rfac,
-                                     float* Lt, int32_t* lead_row, double* lead_rows, int32_t* info, void* workspace,
+                                     float* L, int32_t* lead_row, double* lead_rows, int32_t* info, void* workspace,
                                      size_t workspace_bytes, int32_t* nlead_host, void* stream) {
-    GMD_REQUIRE(X && Lt && lead_row && lead_rows && info && workspace && nlead_host, GMD_ERR_BAD_ARG,
+    GMD_REQUIRE(X && L && lead_row && lead_rows && info && workspace && nlead_host, GMD_ERR_BAD_ARG,
                 "group_leaders: null pointer");
     GMD_REQUIRE(N > 0 && D >= 1 && D <= GMD_MAX_D && ns >= 1 && ns <= N && cap >= 1 && rfac > 0.0f, GMD_ERR_BAD_ARG,
                 "group_leaders: bad sizes (N=%lld ns=%d cap=%d)", (long long)N, ns, cap);
@@ -331,9 +344,12 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
     const long long ne = (long long)ns * D;
     gather_samples_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, stride, ns, D, center, S);
     GMD_CUDA_CHECK(cudaGetLastError());
-    sample_nn_kernel<<<(unsigned)((nprobe * 32 + 255) / 256), 256, 0, st>>>(S, ns, D, nprobe, nn);
+    sample_nn_kernel<<<(unsigned)nprobe, 256, 0, st>>>(S, ns, D, nprobe, nn);
     GMD_CUDA_CHECK(cudaGetLastError());
-    leader_kernel<<<1, LEAD_THREADS, 0, st>>>(S, ns, stride, D, nn, nprobe, rfac, cap, Lt, lead_row, info);
+    const int B = D <= 48 ? 256 : (D <= 96 ? 128 : 64);       // batch: [D][B] floats of shared memory
+    const size_t lsm = ((size_t)D * B + 2 * (size_t)B) * sizeof(float);
+    GMD_CUDA_CHECK(cudaFuncSetAttribute(leader_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, stride, D, nn, nprobe, rfac, cap, B, L, lead_row, info);
     GMD_CUDA_CHECK(cudaGetLastError());
     int32_t h[2] = {0, 0};
     GMD_CUDA_CHECK(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
                                                      const float* __restrict__ cand_tau,
                                                      const float* __restrict__ stats, int32_t* __restrict__ out_idx,
                                                      double* __restrict__ out_dist, int32_t* fail_count,
-                                                     int32_t* __restrict__ fail_rows) {
+                                                     int32_t* __restrict__ fail_rows,
+                                                     const uint32_t* __restrict__ qorder, long long nqpos) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int RPW = 32 / G;  // rows per warp
     constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -62,8 +63,17 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
     const int nslots = (blockDim.x >> 5) * RPW;
     double* sd = reinterpret_cast<double*>(sm_raw) + (size_t)slot * m;
     uint32_t* si = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(sm_raw) + (size_t)nslots * m) + (size_t)slot * m;
-    const long long q = (long long)blockIdx.x * nslots + slot;
-    const bool live = q < Nq;                          // dead groups still take part in the shuffles
+    // qorder (nullable): the queries are visited in the scan's staging order (position -> row,
+    // GMD_EMPTY_IDX = padding), so that consecutive blocks re-rank against the same neighbourhood of
+    // candidate rows and find them in L2
+    const long long qp = (long long)blockIdx.x * nslots + slot;
+    long long q = qp;
+    bool live = qp < Nq;                               // dead groups still take part in the shuffles
+    if (qorder) {
+        const uint32_t r = qp < nqpos ? qorder[qp] : GMD_EMPTY_IDX;
+        live = r != GMD_EMPTY_IDX;
+        q = live ? (long long)r : 0;
+    }
     const double* qrow = Q + (size_t)(live ? q : 0) * D;
     const uint32_t* ci = cand_idx + (size_t)(live ? q : 0) * m;
 
@@ -364,11 +374,11 @@ __global__ void __launch_bounds__(EX_THREADS) exact_rows_kernel(const double* __
 
 }  // namespace
 
-extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
-                                   const double* center, int k, int kk, int nsplit, int metric, int form,
-                                   const uint32_t* cand_idx, const float* cand_val, const float* cand_tau,
-                                   const float* stats, int32_t* out_idx, double* out_dist, int32_t* fail_count, int32_t* fail_rows,
-                                   void* stream) {
+extern "C" int gmd_refine_topk_order_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                                         const double* center, int k, int kk, int nsplit, int metric, int form,
+                                         const uint32_t* cand_idx, const float* cand_val, const float* cand_tau,
+                                         const float* stats, int32_t* out_idx, double* out_dist, int32_t* fail_count,
+                                         int32_t* fail_rows, const uint32_t* qorder, int64_t nqpos, void* stream) {
     GMD_REQUIRE(Q && C && cand_idx && cand_val && cand_tau && stats && out_idx && out_dist && fail_count && fail_rows,
                 GMD_ERR_BAD_ARG, "refine: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1 && k >= 1 && kk >= k && nsplit >= 1 && k <= Nc, GMD_ERR_BAD_ARG,
@@ -381,12 +391,23 @@ extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C,
     GMD_REQUIRE(smem <= 200 * 1024, GMD_ERR_UNSUPPORTED, "refine: kk*nsplit=%d too large", kk * nsplit);
     auto kern = narrow ? refine_kernel<8> : refine_kernel<32>;
     GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((Nq + rows_per_block - 1) / rows_per_block);
+    const int64_t nslots = qorder ? nqpos : Nq;
+    GMD_REQUIRE(nslots > 0, GMD_ERR_BAD_ARG, "refine: empty query order");
+    const unsigned grid = (unsigned)((nslots + rows_per_block - 1) / rows_per_block);
     kern<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, Nq, C, D, center, k, kk, nsplit, metric, form, cand_idx,
                                                         cand_val, cand_tau, stats, out_idx, out_dist, fail_count,
-                                                        fail_rows);
+                                                        fail_rows, qorder, nqpos);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
+}
+
+extern "C" int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                                   const double* center, int k, int kk, int nsplit, int metric, int form,
+                                   const uint32_t* cand_idx, const float* cand_val, const float* cand_tau,
+                                   const float* stats, int32_t* out_idx, double* out_dist, int32_t* fail_count, int32_t* fail_rows,
+                                   void* stream) {
+    return gmd_refine_topk_order_f64(Q, Nq, C, Nc, D, center, k, kk, nsplit, metric, form, cand_idx, cand_val, cand_tau,
+                                     stats, out_idx, out_dist, fail_count, fail_rows, nullptr, 0, stream);
 }
 
 extern "C" size_t gmd_exact_workspace_bytes(int64_t Nq) {

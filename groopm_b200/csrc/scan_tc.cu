@@ -337,16 +337,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t cbase = (uint32_t)(t + t_first < ntiles_c ? t + t_first : t + t_first - ntiles_c) * TM;
             const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TM);
-            // all 128 columns of the row in flight at once, then the accumulator stage goes back
+            // all 128 columns of the row in one load, then the accumulator stage goes back
             uint32_t r0[32], r1[32], r2[32], r3[32];
-            tmem_ld32(trow, r0);
-            tmem_ld32(trow + 32, r1);
-            tmem_ld32(trow + 64, r2);
-            tmem_ld32(trow + 96, r3);
-            tmem_ld_wait(r0);
-            tmem_ld_wait(r1);
-            tmem_ld_wait(r2);
-            tmem_ld_wait(r3);
+            tmem_ld128_sync4(trow, r0, r1, r2, r3);   // load and wait in ONE statement (see tc_common.cuh)
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);

@@ -34,7 +34,7 @@
 
 namespace gmd_tc {
 
-constexpr int LCAP = 1024;                     // tiles per round
+constexpr int LCAP = 1024;                     // tiles per round (DUAL: half)
 constexpr int WMAX = 32;                       // tiles of the opening window
 constexpr int META_MAX = GMD_MAX_D + 4;        // centroid + radius of the query tile in shared memory
 constexpr float LB_REL = 1.0f / 16384.0f;      // relative slack on every FP32-evaluated term of a bound
@@ -71,8 +71,14 @@ __device__ __forceinline__ float ball_bound(float d2, float rsum) {
     return sqrtf(d2) * (1.0f - LB_REL) - rsum * (1.0f + LB_REL) - LB_ABS;
 }
 
-template <int NKB>
-__global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneParams p) {
+// DUAL: two CTAs per SM.  With few tiles to visit the scan is bound by the selection threads' dependent
+// shared-memory round trips (heap updates), not by the tensor pipe, and a CTA's four selection warps -- one
+// per scheduler -- cannot hide them; a second resident CTA doubles the queries in flight per SM.  Each CTA
+// then takes half the resources: 2 accumulator stages (256 tensor-memory columns), a 2-stage ring, a
+// 12-deep hit queue per thread, and reads an accumulator row in two halves of 64 columns so that the
+// selection threads fit the 144 registers two CTAs leave each thread.  NKB == 1 only.
+template <int NKB, bool DUAL, int NA_ = (DUAL ? 2 : NACC), bool HALF = DUAL, int MINB = (DUAL ? 2 : 1)>
+__global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const PruneParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const long long qt = blockIdx.x;
     const int grp = p.tgroup_q[qt];
@@ -81,6 +87,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int nkb = NKB;
     constexpr int TILE_B = tile_bytes(nkb);
+    constexpr int NA = NA_;                                // accumulator stages
+    constexpr int TQP = DUAL ? 12 : TQ;                    // parked hits per selection thread
+    constexpr int LC = DUAL ? LCAP / 2 : LCAP;
     const int ns = p.ns, kk = p.kk, kkp = kk | 1, D = p.D;
     const int nw = (p.ntiles_c + 31) >> 5;
     unsigned char* Aimg = base;
@@ -93,9 +102,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
     uint64_t* qbar = bars + 2 * NS_MAX + 2 * NACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS_MAX + 2 * NACC + 2);
     uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NS_MAX + 2 * NACC + 4);
-    uint64_t* lists = reinterpret_cast<uint64_t*>(queues + TQ * TM);
-    uint32_t* tlist = reinterpret_cast<uint32_t*>(lists + (size_t)TM * kkp);   // [LCAP] tiles of the round / groups
-    float* mq = reinterpret_cast<float*>(tlist + LCAP);                        // [META_MAX] centroid, radius
+    uint64_t* lists = reinterpret_cast<uint64_t*>(queues + TQP * TM);
+    uint32_t* tlist = reinterpret_cast<uint32_t*>(lists + (size_t)TM * kkp);   // [LC] tiles of the round / groups
+    float* mq = reinterpret_cast<float*>(tlist + LC);                          // [META_MAX] centroid, radius
     float* Tw = mq + META_MAX;                                                 // [4] per selection warp
     int* ctl = reinterpret_cast<int*>(Tw + 4);                                 // [2][2] (count, pending) by round parity
     uint32_t* visited = reinterpret_cast<uint32_t*>(ctl + 4);                  // [nw]
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
             mbar_init(&full[s], 1);
             mbar_init(&sfree[s], 1);
         }
-        for (int a = 0; a < NACC; ++a) {
+        for (int a = 0; a < NA; ++a) {
             mbar_init(&tdone[a], 1);
             mbar_init(&tempty[a], 4);
         }
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
     for (int e = tid; e <= D; e += NTHREADS) mq[e] = p.tmeta_q[(size_t)e * p.nt_alloc_q + qt];
     if (tid < 4) Tw[tid] = __int_as_float(0x7f800000);     // no threshold yet: nothing can be pruned
     if (warp == W_ISSUE) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NA * TM));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
     const int row = quarter * 32 + lane;                   // only meaningful for the selection warps
     uint64_t* h = lists + (size_t)row * kkp;
     uint2* myq = queues + row;
-    int qcnt = 0;
+    int qcnt = 0, hn = 0;                                  // parked hits; entries in the top-kk set
     float thr = __int_as_float(0x7f800000);
     float uthr = __int_as_float(0xff800000);
     const long long qpos = qt * TM + row;
@@ -201,12 +210,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
                 const float lb = ball_bound(d2, rq + p.gmeta[(size_t)D * p.ng_alloc + g]);
                 if (!(lb > T)) {
                     const int slot = atomicAdd(nsurv, 1);
-                    if (slot < LCAP) tlist[slot] = (uint32_t)g;
+                    if (slot < LC) tlist[slot] = (uint32_t)g;
                 }
             }
             __syncthreads();
             const int ng = *nsurv;
-            const bool all = ng > LCAP;                   // list overflow: walk every group
+            const bool all = ng > LC;                     // list overflow: walk every group
             const int ngl = all ? p.ngroups : ng;
             // tiles of the surviving groups: a warp per group, a lane per tile
             for (int gi = warp; gi < ngl; gi += NTHREADS / 32) {
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
                     while (bits) {
                         const int b = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        if (pos < LCAP)
+                        if (pos < LC)
                             tlist[pos] = (uint32_t)(w * 32 + b);
                         else
                             keep |= 1u << b;
@@ -259,8 +268,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
                         visited[w] |= orig & ~keep;
                     }
                     left |= __any_sync(FULLW, keep != 0u);
-                    n = min(LCAP, n + total);
-                    if (n >= LCAP && w0 + 32 < nw) {       // the list is full: whatever is left waits for the next round
+                    n = min(LC, n + total);
+                    if (n >= LC && w0 + 32 < nw) {       // the list is full: whatever is left waits for the next round
                         left = true;
                         break;
                     }
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
                             // a stage that held the last K block of a tile is free when the tile's accumulator
                             // is complete (tdone), any other when the MMAs of its K block are (sfree)
                             if (p_pkb == nkb - 1) {
-                                mbar_wait_backoff(&tdone[p_pt % NACC], (uint32_t)(p_pt / NACC) & 1u, 64);
+                                mbar_wait_backoff(&tdone[p_pt % NA], (uint32_t)(p_pt / NA) & 1u, 64);
                             } else {
                                 mbar_wait_backoff(&sfree[p_s], (p_sph >> p_s) & 1u, 64);
                                 p_sph ^= 1u << p_s;
@@ -311,8 +320,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
                         while (i_s >= ns) i_s -= ns, i_ph ^= 1u;
                         continue;
                     }
-                    const int a = (int)(t % NACC);
-                    if (t >= NACC) mbar_wait(&tempty[a], (uint32_t)((t / NACC) - 1) & 1u);
+                    const int a = (int)(t % NA);
+                    if (t >= NA) mbar_wait(&tempty[a], (uint32_t)((t / NA) - 1) & 1u);
                     const uint32_t acc = tmem + (uint32_t)(a * TM);
 #pragma unroll
                     for (int kb = 0; kb < nkb; ++kb) {
@@ -339,77 +348,127 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
                 qnv = reinterpret_cast<const float*>(Aimg + (size_t)nkb * KB_B)[row];
             }
             for (long long t = tbase; t < tbase + cnt; ++t) {
-                const int a = (int)(t % NACC);
-                mbar_wait(&tdone[a], (uint32_t)(t / NACC) & 1u);
+                const int a = (int)(t % NA);
+                mbar_wait(&tdone[a], (uint32_t)(t / NA) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t cbase = tlist[t - tbase] * TM;
                 const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TM);
-                uint32_t r0[32], r1[32], r2[32], r3[32];
-                tmem_ld32(trow, r0);
-                tmem_ld32(trow + 32, r1);
-                tmem_ld32(trow + 64, r2);
-                tmem_ld32(trow + 96, r3);
-                tmem_ld_wait(r0);
-                tmem_ld_wait(r1);
-                tmem_ld_wait(r2);
-                tmem_ld_wait(r3);
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[a]);
-                float gm[16];
-                auto tree = [&](const uint32_t (&r)[32], int b) {
+                // group maxima of 8 columns as shallow trees, one vote per batch of columns, then 8 values at a
+                // time: park what beats the (possibly stale) threshold, drain all the warp's queues side by
+                // side when one of them is nearly full
+                auto tree = [&](const uint32_t (&r)[32], float* gm) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float m0 = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
                         const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4])), __uint_as_float(r[8 * g + 5]));
                         const float m2 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-                        gm[4 * b + g] = fmaxf(fmaxf(m0, m1), m2);
+                        gm[g] = fmaxf(fmaxf(m0, m1), m2);
                     }
                 };
-                tree(r0, 0);
-                tree(r1, 1);
-                tree(r2, 2);
-                tree(r3, 3);
-                float cm;
-                {
-                    const float a0 = fmaxf(fmaxf(gm[0], gm[1]), gm[2]), a1 = fmaxf(fmaxf(gm[3], gm[4]), gm[5]);
-                    const float a2 = fmaxf(fmaxf(gm[6], gm[7]), gm[8]), a3 = fmaxf(fmaxf(gm[9], gm[10]), gm[11]);
-                    const float a4 = fmaxf(fmaxf(gm[12], gm[13]), gm[14]);
-                    cm = fmaxf(fmaxf(fmaxf(a0, a1), a2), fmaxf(fmaxf(a3, a4), gm[15]));
-                }
-                if (!__any_sync(FULLW, cm > uthr)) continue;
-                unsigned mine = 0;
-#pragma unroll
-                for (int g = 0; g < 16; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
-                const unsigned hot = __reduce_or_sync(FULLW, mine);
-                auto park = [&](const uint32_t (&r)[32], int b) {
+                auto park = [&](const uint32_t (&r)[32], unsigned hot, uint32_t c0) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        if (hot & (1u << (4 * b + g))) {
+                        if (hot & (1u << g)) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float u = __uint_as_float(r[8 * g + j]);
                                 if (u > uthr) {
-                                    myq[qcnt * TM] = make_uint2(cbase + 32 * b + 8 * g + j, __float_as_uint(-2.0f * u));
+                                    myq[qcnt * TM] = make_uint2(c0 + 8 * g + j, __float_as_uint(-2.0f * u));
                                     ++qcnt;
                                 }
                             }
-                            if (__any_sync(FULLW, qcnt > TQ - 8)) {
-                                thr = drain_own(h, kk, myq, qcnt);
+                            if (__any_sync(FULLW, qcnt > TQP - 8)) {
+                                {
+                                    const DrainState ds = drain_fill(h, kk, hn, myq, qcnt);
+                                    thr = ds.thr;
+                                    hn = ds.hn;
+                                }
                                 uthr = -0.5f * thr;
                                 qcnt = 0;
                             }
                         }
                     }
                 };
-                park(r0, 0);
-                park(r1, 1);
-                park(r2, 2);
-                park(r3, 3);
+                if constexpr (HALF) {
+                    uint32_t r0[32], r1[32];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        tmem_ld64_sync(trow + 64 * half, r0, r1);
+                        if (half == 1) {
+                            asm volatile("tcgen05.fence::before_thread_sync;");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[a]);
+                        }
+                        float gm[8];
+                        tree(r0, gm);
+                        tree(r1, gm + 4);
+                        const float cm = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])),
+                                               fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
+                        if (!__any_sync(FULLW, cm > uthr)) continue;
+                        unsigned mine = 0;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
+                        const unsigned hot = __reduce_or_sync(FULLW, mine);
+                        park(r0, hot & 15u, cbase + 64 * half);
+                        park(r1, hot >> 4, cbase + 64 * half + 32);
+                    }
+                } else {
+                    uint32_t r[128];
+                    tmem_ld128_sync(trow, r);
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[a]);
+                    float gm[16];
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) {
+                        const float m0 = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
+                        const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4])), __uint_as_float(r[8 * g + 5]));
+                        const float m2 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                        gm[g] = fmaxf(fmaxf(m0, m1), m2);
+                    }
+                    float cm;
+                    {
+                        const float a0 = fmaxf(fmaxf(gm[0], gm[1]), gm[2]), a1 = fmaxf(fmaxf(gm[3], gm[4]), gm[5]);
+                        const float a2 = fmaxf(fmaxf(gm[6], gm[7]), gm[8]), a3 = fmaxf(fmaxf(gm[9], gm[10]), gm[11]);
+                        const float a4 = fmaxf(fmaxf(gm[12], gm[13]), gm[14]);
+                        cm = fmaxf(fmaxf(fmaxf(a0, a1), a2), fmaxf(fmaxf(a3, a4), gm[15]));
+                    }
+                    if (!__any_sync(FULLW, cm > uthr)) continue;
+                    unsigned mine = 0;
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
+                    const unsigned hot = __reduce_or_sync(FULLW, mine);
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) {
+                        if (hot & (1u << g)) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float u = __uint_as_float(r[8 * g + j]);
+                                if (u > uthr) {
+                                    myq[qcnt * TM] = make_uint2(cbase + 8 * g + j, __float_as_uint(-2.0f * u));
+                                    ++qcnt;
+                                }
+                            }
+                            if (__any_sync(FULLW, qcnt > TQP - 8)) {
+                                {
+                                    const DrainState ds = drain_fill(h, kk, hn, myq, qcnt);
+                                    thr = ds.thr;
+                                    hn = ds.hn;
+                                }
+                                uthr = -0.5f * thr;
+                                qcnt = 0;
+                            }
+                        }
+                    }
+                }
             }
             // end of the round: fold what is parked, publish the warp's largest threshold DISTANCE
             // (scaled units; padding rows do not count)
-            thr = drain_own(h, kk, myq, qcnt);
+            {
+                                    const DrainState ds = drain_fill(h, kk, hn, myq, qcnt);
+                                    thr = ds.thr;
+                                    hn = ds.hn;
+                                }
             uthr = -0.5f * thr;
             qcnt = 0;
             float tq = 0.0f;
@@ -449,9 +508,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
             p.cand_idx[ob + x] = oi;
             p.cand_val[ob + x] = vv;
         }
-        float tau = thr;
-        if (h[0] != GMD_EMPTY_KEY) tau = fmaxf(tau + qnv, 0.0f) * unscale;
-        p.cand_tau[q] = tau;
+        // a set that never filled lists every candidate it was shown: nothing is bounded by it
+        p.cand_tau[q] = hn == kk ? fmaxf(thr + qnv, 0.0f) * unscale : __int_as_float(0x7f800000);
     }
     if (tid == 0) {
         if (tbase == 0) mbar_wait(qbar, 0);                // nothing was scanned: the query tile's copy must still land
@@ -462,11 +520,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_prune_kernel(const PruneP
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    if (warp == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NA * TM));
 }
 
 // leader rows and group radii in the scan's scaled units, dimension-major
-__global__ void __launch_bounds__(256) group_meta_kernel(const float* __restrict__ Lt, int cap, const float* __restrict__ grad,
+__global__ void __launch_bounds__(256) group_meta_kernel(const float* __restrict__ L, const float* __restrict__ grad,
                                                         int ngroups, int D, const float* __restrict__ stats_c,
                                                         const float* __restrict__ stats_q, float* __restrict__ gmeta,
                                                         int ng_alloc) {
@@ -475,28 +533,36 @@ __global__ void __launch_bounds__(256) group_meta_kernel(const float* __restrict
     const int d = e / ngroups, g = e - d * ngroups;
     const float scale = ldexpf(1.0f, gmd_tc_exponent(stats_c[0], stats_q[0]));
     // the radius is a float64 distance between ORIGINAL rows, rounded up; LB_ABS covers the centring
-    gmeta[(size_t)d * ng_alloc + g] = d < D ? Lt[(size_t)d * cap + g] * scale : grad[g] * scale * (1.0f + 1.0f / 1048576.0f);
+    gmeta[(size_t)d * ng_alloc + g] = d < D ? L[(size_t)g * D + d] * scale : grad[g] * scale * (1.0f + 1.0f / 1048576.0f);
 }
 
 }  // namespace gmd_tc
+
+namespace {
+// shared memory of one CTA without the ring and the two bitmasks
+size_t prune_fixed_smem(int nkb, int kk, bool dual) {
+    using namespace gmd_tc;
+    return 1024 + (size_t)tile_bytes(nkb) + 512 + (size_t)(dual ? 12 : TQ) * TM * 8 + (size_t)TM * (kk | 1) * 8 +
+           (size_t)(dual ? LCAP / 2 : LCAP) * 4 + (size_t)META_MAX * 4 + 64;
+}
+constexpr size_t DUAL_SMEM_LIMIT = (228 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved for each
+}  // namespace
 
 extern "C" size_t gmd_tc_prune_max_tiles(int D, int kk) {
     using namespace gmd_tc;
     const int nkb = tc_nkb(D);
     if (nkb > MAX_KB) return 0;
-    const size_t fixed = 1024 + (size_t)tile_bytes(nkb) + 512 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8 +
-                         (size_t)LCAP * 4 + (size_t)META_MAX * 4 + 64;
-    const size_t need = fixed + (size_t)std::max(2, nkb + 1) * KB_B;   // at least nkb + 1 ring stages
+    const size_t need = prune_fixed_smem(nkb, kk, false) + (size_t)std::max(2, nkb + 1) * KB_B;   // >= nkb + 1 ring stages
     if (need >= GMD_SMEM_LIMIT) return 0;
     return (size_t)(GMD_SMEM_LIMIT - need) / 8 * 32;                  // two bitmask words per 32 tiles
 }
 
-extern "C" int gmd_tc_group_meta(const float* Lt, int cap, const float* grad, int ngroups, int D, const float* stats_c,
+extern "C" int gmd_tc_group_meta(const float* L, const float* grad, int ngroups, int D, const float* stats_c,
                                  const float* stats_q, float* gmeta, int ng_alloc, void* stream) {
-    GMD_REQUIRE(Lt && grad && stats_c && stats_q && gmeta && ngroups > 0 && ngroups <= cap && ngroups <= ng_alloc && D >= 1,
+    GMD_REQUIRE(L && grad && stats_c && stats_q && gmeta && ngroups > 0 && ngroups <= ng_alloc && D >= 1,
                 GMD_ERR_BAD_ARG, "tc_group_meta: bad arguments");
     const int n = (D + 1) * ngroups;
-    gmd_tc::group_meta_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(Lt, cap, grad, ngroups, D, stats_c, stats_q,
+    gmd_tc::group_meta_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(L, grad, ngroups, D, stats_c, stats_q,
                                                                                 gmeta, ng_alloc);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
@@ -523,9 +589,17 @@ extern "C" int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const v
     GMD_REQUIRE((size_t)ntiles_c <= gmd_tc_prune_max_tiles(D, kk), GMD_ERR_UNSUPPORTED,
                 "scan_tc_prune: %d candidate tiles exceed the shared-memory bitmasks", ntiles_c);
     const int nw = (ntiles_c + 31) / 32;
-    const size_t fixed = 1024 + (size_t)tile_bytes(nkb) + 512 + (size_t)TQ * TM * 8 + (size_t)TM * (kk | 1) * 8 +
-                         (size_t)LCAP * 4 + (size_t)META_MAX * 4 + 64 + (size_t)nw * 8;
-    const int ns = (int)std::min<size_t>(std::min(NS_MAX, NACC * nkb), (GMD_SMEM_LIMIT - fixed) / KB_B);
+    // two CTAs per SM when a CTA's half fits (one K block, GMD_TC_DUAL=0 switches it off)
+    // EXPERIMENTAL, off unless GMD_TC_DUAL=1: the builds that cap the registers for two CTAs per SM return wrong
+    // accumulators (cause not found yet; the one-CTA build of the same code is correct)
+    bool dual = nkb == 1 && prune_fixed_smem(nkb, kk, true) + (size_t)nw * 8 + 2 * (size_t)KB_B <= DUAL_SMEM_LIMIT;
+    {
+        const char* env = getenv("GMD_TC_DUAL");
+        dual = dual && env && atoi(env) != 0;
+    }
+    const size_t fixed = prune_fixed_smem(nkb, kk, dual) + (size_t)nw * 8;
+    const int ns = dual ? 2
+                        : (int)std::min<size_t>(std::min(NS_MAX, NACC * nkb), (GMD_SMEM_LIMIT - fixed) / KB_B);
     GMD_REQUIRE(ns >= 2, GMD_ERR_UNSUPPORTED, "scan_tc_prune: D=%d kk=%d needs more than 227 KB of shared memory", D, kk);
     const size_t smem = fixed + (size_t)ns * KB_B;
     PruneParams p;
@@ -558,16 +632,24 @@ extern "C" int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const v
     p.counters = (unsigned long long*)counters;
     auto launch = [&](auto kern) -> int {
         GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         kern<<<(unsigned)ntiles_q, NTHREADS, smem, (cudaStream_t)stream>>>(p);
         return GMD_OK;
     };
     int rc;
     switch (nkb) {
-        case 1: rc = launch(scan_tc_prune_kernel<1>); break;
-        case 2: rc = launch(scan_tc_prune_kernel<2>); break;
-        case 3: rc = launch(scan_tc_prune_kernel<3>); break;
-        case 4: rc = launch(scan_tc_prune_kernel<4>); break;
-        default: rc = launch(scan_tc_prune_kernel<5>); break;
+        case 1: {
+            const int var = getenv("GMD_TC_VAR") ? atoi(getenv("GMD_TC_VAR")) : 0;   // (temporary: isolating the DUAL failure)
+            if (!dual) rc = launch(scan_tc_prune_kernel<1, false>);
+            else if (var == 1) rc = launch(scan_tc_prune_kernel<1, true, 2, false, 1>);
+            else if (var == 2) rc = launch(scan_tc_prune_kernel<1, true, 2, true, 1>);
+            else rc = launch(scan_tc_prune_kernel<1, true>);
+            break;
+        }
+        case 2: rc = launch(scan_tc_prune_kernel<2, false>); break;
+        case 3: rc = launch(scan_tc_prune_kernel<3, false>); break;
+        case 4: rc = launch(scan_tc_prune_kernel<4, false>); break;
+        default: rc = launch(scan_tc_prune_kernel<5, false>); break;
     }
     if (rc != GMD_OK) return rc;
     GMD_CUDA_CHECK(cudaGetLastError());

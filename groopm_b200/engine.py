@@ -240,10 +240,13 @@ class KnnPipeline:
                                               _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))
 
     def refine(self, q: torch.Tensor, c: torch.Tensor):
-        _lib.check(self.lib.gmd_refine_topk_f64(
+        # after a pruned scan the queries are re-ranked in their staging order (candidate rows stay in L2)
+        qorder, nqpos = (self.grouped.perm_q, self.grouped.npos_q) if self.prune else (0, 0)
+        _lib.check(self.lib.gmd_refine_topk_order_f64(
             _ptr(q), self.nq, _ptr(c), self.nc, self.d, _ptr(self.center), self.k, self.kk, self.nsplit,
             self.metric, self.form, _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau), _ptr(self.stats),
-            _ptr(self.out_idx), _ptr(self.out_dist), _ptr(self.flags) + 4, _ptr(self.fail_rows), _stream_ptr()))
+            _ptr(self.out_idx), _ptr(self.out_dist), _ptr(self.flags) + 4, _ptr(self.fail_rows), qorder, nqpos,
+            _stream_ptr()))
 
     def exact_rows(self, q: torch.Tensor, c: torch.Tensor):
         _lib.check(self.lib.gmd_exact_rows_f64(

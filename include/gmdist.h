@@ -180,7 +180,7 @@ GMD_API int gmd_scan_tc_sweep_f32(const void* qtiles, int64_t Nq, const void* ct
  *   Grouped order.  gmd_group_leaders_f64 picks "leaders" from a strided sample of ns rows by leader
  * clustering (a sample becomes a leader unless an earlier leader lies within rfac x the median
  * nearest-sample distance; at most cap); SYNCHRONISES the stream to return their number.  Outputs:
- * Lt [D][cap] centred FP32 leader rows (dimension-major), lead_row [cap] their row numbers,
+ * L [cap][D] centred FP32 leader rows, lead_row [cap] their row numbers,
  * lead_rows [cap][D] float64 copies (the candidate set of the nearest-leader search, which is this
  * library's own k = 1 pipeline), info [2] = {leaders, float bits of the radius}.
  * gmd_group_order: given every row's nearest leader and float64 distance to it, keys the rows by
@@ -218,7 +218,7 @@ GMD_API void gmd_group_params(int64_t N, int* ns, int* cap);
 GMD_API int64_t gmd_group_positions(int64_t N, int ngroups, int tile);
 GMD_API size_t gmd_group_leaders_workspace_bytes(int ns, int D);
 GMD_API int gmd_group_leaders_f64(const double* X, int64_t N, int D, const double* center, int ns, int cap, float rfac,
-                     float* Lt, int32_t* lead_row, double* lead_rows, int32_t* info, void* workspace,
+                     float* L, int32_t* lead_row, double* lead_rows, int32_t* info, void* workspace,
                      size_t workspace_bytes, int32_t* nlead_host, void* stream);
 GMD_API size_t gmd_group_order_workspace_bytes(int ngroups);
 GMD_API int gmd_group_order(const int32_t* lead, const double* dist, int64_t N, int ngroups, const int32_t* info,
@@ -227,7 +227,7 @@ GMD_API int gmd_group_order(const int32_t* lead, const double* dist, int64_t N, 
 GMD_API int gmd_prep_tc_grouped_f64(const double* X, int64_t Npos, int D, const double* center, int role,
                      const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
                      float* tmeta, int nt_alloc, void* stream);
-GMD_API int gmd_tc_group_meta(const float* Lt, int cap, const float* grad, int ngroups, int D, const float* stats_c,
+GMD_API int gmd_tc_group_meta(const float* L, const float* grad, int ngroups, int D, const float* stats_c,
                      const float* stats_q, float* gmeta, int ng_alloc, void* stream);
 GMD_API int gmd_use_tc_prune(int64_t Nq, int64_t Nc, int k, int metric, int D);   /* the size policy of gmd_knn_f64 */
 GMD_API size_t gmd_tc_prune_max_tiles(int D, int kk);
@@ -255,6 +255,14 @@ GMD_API int gmd_refine_topk_f64(const double* Q, int64_t Nq, const double* C, in
                         const float* cand_tau, const float* stats, int32_t* out_idx,
                         double* out_dist,
                         int32_t* fail_count, int32_t* fail_rows, void* stream);
+/* The same with the queries visited in a staging order (qorder[position] = query row, 0xFFFFFFFF =
+ * padding, nqpos positions; e.g. gmd_grouped.perm_q): consecutive blocks then re-rank against the same
+ * neighbourhood of candidate rows and find them in L2.  Results are identical.               */
+GMD_API int gmd_refine_topk_order_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                     const double* center, int k, int kk, int nsplit, int metric, int form,
+                     const uint32_t* cand_idx, const float* cand_val, const float* cand_tau,
+                     const float* stats, int32_t* out_idx, double* out_dist, int32_t* fail_count,
+                     int32_t* fail_rows, const uint32_t* qorder, int64_t nqpos, void* stream);
 
 /* exact float64 scan of all candidates for the listed rows (reads the count on device).
  * With a workspace of gmd_exact_workspace_bytes(Nq) the listed rows (up to 4096) share one
