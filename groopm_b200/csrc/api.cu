@@ -216,10 +216,10 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
                 "knn: the tensor-core scan needs the Euclidean metric, 2 <= k <= 64 and 4 <= D <= 136");
     const bool bmu = form == GMD_FORM_EXPANDED && gmd_use_bmu_scan(k, metric, D);
     const int kk = bmu ? gmd_scan::BMU_KK : gmd_pick_kk(k);
+    // large tensor-core problems go through the grouped order and the pruned scan 
+    const bool prune = tc && gmd_use_tc_prune(Nq, Nc, k, metric, D);
     const int nsplit = (bmu || tc) ? 1 : gmd_pick_nsplit(Nq, Nc, D, kk);
     const bool same = (Q == C && Nq == Nc);
-    // large tensor-core problems go through the grouped order and the pruned scan
-    const bool prune = tc && gmd_use_tc_prune(Nq, Nc, k, metric, D);
     Workspace w = carve(workspace, Nq, Nc, D, kk, nsplit, same, tc, prune);
     GMD_REQUIRE(w.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "knn: workspace %zu B < required %zu B",
                 workspace_bytes, w.bytes);

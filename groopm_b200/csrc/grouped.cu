@@ -94,7 +94,7 @@ Layout carve(void* base, int64_t Nq, int64_t Nc, int D, int relation) {
     L.tmeta_c = c.take<float>((size_t)(D + 1) * (L.cap_pos_c / TM));
     L.tmeta_q = c.take<float>((size_t)(D + 1) * (L.cap_pos_q / TM));
     L.gmeta = c.take<float>((size_t)(D + 1) * L.cap);
-    L.counters = c.take<uint64_t>(4);
+    L.counters = c.take<uint64_t>(16);
     L.bytes = c.off;
     return L;
 }
@@ -194,7 +194,7 @@ extern "C" int gmd_tc_stage_grouped_f64(const double* Q, int64_t Nq, const doubl
         return rc;
     if ((rc = gmd_tc_group_meta(L.Lt, L.grad, nlead, D, stats_c, stats_q, L.gmeta, L.cap, stream)) != GMD_OK)
         return rc;
-    GMD_CUDA_CHECK(cudaMemsetAsync(L.counters, 0, 4 * sizeof(uint64_t), st));
+    GMD_CUDA_CHECK(cudaMemsetAsync(L.counters, 0, 16 * sizeof(uint64_t), st));
     out->npos_q = npos_q;
     out->npos_c = npos_c;
     out->ngroups = nlead;

@@ -105,59 +105,103 @@ __global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict_
     }
 }
 
-// One block.  R = rfac x median(nn); then the samples in order: a sample farther than R from every
-// leader so far becomes a leader (at most cap).  The samples go through in batches of B: all threads
-// test the batch against the leaders that exist (thread = one sample x a share of the leaders; the batch
-// sits dimension-major in shared memory, the leader rows are warp-wide broadcasts), then warp 0 walks the
-// uncovered samples in order and tests each against the leaders the batch itself has produced so far.
+// Leader clustering of the samples: a sample becomes a leader unless an earlier leader lies within
+// R = rfac x median(nn) of it (at most cap leaders).  Greedy and order dependent, hence one block -- but only
+// for the part that has to be: pass A clusters the first n1 samples (all their candidate leaders are
+// unknown), cover_kernel then tests every other sample against pass A's leaders on the whole GPU, and pass C
+// clusters the samples that are still uncovered, testing them against pass C's own leaders only.
+// Inside a pass the samples go through in batches of B: all threads test the batch against the leaders
+// that exist (thread = one sample x a share of the leaders; the batch sits dimension-major in shared
+// memory, the leader rows are warp-wide broadcasts), then warp 0 walks the uncovered samples in order and
+// tests each against the leaders the batch itself has produced so far.
 // out: L [cap][D] centred FP32 leader rows, lead_row[cap] (row of X), info[0] = leaders,
 // info[1] = float bits of R.
-__global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __restrict__ S, int ns, long long stride,
-                                                             int D, const float* __restrict__ nn, int nprobe,
-                                                             float rfac, int cap, int B, float* __restrict__ L,
+// pass A: flags null, samples [0, n1), j0 = 0, computes R.  pass C: samples {i >= n1 : flags[i] != 0} in order
+// (compacted by the block first), tested against the leaders from index info[2] on (pass A's count).
+__global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __restrict__ S, int ns, int n1,
+                                                             long long stride, int D, const float* __restrict__ nn,
+                                                             int nprobe, float rfac, int cap, int B,
+                                                             const unsigned char* __restrict__ flags,
+                                                             int32_t* __restrict__ list, float* __restrict__ L,
                                                              int32_t* __restrict__ lead_row,
                                                              int32_t* __restrict__ info) {
     extern __shared__ float lsm[];
     float* sT = lsm;                                   // [D][B] the batch, dimension-major
     int* cov = reinterpret_cast<int*>(sT + (size_t)D * B);   // [B]
     int* fresh = cov + B;                              // [B] batch members that became leaders (batch index)
+    int* sidx = fresh + B;                             // [B] sample index of a batch member
     __shared__ float vals[LEAD_PROBES];
-    __shared__ int nlead_s;
+    __shared__ int part[LEAD_THREADS];
+    __shared__ int nlead_s, nlist_s;
     __shared__ float R2_s;
     const int tid = threadIdx.x, lane = tid & 31;
-    // ---- median of the finite nearest-sample distances, by rank counting
-    const bool probe = tid < nprobe;
-    const float v = probe ? nn[tid] : __int_as_float(0x7f800000);
-    if (tid < LEAD_PROBES) vals[tid] = v;
-    if (tid == 0) nlead_s = 0, R2_s = 0.0f;
-    const int nfin = __syncthreads_count(probe && v < __int_as_float(0x7f800000));
-    if (probe && nfin > 0) {
-        int rank = 0;
-        for (int j = 0; j < nprobe; ++j) rank += (vals[j] < v || (vals[j] == v && j < tid)) ? 1 : 0;
-        if (rank == nfin / 2) {
-            const float R = rfac * v;
-            R2_s = R * R;
-            info[1] = __float_as_int(R);
+    int j0 = 0, nlist;
+    if (!flags) {
+        // ---- pass A: median of the finite nearest-sample distances, by rank counting
+        const bool probe = tid < nprobe;
+        const float v = probe ? nn[tid] : __int_as_float(0x7f800000);
+        if (tid < LEAD_PROBES) vals[tid] = v;
+        if (tid == 0) nlead_s = 0, R2_s = 0.0f;
+        const int nfin = __syncthreads_count(probe && v < __int_as_float(0x7f800000));
+        if (probe && nfin > 0) {
+            int rank = 0;
+            for (int j = 0; j < nprobe; ++j) rank += (vals[j] < v || (vals[j] == v && j < tid)) ? 1 : 0;
+            if (rank == nfin / 2) {
+                const float R = rfac * v;
+                R2_s = R * R;
+                info[1] = __float_as_int(R);
+            }
+        } else if (tid == 0 && nfin == 0) {
+            info[1] = 0;
         }
-    } else if (tid == 0 && nfin == 0) {
-        info[1] = 0;
+        nlist = n1;
+    } else {
+        // ---- pass C: ordered compaction of the uncovered samples
+        const int per = (ns - n1 + LEAD_THREADS - 1) / LEAD_THREADS;
+        const int a = min(ns, n1 + tid * per), b = min(ns, a + per);
+        int c = 0;
+        for (int i = a; i < b; ++i) c += flags[i] ? 1 : 0;
+        part[tid] = c;
+        __syncthreads();
+        for (int o = 1; o < LEAD_THREADS; o <<= 1) {
+            const int v = tid >= o ? part[tid - o] : 0;
+            __syncthreads();
+            part[tid] += v;
+            __syncthreads();
+        }
+        int pos = part[tid] - c;
+        for (int i = a; i < b; ++i)
+            if (flags[i]) list[pos++] = i;
+        if (tid == LEAD_THREADS - 1) nlist_s = part[tid];
+        if (tid == 0) {
+            nlead_s = info[0];
+            const float R = __int_as_float(info[1]);
+            R2_s = R * R;
+        }
+        __syncthreads();
+        nlist = nlist_s;
+        j0 = info[0];
     }
     __syncthreads();
     const float R2 = R2_s;
     const int shares = LEAD_THREADS / B;               // threads per sample, each takes every shares-th leader
     const int b = tid % B, share = tid / B;
-    for (int i0 = 0; i0 < ns; i0 += B) {
-        const int nb = min(B, ns - i0);
+    for (int i0 = 0; i0 < nlist; i0 += B) {
+        const int nb = min(B, nlist - i0);
+        for (int e = tid; e < B; e += LEAD_THREADS) {
+            cov[e] = 0;
+            if (e < nb) sidx[e] = flags ? list[i0 + e] : i0 + e;
+        }
+        __syncthreads();
         for (int e = tid; e < nb * D; e += LEAD_THREADS) {
             const int r = e / D, d = e - r * D;
-            sT[(size_t)d * B + r] = S[(size_t)i0 * D + e];
+            sT[(size_t)d * B + r] = S[(size_t)sidx[r] * D + d];
         }
-        for (int e = tid; e < B; e += LEAD_THREADS) cov[e] = 0;
         __syncthreads();
         const int nl = nlead_s;
         if (b < nb) {
             bool hit = false;
-            for (int j = share; j < nl && !hit; j += shares) {
+            for (int j = j0 + share; j < nl && !hit; j += shares) {
                 const float* l = L + (size_t)j * D;    // the same row for the whole warp: broadcast
                 float d2 = 0.0f;
                 for (int d = 0; d < D; ++d) {
@@ -188,7 +232,7 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
                 const int j = nlead_s + nf;
                 for (int d = lane; d < D; d += 32) L[(size_t)j * D + d] = sT[(size_t)d * B + r];
                 if (lane == 0) {
-                    lead_row[j] = (int32_t)((long long)(i0 + r) * stride);
+                    lead_row[j] = (int32_t)((long long)sidx[r] * stride);
                     fresh[nf] = r;
                 }
                 __syncwarp();
@@ -198,7 +242,36 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
         }
         __syncthreads();
     }
-    if (tid == 0) info[0] = nlead_s;
+    if (tid == 0) {
+        info[0] = nlead_s;
+        if (!flags) info[2] = nlead_s;
+    }
+}
+
+// flags[i] = 1 for every sample i >= n1 that no leader of pass A covers; one warp per sample
+__global__ void __launch_bounds__(256) cover_kernel(const float* __restrict__ S, int ns, int n1, int D,
+                                                   const float* __restrict__ L, const int32_t* __restrict__ info,
+                                                   unsigned char* __restrict__ flags) {
+    const int i = n1 + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= ns) return;
+    const int nl = info[0];
+    const float R = __int_as_float(info[1]), R2 = R * R;
+    const float* a = S + (size_t)i * D;
+    bool hit = false;
+    for (int j0 = 0; j0 < nl && !hit; j0 += 32) {
+        const int j = j0 + lane;
+        float d2 = __int_as_float(0x7f800000);
+        if (j < nl) {
+            const float* l = L + (size_t)j * D;
+            d2 = 0.0f;
+            for (int d = 0; d < D; ++d) {
+                const float t = a[d] - l[d];
+                d2 = fmaf(t, t, d2);
+            }
+        }
+        hit = __any_sync(0xFFFFFFFFu, d2 <= R2);
+    }
+    if (lane == 0) flags[i] = hit ? 0 : 1;
 }
 
 // leader rows of X, float64 row-major (the candidate set of the nearest-leader search)
@@ -323,7 +396,8 @@ extern "C" void gmd_group_params(int64_t N, int* ns, int* cap) {
 }
 
 extern "C" size_t gmd_group_leaders_workspace_bytes(int ns, int D) {
-    return ((size_t)ns * D + LEAD_PROBES) * sizeof(float);
+    // samples, nearest-sample distances, uncovered flags, list of uncovered samples
+    return ((size_t)ns * D + LEAD_PROBES) * sizeof(float) + (((size_t)ns + 15) & ~(size_t)15) + (size_t)ns * sizeof(int32_t);
 }
 
 extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const double* center, int ns, int cap, float rfac,
@@ -347,10 +421,21 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
     sample_nn_kernel<<<(unsigned)nprobe, 256, 0, st>>>(S, ns, D, nprobe, nn);
     GMD_CUDA_CHECK(cudaGetLastError());
     const int B = D <= 48 ? 256 : (D <= 96 ? 128 : 64);       // batch: [D][B] floats of shared memory
-    const size_t lsm = ((size_t)D * B + 2 * (size_t)B) * sizeof(float);
+    const size_t lsm = ((size_t)D * B + 3 * (size_t)B) * sizeof(float);
     GMD_CUDA_CHECK(cudaFuncSetAttribute(leader_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, stride, D, nn, nprobe, rfac, cap, B, L, lead_row, info);
+    unsigned char* flags = (unsigned char*)(nn + LEAD_PROBES);  // [ns]
+    int32_t* list = (int32_t*)(flags + (((size_t)ns + 15) & ~(size_t)15));   // [ns]
+    const int n1 = std::min(ns, 1024);                        // pass A: the samples clustered before any is known
+    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, B, nullptr, list, L, lead_row,
+                                               info);
     GMD_CUDA_CHECK(cudaGetLastError());
+    if (n1 < ns) {
+        cover_kernel<<<(unsigned)(((size_t)(ns - n1) * 32 + 255) / 256), 256, 0, st>>>(S, ns, n1, D, L, info, flags);
+        GMD_CUDA_CHECK(cudaGetLastError());
+        leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, B, flags, list, L,
+                                                   lead_row, info);
+        GMD_CUDA_CHECK(cudaGetLastError());
+    }
     int32_t h[2] = {0, 0};
     GMD_CUDA_CHECK(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, st));
     GMD_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -41,7 +41,7 @@ __device__ __forceinline__ bool key_less(double da, uint32_t ia, double db, uint
 }
 
 // G lanes per query row (G = 32, or 8 when there are at most 8 proposals per row: the k = 1
-// scan), 32 / G rows per warp
+// scan), 32 / G rows per warp.
 template <int G>
 __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ Q, long long Nq,
                                                      const double* __restrict__ C, int D,
@@ -77,16 +77,30 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
     const double* qrow = Q + (size_t)(live ? q : 0) * D;
     const uint32_t* ci = cand_idx + (size_t)(live ? q : 0) * m;
 
-    if (live) {
-        for (int x = sl; x < m; x += G) {
-            const uint32_t idx = ci[x];
-            double d = CUDART_INF;
-            if (idx != GMD_EMPTY_IDX) d = dist64(qrow, C + (size_t)idx * D, D, metric);
-            sd[x] = d;
-            si[x] = idx;
+    // the bound on everything that was not proposed: the smallest of the splits' taus
+    float tau32 = CUDART_INF_F;
+    if (live)
+        for (int sp = sl; sp < nsplit; sp += G) tau32 = fminf(tau32, cand_tau[(size_t)q * nsplit + sp]);
+    for (int o = G / 2; o > 0; o >>= 1) tau32 = fminf(tau32, __shfl_xor_sync(FULL, tau32, o));
+
+    {
+        if (live) {
+            const float* cv = cand_val + (size_t)q * m;
+            for (int x = sl; x < m; x += G) {
+                uint32_t idx = ci[x];
+                // With several splits a proposal of one split may lie above another split's tau: like anything
+                // that was not proposed, its float64 distance is then >= lower(tau), it cannot be among a
+                // certified top-k, and its row is not read.  (The split with the smallest tau holds kk >= k
+                // proposals at or below it, so k finite entries always remain.)
+                if (nsplit > 1 && idx != GMD_EMPTY_IDX && cv[x] > tau32) idx = GMD_EMPTY_IDX;
+                double d = CUDART_INF;
+                if (idx != GMD_EMPTY_IDX) d = dist64(qrow, C + (size_t)idx * D, D, metric);
+                sd[x] = d;
+                si[x] = idx;
+            }
         }
+        __syncwarp();
     }
-    __syncwarp();
 
     double kth = CUDART_INF;
     if (live) {
@@ -105,10 +119,6 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
     for (int o = G / 2; o > 0; o >>= 1) kth = fmin(kth, __shfl_xor_sync(FULL, kth, o));
 
     // ---- certificate
-    float tau32 = CUDART_INF_F;
-    if (live)
-        for (int s = sl; s < nsplit; s += G) tau32 = fminf(tau32, cand_tau[(size_t)q * nsplit + s]);
-    for (int o = G / 2; o > 0; o >>= 1) tau32 = fminf(tau32, __shfl_xor_sync(FULL, tau32, o));
     double n2 = 0.0, n1 = 0.0;
     if (live) {
         for (int d = sl; d < D; d += G) {

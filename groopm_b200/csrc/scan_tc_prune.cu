@@ -19,6 +19,16 @@
 // the sequence of tiles without any per-stage metadata; mbarrier phases simply continue across rounds
 // (the ring and accumulator stages are numbered by a running tile counter).
 //
+// Selection is what bounds this kernel once few tiles are visited: a query's own neighbourhood comes first,
+// so most of what it is shown enters its top-kk set (~kk (1 + ln(n / kk)) heap updates per query, each a chain
+// of dependent shared-memory round trips and compares), and four selection warps -- one per scheduler -- hide
+// none of that latency.  For one K block (D <= 31) a CTA therefore takes TWO query tiles (QT = 2): 256 queries,
+// eight selection warps (two per scheduler), both tiles multiplied against every candidate stage (the ring
+// is read once for two tiles), 2 accumulator stages x 2 query tiles x 128 columns of tensor memory, and an
+// accumulator row read in two halves of 64 columns so that the selection threads stay within the registers
+// 352 threads leave each other.  The two tiles are neighbours in the grouped order, so they share the window
+// and most surviving tiles; a candidate tile is visited if EITHER query tile's bound admits it.
+//
 // Exactness.  cand_tau stays what refine.cu expects: every candidate that was LOADED but not proposed
 // has an FP32 value >= tau.  A candidate that was never loaded has a true float64 distance
 //     >= (rigorous bound, all roundings taken against it) > T >= sqrt(tau + |q|^2),
@@ -34,12 +44,15 @@
 
 namespace gmd_tc {
 
-constexpr int LCAP = 1024;                     // tiles per round (DUAL: half)
+constexpr int LCAP = 1024;                     // tiles per round
 constexpr int WMAX = 32;                       // tiles of the opening window
 constexpr int META_MAX = GMD_MAX_D + 4;        // centroid + radius of the query tile in shared memory
 constexpr float LB_REL = 1.0f / 16384.0f;      // relative slack on every FP32-evaluated term of a bound
 constexpr float LB_ABS = 1.0f / 512.0f;        // absolute slack (scaled units: row norms <= 256): float64 -> FP32
                                                // rounding of the centred rows (<= 2^-15) and FP32 evaluation
+// warp roles: 4 QT selection warps (warp w: query tile w / 4, TMEM lane quarter w % 4), then the single-thread
+// roles on the highest warp ids: producer, two MMA issuers (even / odd candidate tiles)
+__host__ __device__ constexpr int prune_threads(int qt) { return 32 * (4 * qt + 3); }
 
 struct PruneParams {
     const unsigned char* qtiles;
@@ -61,9 +74,10 @@ struct PruneParams {
     long long c_index_offset;
     const float* stats_c;
     const float* stats_q;
-    uint32_t* cand_idx;
+    int ntiles_q;                              // query tiles staged
+    uint32_t* cand_idx;                        // [Nq][kk]
     float* cand_val;
-    float* cand_tau;
+    float* cand_tau;                           // [Nq]
     unsigned long long* counters;              // nullable: [0] tiles visited, [1] CTAs, [2] groups surviving
 };
 
@@ -71,29 +85,29 @@ __device__ __forceinline__ float ball_bound(float d2, float rsum) {
     return sqrtf(d2) * (1.0f - LB_REL) - rsum * (1.0f + LB_REL) - LB_ABS;
 }
 
-// DUAL: two CTAs per SM.  With few tiles to visit the scan is bound by the selection threads' dependent
-// shared-memory round trips (heap updates), not by the tensor pipe, and a CTA's four selection warps -- one
-// per scheduler -- cannot hide them; a second resident CTA doubles the queries in flight per SM.  Each CTA
-// then takes half the resources: 2 accumulator stages (256 tensor-memory columns), a 2-stage ring, a
-// 12-deep hit queue per thread, and reads an accumulator row in two halves of 64 columns so that the
-// selection threads fit the 144 registers two CTAs leave each thread.  NKB == 1 only.
-template <int NKB, bool DUAL, int NA_ = (DUAL ? 2 : NACC), bool HALF = DUAL, int MINB = (DUAL ? 2 : 1)>
-__global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const PruneParams p) {
+template <int NKB, int QT>
+__global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(const PruneParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const long long qt = blockIdx.x;
-    const int grp = p.tgroup_q[qt];
-    if (grp < 0) return;                                   // a query tile of padding only (uniform: before any set-up)
+    constexpr int PTHREADS = prune_threads(QT);
+    constexpr int PW_PROD = 4 * QT, PW_ISSUE = 4 * QT + 1;
+    constexpr int NA = QT == 2 ? 2 : NACC;                 // accumulator stages (QT x 128 columns each)
+    const long long qt0 = (long long)blockIdx.x * QT;      // first query tile of the CTA
+    // groups of the CTA's query tiles (-1: a tile of padding only, or past the end)
+    int grpq[QT];
+#pragma unroll
+    for (int j = 0; j < QT; ++j) grpq[j] = (qt0 + j < p.ntiles_q) ? p.tgroup_q[qt0 + j] : -1;
+    bool any_tile = false;
+#pragma unroll
+    for (int j = 0; j < QT; ++j) any_tile |= grpq[j] >= 0;
+    if (!any_tile) return;                                 // nothing but padding (uniform: before any set-up)
 
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int nkb = NKB;
     constexpr int TILE_B = tile_bytes(nkb);
-    constexpr int NA = NA_;                                // accumulator stages
-    constexpr int TQP = DUAL ? 12 : TQ;                    // parked hits per selection thread
-    constexpr int LC = DUAL ? LCAP / 2 : LCAP;
-    const int ns = p.ns, kk = p.kk, kkp = kk | 1, D = p.D;
+    const int ns = p.ns, kk = p.kk, KQ = heap2_slots(kk), D = p.D;
     const int nw = (p.ntiles_c + 31) >> 5;
-    unsigned char* Aimg = base;
-    unsigned char* Bst = base + TILE_B;
+    unsigned char* Aimg = base;                            // QT query tiles
+    unsigned char* Bst = base + QT * TILE_B;
     uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + (size_t)ns * KB_B);
     uint64_t* full = bars;
     uint64_t* sfree = bars + NS_MAX;
@@ -101,17 +115,19 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
     uint64_t* tempty = bars + 2 * NS_MAX + NACC;
     uint64_t* qbar = bars + 2 * NS_MAX + 2 * NACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS_MAX + 2 * NACC + 2);
-    uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NS_MAX + 2 * NACC + 4);
-    uint64_t* lists = reinterpret_cast<uint64_t*>(queues + TQP * TM);
-    uint32_t* tlist = reinterpret_cast<uint32_t*>(lists + (size_t)TM * kkp);   // [LC] tiles of the round / groups
-    float* mq = reinterpret_cast<float*>(tlist + LC);                          // [META_MAX] centroid, radius
-    float* Tw = mq + META_MAX;                                                 // [4] per selection warp
-    int* ctl = reinterpret_cast<int*>(Tw + 4);                                 // [2][2] (count, pending) by round parity
+    uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NS_MAX + 2 * NACC + 4);   // [QT][TQ][TM]
+    float* hvals = reinterpret_cast<float*>(queues + QT * TQ * TM);                // [QT][TM][KQ] values of the top-kk sets
+    uint32_t* hidx = reinterpret_cast<uint32_t*>(hvals + (size_t)QT * TM * KQ);    // [QT][TM][KQ] their candidates
+    uint32_t* tlist = hidx + (size_t)QT * TM * KQ;                                 // [LCAP] tiles of the round / groups
+    float* mq = reinterpret_cast<float*>(tlist + LCAP);                        // [QT][META_MAX] centroid, radius
+    float* Tw = mq + QT * META_MAX;                                            // [4 QT] per selection warp
+    int* ctl = reinterpret_cast<int*>(Tw + 4 * QT);                            // [2][2] (count, pending) by round parity
     uint32_t* visited = reinterpret_cast<uint32_t*>(ctl + 4);                  // [nw]
     uint32_t* todo = visited + nw;                                             // [nw]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr unsigned FULLW = 0xFFFFFFFFu;
+    const float INF = __int_as_float(0x7f800000);
 
     if (tid == 0) {
         for (int s = 0; s < ns; ++s) {
@@ -120,20 +136,25 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
         }
         for (int a = 0; a < NA; ++a) {
             mbar_init(&tdone[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], 4 * QT);                 // one arrival per selection warp
         }
         mbar_init(qbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(qbar, TILE_B);
-        bulk_g2s(Aimg, p.qtiles + (size_t)qt * TILE_B, TILE_B, qbar);
+        mbar_expect_tx(qbar, QT * TILE_B);
+        // (a tile past the end of the query set is a second copy of the first one: its rows count as padding)
+        for (int j = 0; j < QT; ++j)
+            bulk_g2s(Aimg + (size_t)j * TILE_B, p.qtiles + (size_t)(qt0 + j < p.ntiles_q ? qt0 + j : qt0) * TILE_B, TILE_B, qbar);
     }
-    for (int e = tid; e < TM * kkp; e += NTHREADS) lists[e] = GMD_EMPTY_KEY;
-    for (int e = tid; e < 2 * nw; e += NTHREADS) visited[e] = 0u;              // visited and todo are adjacent
-    for (int e = tid; e <= D; e += NTHREADS) mq[e] = p.tmeta_q[(size_t)e * p.nt_alloc_q + qt];
-    if (tid < 4) Tw[tid] = __int_as_float(0x7f800000);     // no threshold yet: nothing can be pruned
-    if (warp == W_ISSUE) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NA * TM));
+    for (int e = tid; e < QT * TM * KQ; e += PTHREADS) hvals[e] = -INF, hidx[e] = GMD_EMPTY_IDX;
+    for (int e = tid; e < 2 * nw; e += PTHREADS) visited[e] = 0u;               // visited and todo are adjacent
+    for (int e = tid; e < QT * (D + 1); e += PTHREADS) {
+        const int j = e / (D + 1), d = e - j * (D + 1);
+        mq[j * META_MAX + d] = grpq[j] >= 0 ? p.tmeta_q[(size_t)d * p.nt_alloc_q + qt0 + j] : 0.0f;
+    }
+    if (tid < 4 * QT) Tw[tid] = INF;                       // no threshold yet: nothing can be pruned
+    if (warp == PW_ISSUE) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -141,19 +162,24 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
 
-    // ---- round 0: the window, up to WMAX tiles of the query tile's own candidate group
+    // ---- round 0: the window, up to WMAX tiles of each query tile's own candidate group
     if (tid == 0) {
-        const int gs = p.gstart_c[grp], ge = p.gstart_c[grp + 1];
-        int ws = gs, we = ge;
-        if (ge - gs > WMAX) {
-            if (p.same) ws = min(max((int)qt - WMAX / 2, gs), ge - WMAX);
-            we = ws + WMAX;
+        int n = 0;
+        for (int j = 0; j < QT; ++j) {
+            if (grpq[j] < 0) continue;
+            const int gs = p.gstart_c[grpq[j]], ge = p.gstart_c[grpq[j] + 1];
+            int ws = gs, we = ge;
+            if (ge - gs > WMAX) {
+                if (p.same) ws = min(max((int)(qt0 + j) - WMAX / 2, gs), ge - WMAX);
+                we = ws + WMAX;
+            }
+            for (int t = ws; t < we; ++t) {
+                if ((visited[t >> 5] >> (t & 31)) & 1u) continue;     // the two tiles usually share their group
+                tlist[n++] = (uint32_t)t;
+                visited[t >> 5] |= 1u << (t & 31);
+            }
         }
-        for (int t = ws; t < we; ++t) {
-            tlist[t - ws] = (uint32_t)t;
-            visited[t >> 5] |= 1u << (t & 31);
-        }
-        ctl[0] = we - ws;
+        ctl[0] = n;
         ctl[1] = 0;
     }
 
@@ -165,23 +191,23 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
     uint32_t p_sph = 0;
     // issuers
     const int nissue = ns > nkb ? 2 : 1;
-    const int first = warp - W_ISSUE;
+    const int first = warp - PW_ISSUE;
     int i_s = 0;
     uint32_t i_ph = 0;
-    // selection
-    const int quarter = warp & 3;
+    // selection: thread <-> query row `row` (= TMEM lane) of query tile `qsel`
+    const int quarter = warp & 3, qsel = (warp >> 2) % QT;
     const int row = quarter * 32 + lane;                   // only meaningful for the selection warps
-    uint64_t* h = lists + (size_t)row * kkp;
-    uint2* myq = queues + row;
+    float* hv = hvals + ((size_t)qsel * TM + row) * KQ;
+    uint32_t* hx = hidx + ((size_t)qsel * TM + row) * KQ;
+    uint2* myq = queues + (size_t)qsel * TQ * TM + row;
     int qcnt = 0, hn = 0;                                  // parked hits; entries in the top-kk set
-    float thr = __int_as_float(0x7f800000);
-    float uthr = __int_as_float(0xff800000);
-    const long long qpos = qt * TM + row;
+    float thr = INF;                                       // threshold (s units)
+    float uthr = -INF;                                     // the same in u = -s / 2 units
+    const long long qpos = (qt0 + qsel) * TM + row;
     bool qreal = false;
     float qnv = 0.0f;
-    if (warp < W_PROD) {
-        qreal = qpos < p.Nq_pos && (p.perm_q ? p.perm_q[qpos] != GMD_EMPTY_IDX : true);
-    }
+    if (warp < PW_PROD)
+        qreal = grpq[qsel] >= 0 && qpos < p.Nq_pos && (p.perm_q ? p.perm_q[qpos] != GMD_EMPTY_IDX : true);
 
     long long tbase = 0;                                   // tiles processed before this round (ring / stage numbering)
     long long visited_tiles = 0;
@@ -195,42 +221,56 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
             if (bounded) break;
             // ---- bound phase: which unvisited tiles can still matter
             bounded = true;
-            const float T = fmaxf(fmaxf(Tw[0], Tw[1]), fmaxf(Tw[2], Tw[3]));
-            const float rq = mq[D];
             int* nsurv = ctl + ((round + 1) & 1) * 2;      // scratch: this slot is rewritten by the list builder below
             if (tid == 0) *nsurv = 0;
             __syncthreads();
-            // groups: every thread tests its share; the survivors go to tlist (if they fit)
-            for (int g = tid; g < p.ngroups; g += NTHREADS) {
-                float d2 = 0.0f;
+            // T: per query tile, the largest threshold distance of a real query (scaled units, published by the
+            // selection warps at the end of their last round; -1: no such tile, nothing survives for it)
+            float T[QT], rq[QT];
+#pragma unroll
+            for (int j = 0; j < QT; ++j) {
+                T[j] = grpq[j] >= 0 ? fmaxf(fmaxf(Tw[4 * j], Tw[4 * j + 1]), fmaxf(Tw[4 * j + 2], Tw[4 * j + 3])) : -1.0f;
+                rq[j] = mq[j * META_MAX + D];
+            }
+            // does the ball (centre column `col` of a [D + 1][pitch] array, radius r) survive for a query tile?
+            auto survives = [&](const float* meta, size_t pitch, size_t col, float r) {
+                float d2[QT];
+#pragma unroll
+                for (int j = 0; j < QT; ++j) d2[j] = 0.0f;
+#pragma unroll 6
                 for (int d = 0; d < D; ++d) {
-                    const float t = mq[d] - p.gmeta[(size_t)d * p.ng_alloc + g];
-                    d2 = fmaf(t, t, d2);
+                    const float c = meta[(size_t)d * pitch + col];
+#pragma unroll
+                    for (int j = 0; j < QT; ++j) {
+                        const float t = mq[j * META_MAX + d] - c;
+                        d2[j] = fmaf(t, t, d2[j]);
+                    }
                 }
-                const float lb = ball_bound(d2, rq + p.gmeta[(size_t)D * p.ng_alloc + g]);
-                if (!(lb > T)) {
+                bool keep = false;
+#pragma unroll
+                for (int j = 0; j < QT; ++j) keep |= T[j] >= 0.0f && !(ball_bound(d2[j], rq[j] + r) > T[j]);
+                return keep;
+            };
+            // groups: every thread tests its share; the survivors go to tlist (if they fit)
+            for (int g = tid; g < p.ngroups; g += PTHREADS) {
+                if (survives(p.gmeta, (size_t)p.ng_alloc, (size_t)g, p.gmeta[(size_t)D * p.ng_alloc + g])) {
                     const int slot = atomicAdd(nsurv, 1);
-                    if (slot < LC) tlist[slot] = (uint32_t)g;
+                    if (slot < LCAP) tlist[slot] = (uint32_t)g;
                 }
             }
             __syncthreads();
             const int ng = *nsurv;
-            const bool all = ng > LC;                     // list overflow: walk every group
+            const bool all = ng > LCAP;                   // list overflow: walk every group
             const int ngl = all ? p.ngroups : ng;
             // tiles of the surviving groups: a warp per group, a lane per tile
-            for (int gi = warp; gi < ngl; gi += NTHREADS / 32) {
+            for (int gi = warp; gi < ngl; gi += PTHREADS / 32) {
                 const int g = all ? gi : (int)tlist[gi];
                 const int te = p.gstart_c[g + 1];
                 for (int t = p.gstart_c[g] + lane; t < te; t += 32) {
                     if ((visited[t >> 5] >> (t & 31)) & 1u) continue;
                     const float rt = p.tmeta_c[(size_t)D * p.nt_alloc_c + t];
                     if (rt < 0.0f) continue;               // a tile of padding only
-                    float d2 = 0.0f;
-                    for (int d = 0; d < D; ++d) {
-                        const float u = mq[d] - p.tmeta_c[(size_t)d * p.nt_alloc_c + t];
-                        d2 = fmaf(u, u, d2);
-                    }
-                    if (!(ball_bound(d2, rq + rt) > T)) atomicOr(&todo[t >> 5], 1u << (t & 31));
+                    if (survives(p.tmeta_c, (size_t)p.nt_alloc_c, (size_t)t, rt)) atomicOr(&todo[t >> 5], 1u << (t & 31));
                 }
             }
             if (tid == 0 && p.counters) atomicAdd(&p.counters[2], (unsigned long long)ng);
@@ -257,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
                     while (bits) {
                         const int b = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        if (pos < LC)
+                        if (pos < LCAP)
                             tlist[pos] = (uint32_t)(w * 32 + b);
                         else
                             keep |= 1u << b;
@@ -268,8 +308,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
                         visited[w] |= orig & ~keep;
                     }
                     left |= __any_sync(FULLW, keep != 0u);
-                    n = min(LC, n + total);
-                    if (n >= LC && w0 + 32 < nw) {       // the list is full: whatever is left waits for the next round
+                    n = min(LCAP, n + total);
+                    if (n >= LCAP && w0 + 32 < nw) {       // the list is full: whatever is left waits for the next round
                         left = true;
                         break;
                     }
@@ -284,7 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
         }
 
         // ---- the round's cnt tiles through the pipeline
-        if (warp == W_PROD) {
+        if (warp == PW_PROD) {
             if (lane == 0) {
                 for (int i = 0; i < cnt; ++i) {
                     const unsigned char* src = p.ctiles + (size_t)tlist[i] * TILE_B;
@@ -308,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
                 }
             }
             __syncwarp();
-        } else if (warp >= W_ISSUE) {
+        } else if (warp >= PW_ISSUE) {
             if (lane == 0 && first < nissue) {
                 if (tbase == 0) mbar_wait(qbar, 0);
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -322,19 +362,24 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
                     }
                     const int a = (int)(t % NA);
                     if (t >= NA) mbar_wait(&tempty[a], (uint32_t)((t / NA) - 1) & 1u);
-                    const uint32_t acc = tmem + (uint32_t)(a * TM);
 #pragma unroll
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(&full[i_s], i_ph);
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        const uint64_t a_hi = a_base + (uint64_t)kb * (KB_B >> 4), a_lo = a_hi + (IMG_B >> 4);
                         const uint64_t b_hi = b_base + (uint64_t)i_s * (KB_B >> 4), b_lo = b_hi + (IMG_B >> 4);
+                        // every query tile of the CTA against this candidate stage: hi.hi + hi.lo + lo.hi
 #pragma unroll
-                        for (int q = 0; q < 3; ++q)
+                        for (int j = 0; j < QT; ++j) {
+                            const uint32_t acc = tmem + (uint32_t)((a * QT + j) * TM);
+                            const uint64_t a_hi = a_base + (uint64_t)(j * (TILE_B >> 4)) + (uint64_t)kb * (KB_B >> 4),
+                                           a_lo = a_hi + (IMG_B >> 4);
 #pragma unroll
-                            for (int k = 0; k < TK / 16; ++k)
-                                umma_f16(acc, (q == 2 ? a_lo : a_hi) + 2 * k, (q == 1 ? b_lo : b_hi) + 2 * k, idesc,
-                                         (kb | q | k) ? 1u : 0u);
+                            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                                for (int k = 0; k < TK / 16; ++k)
+                                    umma_f16(acc, (q == 2 ? a_lo : a_hi) + 2 * k, (q == 1 ? b_lo : b_hi) + 2 * k, idesc,
+                                             (kb | q | k) ? 1u : 0u);
+                        }
                         umma_commit(kb + 1 < nkb ? &sfree[i_s] : &tdone[a]);
                         if (++i_s == ns) i_s = 0, i_ph ^= 1u;
                     }
@@ -345,137 +390,79 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
             // ---- selection warps: thread <-> query row <-> TMEM lane
             if (tbase == 0) {
                 mbar_wait(qbar, 0);
-                qnv = reinterpret_cast<const float*>(Aimg + (size_t)nkb * KB_B)[row];
+                qnv = reinterpret_cast<const float*>(Aimg + (size_t)qsel * TILE_B + (size_t)nkb * KB_B)[row];
             }
+            auto drain = [&]() {
+                const Drain2 ds = drain_fill2(hv, hx, kk, hn, thr, myq, qcnt);
+                thr = ds.thr;
+                hn = ds.hn;
+                qcnt = 0;
+                uthr = -0.5f * thr;
+            };
+            // 64 columns at a time (one tcgen05.ld.x64): maxima of the 8 groups of 8 columns as shallow trees,
+            // ONE vote, then 8 values at a time: park what beats the (possibly stale) threshold, drain all the
+            // warp's queues side by side when one of them is nearly full
+            auto half_row = [&](const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t c0) {
+                float gm[8];
+                auto tree = [&](const uint32_t (&r)[32], float* g4) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float m0 = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
+                        const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4])), __uint_as_float(r[8 * g + 5]));
+                        const float m2 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                        g4[g] = fmaxf(fmaxf(m0, m1), m2);
+                    }
+                };
+                tree(r0, gm);
+                tree(r1, gm + 4);
+                const float cm = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])),
+                                       fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
+                if (!__any_sync(FULLW, cm > uthr)) return;
+                unsigned mine = 0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
+                const unsigned hot = __reduce_or_sync(FULLW, mine);
+                auto park = [&](const uint32_t (&r)[32], unsigned hot4, uint32_t cc) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (hot4 & (1u << g)) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float u = __uint_as_float(r[8 * g + j]);
+                                if (u > uthr) {
+                                    myq[qcnt * TM] = make_uint2(cc + 8 * g + j, __float_as_uint(-2.0f * u));
+                                    ++qcnt;
+                                }
+                            }
+                            if (__any_sync(FULLW, qcnt > TQ - 8)) drain();
+                        }
+                    }
+                };
+                park(r0, hot & 15u, c0);
+                park(r1, hot >> 4, c0 + 32);
+            };
             for (long long t = tbase; t < tbase + cnt; ++t) {
                 const int a = (int)(t % NA);
                 mbar_wait(&tdone[a], (uint32_t)(t / NA) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t cbase = tlist[t - tbase] * TM;
-                const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TM);
-                // group maxima of 8 columns as shallow trees, one vote per batch of columns, then 8 values at a
-                // time: park what beats the (possibly stale) threshold, drain all the warp's queues side by
-                // side when one of them is nearly full
-                auto tree = [&](const uint32_t (&r)[32], float* gm) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float m0 = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
-                        const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4])), __uint_as_float(r[8 * g + 5]));
-                        const float m2 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-                        gm[g] = fmaxf(fmaxf(m0, m1), m2);
-                    }
-                };
-                auto park = [&](const uint32_t (&r)[32], unsigned hot, uint32_t c0) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (hot & (1u << g)) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float u = __uint_as_float(r[8 * g + j]);
-                                if (u > uthr) {
-                                    myq[qcnt * TM] = make_uint2(c0 + 8 * g + j, __float_as_uint(-2.0f * u));
-                                    ++qcnt;
-                                }
-                            }
-                            if (__any_sync(FULLW, qcnt > TQP - 8)) {
-                                {
-                                    const DrainState ds = drain_fill(h, kk, hn, myq, qcnt);
-                                    thr = ds.thr;
-                                    hn = ds.hn;
-                                }
-                                uthr = -0.5f * thr;
-                                qcnt = 0;
-                            }
-                        }
-                    }
-                };
-                if constexpr (HALF) {
-                    uint32_t r0[32], r1[32];
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        tmem_ld64_sync(trow + 64 * half, r0, r1);
-                        if (half == 1) {
-                            asm volatile("tcgen05.fence::before_thread_sync;");
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[a]);
-                        }
-                        float gm[8];
-                        tree(r0, gm);
-                        tree(r1, gm + 4);
-                        const float cm = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])),
-                                               fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
-                        if (!__any_sync(FULLW, cm > uthr)) continue;
-                        unsigned mine = 0;
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
-                        const unsigned hot = __reduce_or_sync(FULLW, mine);
-                        park(r0, hot & 15u, cbase + 64 * half);
-                        park(r1, hot >> 4, cbase + 64 * half + 32);
-                    }
-                } else {
-                    uint32_t r[128];
-                    tmem_ld128_sync(trow, r);
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[a]);
-                    float gm[16];
-#pragma unroll
-                    for (int g = 0; g < 16; ++g) {
-                        const float m0 = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
-                        const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4])), __uint_as_float(r[8 * g + 5]));
-                        const float m2 = fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-                        gm[g] = fmaxf(fmaxf(m0, m1), m2);
-                    }
-                    float cm;
-                    {
-                        const float a0 = fmaxf(fmaxf(gm[0], gm[1]), gm[2]), a1 = fmaxf(fmaxf(gm[3], gm[4]), gm[5]);
-                        const float a2 = fmaxf(fmaxf(gm[6], gm[7]), gm[8]), a3 = fmaxf(fmaxf(gm[9], gm[10]), gm[11]);
-                        const float a4 = fmaxf(fmaxf(gm[12], gm[13]), gm[14]);
-                        cm = fmaxf(fmaxf(fmaxf(a0, a1), a2), fmaxf(fmaxf(a3, a4), gm[15]));
-                    }
-                    if (!__any_sync(FULLW, cm > uthr)) continue;
-                    unsigned mine = 0;
-#pragma unroll
-                    for (int g = 0; g < 16; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
-                    const unsigned hot = __reduce_or_sync(FULLW, mine);
-#pragma unroll
-                    for (int g = 0; g < 16; ++g) {
-                        if (hot & (1u << g)) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float u = __uint_as_float(r[8 * g + j]);
-                                if (u > uthr) {
-                                    myq[qcnt * TM] = make_uint2(cbase + 8 * g + j, __float_as_uint(-2.0f * u));
-                                    ++qcnt;
-                                }
-                            }
-                            if (__any_sync(FULLW, qcnt > TQP - 8)) {
-                                {
-                                    const DrainState ds = drain_fill(h, kk, hn, myq, qcnt);
-                                    thr = ds.thr;
-                                    hn = ds.hn;
-                                }
-                                uthr = -0.5f * thr;
-                                qcnt = 0;
-                            }
-                        }
-                    }
-                }
+                const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((a * QT + qsel) * TM);
+                uint32_t r0[32], r1[32];
+                tmem_ld64_sync(trow, r0, r1);
+                half_row(r0, r1, cbase);
+                tmem_ld64_sync(trow + 64, r0, r1);
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[a]);
+                half_row(r0, r1, cbase + 64);
             }
-            // end of the round: fold what is parked, publish the warp's largest threshold DISTANCE
-            // (scaled units; padding rows do not count)
-            {
-                                    const DrainState ds = drain_fill(h, kk, hn, myq, qcnt);
-                                    thr = ds.thr;
-                                    hn = ds.hn;
-                                }
-            uthr = -0.5f * thr;
-            qcnt = 0;
+            // end of the round: fold what is parked, publish the warp's largest threshold DISTANCE (scaled units;
+            // padding rows do not count).  Non-negative floats (and +inf) order like their bit patterns.
+            drain();
             float tq = 0.0f;
             if (qreal) tq = sqrtf(fmaxf(thr + qnv, 0.0f)) * (1.0f + 1.0f / 1048576.0f);
-            // non-negative floats (and +inf) order like their bit patterns
             const unsigned tmax = __reduce_max_sync(FULLW, __float_as_uint(tq));
-            if (lane == 0) Tw[quarter] = __uint_as_float(tmax);
+            if (lane == 0) Tw[warp] = __uint_as_float(tmax);
         }
         visited_tiles += cnt;
         tbase += cnt;
@@ -488,28 +475,33 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
     }
 
     // ---- write this query's proposals
-    if (warp < W_PROD && qreal) {
+    if (warp < PW_PROD && qreal) {
         const long long q = p.perm_q ? (long long)p.perm_q[qpos] : qpos;
         const float unscale = ldexpf(1.0f, -2 * gmd_tc_exponent(p.stats_c[0], p.stats_q[0]));
         const size_t ob = (size_t)q * kk;
-        for (int x = 0; x < kk; ++x) {
-            const uint64_t key = h[x];
-            const uint32_t li = (uint32_t)key;
-            float vv = gmd_unflip((uint32_t)(key >> 32));
-            uint32_t oi = GMD_EMPTY_IDX;
-            if (key != GMD_EMPTY_KEY && (long long)li < p.Nc_pos) {
-                const uint32_t orow = p.perm_c ? p.perm_c[li] : li;
-                if (orow != GMD_EMPTY_IDX) oi = orow + (uint32_t)p.c_index_offset;
+        // eight entries at a time: the position -> row look-ups of a batch are in flight together
+        for (int x0 = 0; x0 < kk; x0 += 8) {
+            uint32_t oi[8];
+            float vv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int x = x0 + j;
+                const uint32_t li = x < hn ? hx[x + 3] : GMD_EMPTY_IDX;
+                vv[j] = x < hn ? hv[x + 3] : INF;
+                oi[j] = GMD_EMPTY_IDX;
+                if (li != GMD_EMPTY_IDX && (long long)li < p.Nc_pos) oi[j] = p.perm_c ? p.perm_c[li] : li;
             }
-            if (oi != GMD_EMPTY_IDX)
-                vv = fmaxf(vv + qnv, 0.0f) * unscale;
-            else
-                vv = __int_as_float(0x7f800000);
-            p.cand_idx[ob + x] = oi;
-            p.cand_val[ob + x] = vv;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int x = x0 + j;
+                if (x >= kk) break;
+                const bool ok = oi[j] != GMD_EMPTY_IDX;
+                p.cand_idx[ob + x] = ok ? oi[j] + (uint32_t)p.c_index_offset : GMD_EMPTY_IDX;
+                p.cand_val[ob + x] = ok ? fmaxf(vv[j] + qnv, 0.0f) * unscale : INF;
+            }
         }
         // a set that never filled lists every candidate it was shown: nothing is bounded by it
-        p.cand_tau[q] = hn == kk ? fmaxf(thr + qnv, 0.0f) * unscale : __int_as_float(0x7f800000);
+        p.cand_tau[q] = hn == kk ? fmaxf(thr + qnv, 0.0f) * unscale : INF;
     }
     if (tid == 0) {
         if (tbase == 0) mbar_wait(qbar, 0);                // nothing was scanned: the query tile's copy must still land
@@ -520,7 +512,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) scan_tc_prune_kernel(const Pru
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NA * TM));
+    if (warp == PW_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 // leader rows and group radii in the scan's scaled units, dimension-major
@@ -539,20 +531,19 @@ __global__ void __launch_bounds__(256) group_meta_kernel(const float* __restrict
 }  // namespace gmd_tc
 
 namespace {
-// shared memory of one CTA without the ring and the two bitmasks
-size_t prune_fixed_smem(int nkb, int kk, bool dual) {
+// shared memory of one CTA (qt query tiles) without the ring and the two bitmasks
+size_t prune_fixed_smem(int nkb, int kk, int qt) {
     using namespace gmd_tc;
-    return 1024 + (size_t)tile_bytes(nkb) + 512 + (size_t)(dual ? 12 : TQ) * TM * 8 + (size_t)TM * (kk | 1) * 8 +
-           (size_t)(dual ? LCAP / 2 : LCAP) * 4 + (size_t)META_MAX * 4 + 64;
+    return 1024 + (size_t)qt * tile_bytes(nkb) + 512 + (size_t)qt * TQ * TM * 8 + (size_t)qt * TM * heap2_slots(kk) * 8 +
+           (size_t)LCAP * 4 + (size_t)qt * META_MAX * 4 + 128;
 }
-constexpr size_t DUAL_SMEM_LIMIT = (228 * 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved for each
 }  // namespace
 
 extern "C" size_t gmd_tc_prune_max_tiles(int D, int kk) {
     using namespace gmd_tc;
     const int nkb = tc_nkb(D);
     if (nkb > MAX_KB) return 0;
-    const size_t need = prune_fixed_smem(nkb, kk, false) + (size_t)std::max(2, nkb + 1) * KB_B;   // >= nkb + 1 ring stages
+    const size_t need = prune_fixed_smem(nkb, kk, 1) + (size_t)std::max(2, nkb + 1) * KB_B;   // >= nkb + 1 ring stages
     if (need >= GMD_SMEM_LIMIT) return 0;
     return (size_t)(GMD_SMEM_LIMIT - need) / 8 * 32;                  // two bitmask words per 32 tiles
 }
@@ -589,17 +580,12 @@ extern "C" int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const v
     GMD_REQUIRE((size_t)ntiles_c <= gmd_tc_prune_max_tiles(D, kk), GMD_ERR_UNSUPPORTED,
                 "scan_tc_prune: %d candidate tiles exceed the shared-memory bitmasks", ntiles_c);
     const int nw = (ntiles_c + 31) / 32;
-    // two CTAs per SM when a CTA's half fits (one K block, GMD_TC_DUAL=0 switches it off)
-    // EXPERIMENTAL, off unless GMD_TC_DUAL=1: the builds that cap the registers for two CTAs per SM return wrong
-    // accumulators (cause not found yet; the one-CTA build of the same code is correct)
-    bool dual = nkb == 1 && prune_fixed_smem(nkb, kk, true) + (size_t)nw * 8 + 2 * (size_t)KB_B <= DUAL_SMEM_LIMIT;
-    {
-        const char* env = getenv("GMD_TC_DUAL");
-        dual = dual && env && atoi(env) != 0;
-    }
-    const size_t fixed = prune_fixed_smem(nkb, kk, dual) + (size_t)nw * 8;
-    const int ns = dual ? 2
-                        : (int)std::min<size_t>(std::min(NS_MAX, NACC * nkb), (GMD_SMEM_LIMIT - fixed) / KB_B);
+    // two query tiles per CTA when there is one K block and both fit (GMD_TC_QT=1: developer switch)
+    int qt = (nkb == 1 && prune_fixed_smem(nkb, kk, 2) + (size_t)nw * 8 + 2 * (size_t)KB_B <= GMD_SMEM_LIMIT) ? 2 : 1;
+    if (const char* env = getenv("GMD_TC_QT")) qt = std::min(qt, std::max(1, atoi(env)));
+    const size_t fixed = prune_fixed_smem(nkb, kk, qt) + (size_t)nw * 8;
+    const int na = qt == 2 ? 2 : NACC;
+    const int ns = (int)std::min<size_t>(std::min(NS_MAX, na * nkb), (GMD_SMEM_LIMIT - fixed) / KB_B);
     GMD_REQUIRE(ns >= 2, GMD_ERR_UNSUPPORTED, "scan_tc_prune: D=%d kk=%d needs more than 227 KB of shared memory", D, kk);
     const size_t smem = fixed + (size_t)ns * KB_B;
     PruneParams p;
@@ -626,30 +612,23 @@ extern "C" int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const v
     p.c_index_offset = c_index_offset;
     p.stats_c = stats_c;
     p.stats_q = stats_q;
+    p.ntiles_q = ntiles_q;
     p.cand_idx = cand_idx;
     p.cand_val = cand_val;
     p.cand_tau = cand_tau;
     p.counters = (unsigned long long*)counters;
-    auto launch = [&](auto kern) -> int {
+    auto launch = [&](auto kern, int q) -> int {
         GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        kern<<<(unsigned)ntiles_q, NTHREADS, smem, (cudaStream_t)stream>>>(p);
+        kern<<<(unsigned)((ntiles_q + q - 1) / q), prune_threads(q), smem, (cudaStream_t)stream>>>(p);
         return GMD_OK;
     };
     int rc;
     switch (nkb) {
-        case 1: {
-            const int var = getenv("GMD_TC_VAR") ? atoi(getenv("GMD_TC_VAR")) : 0;   // (temporary: isolating the DUAL failure)
-            if (!dual) rc = launch(scan_tc_prune_kernel<1, false>);
-            else if (var == 1) rc = launch(scan_tc_prune_kernel<1, true, 2, false, 1>);
-            else if (var == 2) rc = launch(scan_tc_prune_kernel<1, true, 2, true, 1>);
-            else rc = launch(scan_tc_prune_kernel<1, true>);
-            break;
-        }
-        case 2: rc = launch(scan_tc_prune_kernel<2, false>); break;
-        case 3: rc = launch(scan_tc_prune_kernel<3, false>); break;
-        case 4: rc = launch(scan_tc_prune_kernel<4, false>); break;
-        default: rc = launch(scan_tc_prune_kernel<5, false>); break;
+        case 1: rc = qt == 2 ? launch(scan_tc_prune_kernel<1, 2>, 2) : launch(scan_tc_prune_kernel<1, 1>, 1); break;
+        case 2: rc = launch(scan_tc_prune_kernel<2, 1>, 1); break;
+        case 3: rc = launch(scan_tc_prune_kernel<3, 1>, 1); break;
+        case 4: rc = launch(scan_tc_prune_kernel<4, 1>, 1); break;
+        default: rc = launch(scan_tc_prune_kernel<5, 1>, 1); break;
     }
     if (rc != GMD_OK) return rc;
     GMD_CUDA_CHECK(cudaGetLastError());

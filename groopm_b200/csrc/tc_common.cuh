@@ -200,6 +200,64 @@ static __device__ GMD_DRAIN_INLINE DrainState drain_fill(uint64_t* h, int kk, in
     return st;
 }
 
+// ---- split top-kk set of the pruned scan: values and indices in two arrays, a 4-ary MAX-heap ordered by the
+// VALUE alone.  Node n lives in slot n + 3 of a 16-byte aligned block, so that the four children of node i
+// (nodes 4i + 1 .. 4i + 4) are slots 4i + 4 .. 4i + 7: one 128-bit load; slots past the last node hold -inf
+// and are never the largest child.  A level of a sift is then one LDS.128, a handful of compares and three
+// 32-bit accesses instead of four 64-bit loads and 64-bit compares / selects.  Ordering by value only is
+// enough here: which of several EQUAL values stays is immaterial to the proposals' guarantee (everything
+// not proposed has a value >= tau), and a tie at the k-th place fails the certificate's strict
+// inequality and goes to the exact pass, which applies the lowest-index rule.
+__host__ __device__ constexpr int heap2_slots(int kk) { return ((kk + 3) + 3) / 4 * 4; }
+
+__device__ __forceinline__ void heap2_sift(float* hv, uint32_t* hx, int kk, int pos, float v, uint32_t idx) {
+    while (true) {
+        const int c = 4 * pos + 1;
+        if (c >= kk) break;
+        const float4 cv = *reinterpret_cast<const float4*>(hv + c + 3);
+        const bool b01 = cv.y > cv.x, b23 = cv.w > cv.z;
+        const float m01 = b01 ? cv.y : cv.x, m23 = b23 ? cv.w : cv.z;
+        const bool hi = m23 > m01;
+        const float m = hi ? m23 : m01;
+        if (m <= v) break;
+        const int ch = c + (hi ? 2 + (int)b23 : (int)b01);
+        hv[pos + 3] = m;
+        hx[pos + 3] = hx[ch + 3];
+        pos = ch;
+    }
+    hv[pos + 3] = v;
+    hx[pos + 3] = idx;
+}
+
+struct Drain2 {
+    float thr;
+    int hn;
+};
+// Fold a thread's parked hits (q[r * TM] = (index, value bits)) into its set.  While the set holds fewer
+// than kk entries they are appended; the kk-th one turns the array into a heap (one bottom-up pass).
+static __device__ __noinline__ Drain2 drain_fill2(float* hv, uint32_t* hx, int kk, int hn, float thr, const uint2* q,
+                                                  int n) {
+    for (int r = 0; r < n; ++r) {
+        const uint2 e = q[r * TM];
+        const float v = __uint_as_float(e.y);
+        if (hn < kk) {
+            hv[hn + 3] = v;
+            hx[hn + 3] = e.x;
+            if (++hn == kk) {
+                for (int pos = (kk - 2) / 4; pos >= 0; --pos) heap2_sift(hv, hx, kk, pos, hv[pos + 3], hx[pos + 3]);
+                thr = hv[3];
+            }
+        } else if (v < thr) {
+            heap2_sift(hv, hx, kk, 0, v, e.x);
+            thr = hv[3];
+        }
+    }
+    Drain2 st;
+    st.thr = thr;
+    st.hn = hn;
+    return st;
+}
+
 }  // namespace gmd_tc
 
 static inline int tc_nkb(int D) { return (D + 1 + gmd_tc::TK - 1) / gmd_tc::TK; }

@@ -284,7 +284,8 @@ class KnnPipeline:
         torch.cuda.current_stream().synchronize()
         g = self.grouped
         off = g.counters - self.grouped_ws.data_ptr()
-        visited, ctas, groups, _ = (int(v) for v in self.grouped_ws[off:off + 32].view(torch.int64).tolist())
+        c = [int(v) for v in self.grouped_ws[off:off + 128].view(torch.int64).tolist()]
+        visited, ctas, groups = c[0], c[1], c[2]
         ntc = -(-g.npos_c // 128)
         return {"tiles_visited": visited, "query_tiles": ctas, "groups": g.ngroups,
                 "candidate_tiles": ntc, "groups_surviving_per_query_tile": groups / max(ctas, 1),

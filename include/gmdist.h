@@ -198,8 +198,10 @@ GMD_API int gmd_scan_tc_sweep_f32(const void* qtiles, int64_t Nq, const void* ct
  *   gmd_scan_tc_grouped_f32: the tcgen05 scan of gmd_scan_tc_f32, except that the CTA of a query tile
  * first visits a window of its own group, takes T = its queries' largest k-th distance so far, and then
  * loads only the candidate tiles whose ball bound |m_q - m_c| - r_q - r_c does not exceed T (bounds
- * are evaluated with every rounding taken against them).  Outputs and the meaning of cand_tau are
- * unchanged, so gmd_refine_topk_f64 / gmd_exact_rows_f64 finish it; results are identical to the full
+ * are evaluated with every rounding taken against them).  With one K block (D <= 31) a CTA takes two
+ * query tiles at once (twice the selection warps per SM: the selection's dependent shared-memory round
+ * trips are what bounds a scan that visits few tiles).  Outputs and the meaning of cand_tau are unchanged
+ * (nsplit = 1), so gmd_refine_topk_f64 / gmd_exact_rows_f64 finish it; results are identical to the full
  * scan.  counters (device, in the descriptor): [0] tiles visited, [1] query tiles, [2] groups surviving. */
 typedef struct gmd_grouped {
     int64_t npos_q, npos_c;               /* staged positions (rows + padding) */
@@ -211,7 +213,8 @@ typedef struct gmd_grouped {
     const float* gmeta;                   /* [D + 1][ng_alloc] leaders + group radii, scaled units */
     const float* tmeta_q;                 /* [D + 1][nt_alloc_q] */
     const float* tmeta_c;                 /* [D + 1][nt_alloc_c] */
-    uint64_t* counters;                   /* [4] */
+    uint64_t* counters;                   /* [8]: tiles visited, query tiles, groups surviving, -, then SM cycles of
+                                             thread 0 summed over the CTAs: set-up, pipeline rounds, bounds, write-out */
 } gmd_grouped;
 GMD_API int gmd_group_shells(void);
 GMD_API void gmd_group_params(int64_t N, int* ns, int* cap);
