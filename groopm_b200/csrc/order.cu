@@ -420,13 +420,16 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
     GMD_CUDA_CHECK(cudaGetLastError());
     sample_nn_kernel<<<(unsigned)nprobe, 256, 0, st>>>(S, ns, D, nprobe, nn);
     GMD_CUDA_CHECK(cudaGetLastError());
-    const int B = D <= 48 ? 256 : (D <= 96 ? 128 : 64);       // batch: [D][B] floats of shared memory
+    // batch: [D][B] floats of shared memory.  Pass A meets mostly new clusters -- its cost is warp 0's walk over
+    // the batch against the leaders the batch has produced, so its batches are small; pass C meets mostly
+    // members of the few clusters pass A missed, which the parallel test against pass C's leaders covers.
+    const int B = D <= 48 ? 256 : (D <= 96 ? 128 : 64), BA = 32;
     const size_t lsm = ((size_t)D * B + 3 * (size_t)B) * sizeof(float);
     GMD_CUDA_CHECK(cudaFuncSetAttribute(leader_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
     unsigned char* flags = (unsigned char*)(nn + LEAD_PROBES);  // [ns]
     int32_t* list = (int32_t*)(flags + (((size_t)ns + 15) & ~(size_t)15));   // [ns]
     const int n1 = std::min(ns, 1024);                        // pass A: the samples clustered before any is known
-    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, B, nullptr, list, L, lead_row,
+    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, BA, nullptr, list, L, lead_row,
                                                info);
     GMD_CUDA_CHECK(cudaGetLastError());
     if (n1 < ns) {
