@@ -7,13 +7,15 @@
 Workload (BASELINE.json: "pair-distances/s (fused top-k); 1M-contig kNN wall time at
 1/2/4/8 B200"): the exact k=32 Euclidean neighbour graph of 1 000 000 synthetic contigs x
 30 samples (configs[4] at 1 M; it fits one GPU).  One step = one complete pass of the path
-over the batch: [all-gather of the row shards, N>1] -> centring -> FP32 tile staging ->
-fused FP32 distance + top-k scan -> float64 re-rank + certificate -> exact rows.
-With N GPUs the 1 M query rows are block-sharded (strong scaling: total work fixed).
+over the batch: [all-gather of the row shards, N>1] -> centring -> grouped staging (leaders,
+nearest-leader keys, padded sort, tiles + balls) -> pruned tcgen05 distance + top-k scan ->
+float64 re-rank + certificate -> exact rows.  With N GPUs the 1 M query rows are block-sharded
+(strong scaling: total work fixed) and every rank runs the SAME algorithm.
 
 Prints ONE JSON line on rank 0.  `value` = pair-distances/s with the float64 profiles
-already resident in HBM; `e2e` = the same through the public API with pinned HOST buffers
-(H2D of the profiles and D2H of the neighbour indices + distances inside the timed region).
+already resident in HBM; `e2e` = the same through the public plugin call with HOST buffers
+(`engine.knn(numpy)` at N=1, `dist.sharded_knn` between pinned host buffers at N>1): H2D of
+the profiles and D2H of the neighbour indices + distances inside the timed region.
 """
 from __future__ import annotations
 
@@ -41,20 +43,22 @@ WORKLOADS = {
     "cfg5_4m_x30_k32": (4_000_000, 30, 32, "euclidean", 5),
     "tiny": (20_000, 30, 32, "euclidean", 5),
 }
+TILE_FLOP = 2.0 * 128 * 128 * 32 * 3          # executed by one (query tile, candidate tile, K block): 3 x FP16 passes
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="cfg5_1m_x30_k32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--order", default="auto", choices=["auto", "on", "off"],
-                    help="locality-ordered sweep of the tensor-core scan (all-pairs, one GPU); auto: on for the "
-                         "default workload, whose ordered results were checked identical on the GPU")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--prune", default="auto", choices=["auto", "on", "off"],
+                    help="pruned tensor-core scan (engine default for large Euclidean problems); off: the "
+                         "locality-ordered full sweep of round 1")
     return ap.parse_args()
 
 
@@ -83,6 +87,12 @@ def emit(line: dict):
     else:
         sys.stdout.flush()
         os.write(_REAL_STDOUT, text.encode())
+
+
+def base_config(workload):
+    n, d, k, metric, _ = WORKLOADS[workload]
+    return {"workload": workload, "contigs": n, "dim": d, "k": k, "metric": metric,
+            "l2": "inputs exceed L2 (float64 profiles %d MB against 126 MB)" % (n * d * 8 // 2**20)}
 
 
 def reference_arm(args):
@@ -114,13 +124,13 @@ def reference_arm(args):
             pool.map(_ref_chunk, jobs)
         dt = time.perf_counter() - t0
     value = sample * n * args.steps / dt
+    cfg = base_config(args.workload)
+    cfg["path"] = "scipy cdist (float64) + argpartition/sort per query row, all candidates"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "contigs": n, "dim": d, "k": k, "metric": metric,
-                   "path": "scipy cdist (float64) + argpartition/sort per query row, all candidates"},
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} of {n} query rows x all {n} candidates per step, "
                                    f"{cores} processes"},
@@ -130,55 +140,168 @@ def reference_arm(args):
     return 0
 
 
-def secondary_workloads(engine, synth, torch, peak):
-    """The other single-GPU configurations of BASELINE.json, device-resident, for context
-    (configs[1] 100 k x 10 k=16 both metrics; configs[2] BMU of 1 M contigs on a 64 x 64 mesh)."""
+# ---------------------------------------------------------------------------- secondary workloads
+
+def _peaks():
+    try:
+        mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return (float(mp["bf16_tflops_sustained"]), float(mp["bf16_tflops"]), float(mp["hbm_gbs"]),
+                "MEASURED_PEAKS.json (bf16_tflops_sustained; the FP16 tensor rate is the bf16 rate)")
+    except (OSError, ValueError, KeyError):
+        return 1590.0, 1590.0, 6500.0, "MEASURED_PEAKS.json absent: fallback 1590 TFLOP/s / 6500 GB/s (B200_PROFILING.md)"
+
+
+def _time_pipeline(torch, pipe, qd, cd, steps):
+    """-> (ms per step, scan ms of the last step) with everything resident."""
+    for _ in range(2):
+        pipe.run(qd, cd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        pipe.reset(); pipe.col_mean(cd); pipe.prep_candidates(cd); pipe.prep_queries(qd)
+        if i == steps - 1:
+            s0.record()
+        pipe.scan()
+        if i == steps - 1:
+            s1.record()
+        pipe.refine(qd, cd); pipe.exact_rows(qd, cd)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, s0.elapsed_time(s1)
+
+
+def _scan_record(pipe, name, nq, nc, d, ms, scan_ms, tc_peak, fp32_peak, metric="euclidean"):
+    pairs = float(nq) * float(nc)
+    alg_tf = 2.0 * d * pairs / (scan_ms * 1e-3) / 1e12
+    rec = {"workload": name, "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "scan_ms": scan_ms,
+           "scan_kernel": ("pruned tensor-core 3xFP16" if pipe.prune else "tensor-core 3xFP16" +
+                           (" (ordered full sweep)" if pipe.order else "")) if pipe.form == 3
+           else ("k=1 BMU scan" if pipe.bmu else "FP32 scan"),
+           "scan_tflops_algorithmic": alg_tf, "exact_rows": pipe.exact_row_count()}
+    if pipe.form == 3:
+        nkb = (d + 1 + 31) // 32
+        if pipe.prune:
+            st = pipe.prune_stats()
+            tiles = st["tiles_visited"]
+            rec["tiles_visited_fraction"] = st["visited_fraction"]
+        else:
+            tiles = -(-nq // 128) * -(-nc // 128)
+        ex_tf = tiles * nkb * TILE_FLOP / (scan_ms * 1e-3) / 1e12
+        rec["roofline"] = {"bound": "tensor", "achieved": alg_tf, "peak": tc_peak, "unit": "TFLOP/s",
+                           "frac": alg_tf / tc_peak, "executed_tflops": ex_tf, "frac_executed": ex_tf / tc_peak}
+    else:
+        pk = fp32_peak if metric == "euclidean" else fp32_peak / 2       # L1 has no FMA form: FADD rate
+        rec["roofline"] = {"bound": "fp32", "achieved": alg_tf, "peak": pk, "unit": "TFLOP/s", "frac": alg_tf / pk}
+    return rec
+
+
+def secondary_workloads(engine, synth, torch, tc_peak, fp32_peak):
+    """The other single-GPU configurations of BASELINE.json, device-resident, each with its own roofline
+    object: configs[4] without pruning (what the tensor pipeline does when nothing can be skipped),
+    configs[1] 100 k x 10 k=16 both metrics, configs[2] BMU of 1 M contigs on a 64 x 64 mesh, configs[3]
+    500 k x 136 raw signatures (k = 16 graph + bin-vs-bin medians), and the latency of the small calls."""
+    from groopm_b200 import _lib, dropin
     out = []
 
-    def run(name, q, c, k, metric, steps=10):
+    def run(name, q, c, k, metric, steps=10, **kw):
         same = c is None
         qd = torch.from_numpy(q).cuda()
         cd = qd if same else torch.from_numpy(c).cuda()
-        pipe = engine.KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, same=same)
-        for _ in range(3):
-            pipe.run(qd, cd)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            pipe.reset(); pipe.col_mean(cd); pipe.prep_candidates(cd); pipe.prep_queries(qd)
-            if i == steps - 1:
-                s0.record()
-            pipe.scan()
-            if i == steps - 1:
-                s1.record()
-            pipe.refine(qd, cd); pipe.exact_rows(qd, cd)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        scan_ms = s0.elapsed_time(s1)
-        pairs = float(qd.shape[0]) * float(cd.shape[0])
-        tf = 2.0 * qd.shape[1] * pairs / (scan_ms * 1e-3) / 1e12
-        pk = peak if metric == "euclidean" else peak / 2       # L1 has no FMA form: FADD rate
-        rec = {"workload": name, "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "scan_ms": scan_ms,
-               "scan_kernel": "tensor-core 3xFP16" if pipe.form == 3 else ("k=1 BMU scan" if pipe.bmu else "FP32 scan"),
-               "scan_tflops_algorithmic": tf, "exact_rows": pipe.exact_row_count()}
-        # fraction of the FP32 CUDA-core peak the ALGORITHMIC flops amount to (> 1 is possible on the tensor path)
-        rec["vs_fp32_pipe_peak"] = tf / pk
-        out.append(rec)
+        pipe = engine.KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, same=same, **kw)
+        ms, scan_ms = _time_pipeline(torch, pipe, qd, cd, steps)
+        out.append(_scan_record(pipe, name, qd.shape[0], cd.shape[0], qd.shape[1], ms, scan_ms, tc_peak, fp32_peak, metric))
+        del pipe
+        return qd
 
+    n, d, k, metric, seed = WORKLOADS["cfg5_1m_x30_k32"]
+    x = synth.cfg_knn_rows(n, d, seed)
+    run("cfg5_1m_x30_k32_full_sweep (no pruning: ordered sweep of every tile)", x, None, k, metric, steps=3,
+        form=_lib.FORM_TC, order=True, prune=False)
+    del x
     x = synth.cfg_knn_rows(100_000, 10, 2)
     run("cfg2_100k_x10_k16_euclidean", x, None, 16, "euclidean")
     run("cfg2_100k_x10_k16_cityblock", x, None, 16, "cityblock")
     block, nodes = synth.cfg_bmu(1_000_000, 64)
     run("cfg3_bmu_1m_x4_on_64x64", block, nodes.reshape(-1, 4), 1, "euclidean")
+    # configs[3]: 500 k raw 136-d signatures: the full 2.5e11-pair k = 16 graph, then the kDistBetweenBins
+    # medians of 250 bins x 2000 rows against their nearest bins (refine.py:1502-1503; 48 pairs timed)
+    sigs = synth.quantise(synth.kmer_sigs(500_000, 4), 34)
+    sd = run("cfg4_500k_x136_k16_euclidean", sigs, None, 16, "euclidean", steps=2)
+    torch.cuda.synchronize()
+    pairs_idx = [(np.arange(a * 2000, (a + 1) * 2000), np.arange(b * 2000, (b + 1) * 2000))
+                 for a in range(8) for b in ((a + 1) % 250, (a + 7) % 250, (a + 31) % 250, (a + 64) % 250,
+                                             (a + 100) % 250, (a + 200) % 250)]
+    t0 = time.perf_counter()
+    for ra, rb in pairs_idx:
+        engine.median_dist(sd[torch.from_numpy(ra).cuda()], sd[torch.from_numpy(rb).cuda()], "cityblock")
+    dt = time.perf_counter() - t0
+    out.append({"workload": "cfg4_bin_vs_bin_medians_2000x2000_d136_cityblock", "medians": len(pairs_idx),
+                "ms_per_median": dt / len(pairs_idx) * 1e3, "pairs_per_s": len(pairs_idx) * 4e6 / dt,
+                "note": "median(cdist(bin_i, bin_j, 'cityblock')) without the block (radix select, 7 passes)"})
+    del sd, sigs
+
+    # small-call latency against the scipy calls they replace (same host, same arrays)
+    from scipy.spatial import KDTree as SpKDTree
+    from scipy.spatial.distance import cdist as sp_cdist
+
+    flat = nodes.reshape(-1, 4)
+    vs = block[:2000]
+    bm = dropin.BestMatcher(flat, 64, 64)
+    for v in vs[:50]:
+        bm(v)
+    t0 = time.perf_counter()
+    for v in vs:
+        bm(v)
+    t_gpu = (time.perf_counter() - t0) / len(vs)
+    t0 = time.perf_counter()
+    for v in vs:
+        int(np.argmin(sp_cdist(flat, [v])))
+    t_cpu = (time.perf_counter() - t0) / len(vs)
+    t0 = time.perf_counter()
+    bm.many(block[:200_000])
+    t_many = (time.perf_counter() - t0) / 200_000
+    lat = {"workload": "small_call_latency_us",
+           "best_match_one_vector_4096_nodes": {"engine": t_gpu * 1e6, "scipy": t_cpu * 1e6,
+                                                "engine_batched_per_vector": t_many * 1e6}}
+    cent = np.random.default_rng(7).random((2000, 3))
+    tree_g, tree_c = dropin.KDTree(cent), SpKDTree(cent)
+    tree_g.query(cent[0], k=6)
+    t0 = time.perf_counter()
+    for r in cent[:500]:
+        tree_g.query(r, k=6)
+    tg = (time.perf_counter() - t0) / 500
+    t0 = time.perf_counter()
+    for r in cent[:500]:
+        tree_c.query(r, k=6)
+    tc_ = (time.perf_counter() - t0) / 500
+    t0 = time.perf_counter()
+    tree_g.query(cent, k=6)
+    tb = (time.perf_counter() - t0) / len(cent)
+    lat["kdtree_query_k6_2000_bins"] = {"engine_per_call": tg * 1e6, "scipy_per_call": tc_ * 1e6,
+                                        "engine_all_bins_one_call_per_bin": tb * 1e6}
+    a, b = x[:400], x[400:900]
+    dropin.k_dist_between(a, b)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        dropin.k_dist_between(a, b)
+    tg = (time.perf_counter() - t0) / 50
+    t0 = time.perf_counter()
+    for _ in range(50):
+        float(np.median(sp_cdist(a, b, "cityblock")))
+    tc_ = (time.perf_counter() - t0) / 50
+    lat["k_dist_between_400x500_d10"] = {"engine": tg * 1e6, "scipy": tc_ * 1e6}
+    out.append(lat)
     return out
 
 
 def cpu_baseline_leg(x, k, metric, seconds_target=12.0):
-    """Single-core oracle on a bounded sample of the same workload (rank 0, N=1 only)."""
+    """Single-core oracle on a bounded sample of the same workload (rank 0, N=1 only), and the
+    reference-literal figure BASELINE.md section 3 asks for: the per-contig ``argmin(cdist(flatNodes, [v]))``
+    Python loop of TorusMesh.bestMatch (torusMesh.py:127) on a 20 k sample of the cfg3 contigs."""
     import oracle
+    from groopm_b200 import synth
 
     n = x.shape[0]
     rows = max(8, int(seconds_target * 1.2e7 // n))
@@ -186,8 +309,18 @@ def cpu_baseline_leg(x, k, metric, seconds_target=12.0):
     t0 = time.perf_counter()
     oracle.knn(x[sel], x, k, metric, chunk=8)
     dt = time.perf_counter() - t0
+    block, nodes = synth.cfg_bmu(20_000, 64)
+    flat = nodes.reshape(-1, 4)
+    t0 = time.perf_counter()
+    for v in block:
+        oracle.best_match(flat, v, 64, 64)
+    lit = (time.perf_counter() - t0) / len(block)
     return {"value": len(sel) * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{len(sel)} of {n} query rows x all {n} candidates, scipy cdist + top-k, 1 thread, {dt:.1f} s"}
+            "sample": f"{len(sel)} of {n} query rows x all {n} candidates, scipy cdist + top-k, 1 thread, {dt:.1f} s",
+            "reference_literal": {"call": "TorusMesh.bestMatch: argmin(cdist(flatNodes, [v])) per contig (torusMesh.py:127)",
+                                  "us_per_contig": lit * 1e6, "pairs_per_s": 4096 / lit,
+                                  "sample": "20000 contigs x 4096 nodes x D=4, 1 thread",
+                                  "extrapolated_s_per_1m_contigs": lit * 1e6}}
 
 
 # ---------------------------------------------------------------------------- clocks
@@ -206,7 +339,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -241,6 +374,7 @@ def engine_arm(args):
     import torch
     import torch.distributed as tdist
 
+    from groopm_b200 import _lib
     from groopm_b200 import dist as gdist
     from groopm_b200 import engine, synth
 
@@ -276,155 +410,229 @@ def engine_arm(args):
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         return float(t.item())
 
-    n, d, k, metric, seed = WORKLOADS[args.workload]
-    x = synth.cfg_knn_rows(n, d, seed)                       # every rank draws the same array
-    r0, r1 = gdist.shard_bounds(n, world, rank)
-    n_local = r1 - r0
-    x_host = torch.from_numpy(x[r0:r1]).pin_memory()         # this rank's shard, pinned host
-    x_dev = x_host.to(dev)
-    order = world == 1 and (args.order == "on" or (args.order == "auto" and args.workload == "cfg5_1m_x30_k32"))
-    pipe = engine.KnnPipeline(max(n_local, 1), n, d, k, metric, same=(world == 1), device=dev, order=order)
-    out_idx_host = torch.empty((n_local, k), dtype=torch.int32).pin_memory()
-    out_dist_host = torch.empty((n_local, k), dtype=torch.float64).pin_memory()
-    scan_ms = []
-
-    def step(src_dev):
-        """One pass of the hot path for this rank's rows; returns device (idx, dist)."""
+    def sum_over_ranks(v: float) -> float:
         if world == 1:
-            q = c = src_dev
-        else:
-            c = gdist.gather_rows(src_dev, n)
-            q = c[r0:r1]
-        pipe.reset()
-        pipe.col_mean(c)
-        pipe.prep_candidates(c)
-        pipe.prep_queries(q)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pipe.scan()
-        e1.record()
-        scan_ms.append((e0, e1))
-        pipe.refine(q, c)
-        pipe.exact_rows(q, c)
-        return pipe.out_idx, pipe.out_dist
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
+        return float(t.item())
 
-    def e2e_step():
-        xd = x_host.to(dev, non_blocking=True)               # H2D of this step's profiles
-        idx, dist_ = step(xd)
-        out_idx_host.copy_(idx[:n_local], non_blocking=True)  # D2H of the step's result
-        out_dist_host.copy_(dist_[:n_local], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    prune = {"auto": None, "on": True, "off": False}[args.prune]
+    tc_peak, tc_burst, hbm_peak, peak_src = _peaks()
+
+    def measure(workload, steps, warmup, sample_clocks):
+        """The step of `workload` on this rank's shard: device-resident and end-to-end timings."""
+        n, d, k, metric, seed = WORKLOADS[workload]
+        x = synth.cfg_knn_rows(n, d, seed)                   # every rank draws the same array
+        r0, r1 = gdist.shard_bounds(n, world, rank)
+        n_local = r1 - r0
+        x_host = torch.from_numpy(x[r0:r1].copy()).pin_memory()   # this rank's shard, pinned host
+        x_dev = x_host.to(dev)
+        kw = dict(prune=prune)
+        if prune is False:
+            kw.update(form=_lib.FORM_TC, order=(world == 1))
+        pipe = engine.KnnPipeline(max(n_local, 1), n, d, k, metric, same=(world == 1), device=dev, **kw)
+        out_idx_host = torch.empty((n_local, k), dtype=torch.int32).pin_memory()
+        out_dist_host = torch.empty((n_local, k), dtype=torch.float64).pin_memory()
+        scan_ev = []
+
+        def step(src_dev):
+            """One pass of the hot path for this rank's rows; returns device (idx, dist)."""
+            if world == 1:
+                q = c = src_dev
+            else:
+                c = gdist.gather_rows(src_dev, n)
+                q = c[r0:r1]                                  # a run of the candidates' rows: the staging shares the keys
+            pipe.reset()
+            pipe.col_mean(c)
+            pipe.prep_candidates(c)
+            pipe.prep_queries(q)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe.scan()
+            e1.record()
+            scan_ev.append((e0, e1))
+            pipe.refine(q, c)
+            pipe.exact_rows(q, c)
+            return pipe.out_idx, pipe.out_dist
+
+        def e2e_step():
+            if world == 1:
+                # the plugin call: host arrays in, host arrays out (engine.knn keeps the pipeline of a shape and
+                # hands back pinned arrays)
+                return engine.knn(x_host.numpy(), None, k=k, metric=metric, prune=prune,
+                                  **({"form": _lib.FORM_TC, "order": True} if prune is False else {}))
+            xd = x_host.to(dev, non_blocking=True)           # H2D of this rank's profiles
+            idx, dist_ = gdist.sharded_knn(xd, n, k, metric, pipeline=pipe)
+            out_idx_host.copy_(idx[:n_local], non_blocking=True)   # D2H of this rank's result
+            out_dist_host.copy_(dist_[:n_local], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_idx_host, out_dist_host
+
+        # ---- (A) device-resident throughput
+        for _ in range(warmup):
+            step(x_dev)
+        barrier()
+        scan_ev.clear()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for _ in range(steps):
+            step(x_dev)
+        t_end.record()
+        barrier()
+        dev_ms = max_over_ranks(t_start.elapsed_time(t_end))
+        scan_ms = sum(a.elapsed_time(b) for a, b in scan_ev) / len(scan_ev)
+        scan_ms_max = max_over_ranks(scan_ms)
+        exact_rows = pipe.exact_row_count()
+        stats = pipe.prune_stats() if pipe.prune else None
+        res_idx, res_dist = pipe.out_idx[:n_local].clone(), pipe.out_dist[:n_local].clone()
+
+        # ---- (B) end to end through the public API with host buffers
+        for _ in range(warmup):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        clocks = sampler.stop() if sampler else None
+
+        # ---- (C) the C-ABI host entry point (gmd_knn_host_f64: library-owned buffers, pageable copies), N = 1
+        cabi_ms = None
+        if world == 1 and rank == 0 and prune is not False:
+            engine.knn_host(x, None, k, metric)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                engine.knn_host(x, None, k, metric)
+            cabi_ms = (time.perf_counter() - t0) / 2 * 1e3
+
+        # ---- (D) verification outside the timed regions: sampled rows of THIS rank's result against the
+        # reference's scipy arithmetic (oracle.knn as the checker)
+        verified = 0
+        ok = True
+        if not args.no_verify and n_local > 0:
+            import oracle
+
+            rows = np.sort(np.random.default_rng(1000 + rank).choice(n_local, min(64, n_local), replace=False))
+            od, oi = oracle.knn(x[r0 + rows], x, k, metric, chunk=16)
+            gi, gd = res_idx[rows].cpu().numpy(), res_dist[rows].cpu().numpy()
+            ok = bool(np.array_equal(gi, oi) and np.array_equal(gd, od))
+            verified = len(rows)
+        verified = int(sum_over_ranks(float(verified)))
+        all_ok = sum_over_ranks(0.0 if ok else 1.0) == 0.0
+        return dict(n=n, d=d, k=k, metric=metric, n_local=n_local, pipe=pipe, dev_ms=dev_ms, scan_ms=scan_ms,
+                    scan_ms_max=scan_ms_max, exact_rows=exact_rows, stats=stats, e2e_s=e2e_s, clocks=clocks,
+                    cabi_ms=cabi_ms, verified=verified, ok=all_ok, x=x,
+                    h2d=int(x_host.numel() * 8 * world),
+                    d2h=int((out_idx_host.numel() * 4 + out_dist_host.numel() * 8) * world))
 
     peak_probe = engine.fp32_peak_tflops()                   # measured FFMA2 peak of this GPU (uniform operand)
-    peak_vector = engine.fp32_peak_tflops(form="vector")     # same stream with the scan's operand mix
+    m = measure(args.workload, args.steps, args.warmup, True)
+    extra = []
+    if world == 8 and args.workload == "cfg5_1m_x30_k32" and not args.no_secondary:
+        # BASELINE configs[4] at its largest size rides along on the 8-GPU line
+        m4 = measure("cfg5_4m_x30_k32", 3, 2, False)
+        if rank == 0:
+            pairs4 = float(m4["n"]) ** 2
+            extra.append({"workload": "cfg5_4m_x30_k32", "n_gpus": world, "ms_per_step": m4["dev_ms"] / 3,
+                          "pairs_per_s": pairs4 * 3 / (m4["dev_ms"] * 1e-3),
+                          "e2e_ms_per_step": m4["e2e_s"] / 3 * 1e3, "scan_ms": m4["scan_ms_max"],
+                          "exact_rows_rank0": m4["exact_rows"], "verified_rows": m4["verified"],
+                          "verified": m4["ok"],
+                          "tiles_visited_fraction": m4["stats"]["visited_fraction"] if m4["stats"] else None})
 
-    # ---- (A) device-resident throughput
-    for _ in range(args.warmup):
-        step(x_dev)
-    barrier()
-    scan_ms.clear()
-    sampler = ClockSampler(local_rank)
+    rc = 0
     if rank == 0:
-        sampler.start()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(args.steps):
-        step(x_dev)
-    t_end.record()
-    barrier()
-    dev_ms = max_over_ranks(t_start.elapsed_time(t_end))
-    scan_avg_ms = sum(a.elapsed_time(b) for a, b in scan_ms) / len(scan_ms)
-    scan_avg_ms_max = max_over_ranks(scan_avg_ms)
-    exact_rows = pipe.exact_row_count()
-
-    # ---- (B) end to end through the public API with host buffers
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    clocks = sampler.stop() if rank == 0 else None
-
-    if rank == 0:
+        n, d, k, metric, pipe = m["n"], m["d"], m["k"], m["metric"], m["pipe"]
         pairs = float(n) * float(n)
-        value = pairs * args.steps / (dev_ms * 1e-3)
-        e2e_value = pairs * args.steps / e2e_s
-        # roofline of the dominant kernel (the FP32 scan): 2*D flop per pair (SURVEY.md 8d),
-        # one launch covers this rank's n_local x n pairs
-        launch_flop = 2.0 * d * float(n_local) * float(n)
-        achieved = launch_flop / (scan_avg_ms * 1e-3) / 1e12
-        nominal = None
-        props = torch.cuda.get_device_properties(dev)
-        if clocks and clocks.get("sm_max_mhz"):
-            nominal = props.multi_processor_count * 128 * 2 * clocks["sm_max_mhz"] * 1e6 / 1e12
+        value = pairs * args.steps / (m["dev_ms"] * 1e-3)
+        e2e_value = pairs * args.steps / m["e2e_s"]
+        # roofline of the dominant kernel: 2*D flop per pair (SURVEY.md 8d), one launch covers this rank's
+        # n_local x n pairs
+        launch_flop = 2.0 * d * float(m["n_local"]) * float(n)
+        achieved = launch_flop / (m["scan_ms"] * 1e-3) / 1e12
+        tc = pipe.form == 3
         traffic = None
         prof = ROOT / "profiles" / "scan_traffic.json"
+        variant = "pruned" if pipe.prune else ("ordered" if pipe.order else "plain")
         if prof.exists():
             try:
-                traffic = json.loads(prof.read_text()).get(args.workload)
+                traffic = json.loads(prof.read_text()).get(f"{args.workload}:{variant}")
             except (ValueError, OSError):
                 traffic = None
-        tc = pipe.form == 3                                    # GMD_FORM_TC: the tensor-core scan
         if tc:
-            # executed tensor work: K padded to 32, three FP16 passes (hi.hi + hi.lo + lo.hi)
-            executed = 2.0 * 32 * 3 * float(n_local) * float(n) / (scan_avg_ms * 1e-3) / 1e12
-            tc_peak, tc_src = 1590.0, "MEASURED_PEAKS.json absent: fallback 1590 TFLOP/s (B200_PROFILING.md)"
-            try:
-                mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-                tc_peak = float(mp["bf16_tflops"])
-                tc_src = "MEASURED_PEAKS.json bf16_tflops (FP16 tensor rate = bf16 rate), burst figure"
-            except (OSError, ValueError, KeyError):
-                pass
-            roofline = {"bound": "tensor", "kernel": "gmd_tc::scan_tc_kernel", "achieved": achieved,
-                        "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "peak_source": tc_src,
-                        "note": "achieved = ALGORITHMIC flops (2*D per pair); the kernel executes 2*32*3 per pair "
-                                "(K padded to 32, 3 x FP16 hi/lo split for FP32-class accuracy)",
-                        "executed_tflops": executed, "frac_executed": executed / tc_peak,
-                        "fp32_pipe_peak": peak_probe, "vs_fp32_pipe_peak": achieved / peak_probe,
-                        "scan_ms_per_launch": scan_avg_ms_max, "flop_per_launch": launch_flop, "traffic": traffic}
+            nkb = (d + 1 + 31) // 32
+            tiles = m["stats"]["tiles_visited"] if m["stats"] else (-(-m["n_local"] // 128) * -(-n // 128))
+            executed = tiles * nkb * TILE_FLOP / (m["scan_ms"] * 1e-3) / 1e12
+            roofline = {
+                "bound": "tensor",
+                "kernel": "gmd_tc::scan_tc_prune_kernel" if pipe.prune else "gmd_tc::scan_tc_kernel",
+                "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+                "peak_source": peak_src, "peak_burst": tc_burst, "frac_of_burst": achieved / tc_burst,
+                "note": "achieved = ALGORITHMIC flops (2*D per pair of the whole Nq x Nc problem) / scan time; the "
+                        "pruned scan loads only the candidate tiles whose ball bound its running thresholds cannot "
+                        "rule out, so it runs above the dense tensor roofline while the result stays exact; "
+                        "executed_tflops counts the tiles it did multiply (K padded to 32, 3 x FP16 hi/lo passes)",
+                "executed_tflops": executed, "frac_executed": executed / tc_peak,
+                "tiles_visited_fraction": m["stats"]["visited_fraction"] if m["stats"] else 1.0,
+                "fp32_pipe_peak": peak_probe, "vs_fp32_pipe_peak": achieved / peak_probe,
+                "scan_ms_per_launch": m["scan_ms_max"], "flop_per_launch": launch_flop, "traffic": traffic,
+                "traffic_source": f"profiles/scan_traffic.json [{args.workload}:{variant}] (ncu --set full of this "
+                                  "variant)" if traffic is not None else None}
         else:
             roofline = {"bound": "fp32", "kernel": "gmd_scan::scan_topk_kernel", "achieved": achieved,
                         "peak": peak_probe, "unit": "TFLOP/s", "frac": achieved / peak_probe,
                         "peak_source": "FFMA2 probe kernel (uniform-register multiplicand) measured on this GPU "
                                        "in this run; MEASURED_PEAKS.json has no FP32 entry",
-                        "peak_vector_operands": peak_vector,
-                        "peak_nominal": nominal, "frac_of_nominal": (achieved / nominal) if nominal else None,
-                        "scan_ms_per_launch": scan_avg_ms_max, "flop_per_launch": launch_flop, "traffic": traffic}
+                        "scan_ms_per_launch": m["scan_ms_max"], "flop_per_launch": launch_flop, "traffic": traffic}
+        cfg = base_config(args.workload)
+        cfg.update({
+            "parallelism": (f"query rows block-sharded over {world} GPUs; one NCCL all-gather of the float64 rows per "
+                            f"step; the same pruned scan on every rank" if world > 1 else "single GPU"),
+            "arithmetic": ("tcgen05 3xFP16 hi/lo split (FP32-class) " if tc else "FP32 ") +
+                          "fused distance+top-k scan proposes k+8 candidates; float64 re-rank and certificate make "
+                          "the result exact" +
+                          ("; profiles staged in the grouped order (leader clustering of a sample, nearest-leader "
+                           "keys, groups padded to whole tiles, all inside the timed step) and candidate tiles "
+                           "skipped by ball bounds" if pipe.prune else ""),
+            "pruned_scan": bool(pipe.prune), "ordered_sweep": bool(pipe.order), "form": pipe.form, "kk": pipe.kk,
+            "exact_rows_last_step": m["exact_rows"], "verified_rows": m["verified"], "verified": m["ok"],
+            "verification": "sampled rows of every rank's result == oracle.knn (scipy float64), bit for bit, outside "
+                            "the timed regions",
+        })
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": m["dev_ms"] / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16x3" if tc else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "contigs": n, "dim": d, "k": k, "metric": metric,
-                       "parallelism": f"query rows block-sharded over {world} GPU(s); one NCCL all-gather of the "
-                                      f"float64 rows per step" if world > 1 else "single GPU",
-                       "l2": "inputs exceed L2 (float64 profiles %d MB, FP32 tiles %d MB)" %
-                             (n * d * 8 // 2**20, pipe.ctiles.numel() * 4 // 2**20),
-                       "arithmetic": ("tcgen05 3xFP16 hi/lo split (FP32-class) " if pipe.form == 3 else "FP32 ") +
-                                     "fused distance+top-k scan proposes k+8 candidates; float64 re-rank "
-                                     "and certificate make the result exact" +
-                                     ("; profiles staged in a locality-preserving order (nearest of %d sampled "
-                                      "profiles, counting sort, inside the timed step), every query tile sweeps "
-                                      "from its own position" % pipe.order_ncl if pipe.order else ""),
-                       "ordered_sweep": bool(pipe.order),
-                       "form": pipe.form, "kk": pipe.kk, "nsplit": pipe.nsplit, "exact_rows_last_step": exact_rows},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "h2d_bytes_per_step": int(x_host.numel() * 8 * world),
-                    "d2h_bytes_per_step": int((out_idx_host.numel() * 4 + out_dist_host.numel() * 8) * world)},
+            "config": cfg,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": m["e2e_s"] / args.steps * 1e3,
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                    "call": "engine.knn(numpy float64 rows) -> numpy (indices, distances)" if world == 1 else
+                            "dist.sharded_knn between pinned host buffers on every rank",
+                    "c_abi_gmd_knn_host_f64_ms": m["cabi_ms"]},
             "gpu_launches": pipe.launches_per_run * args.steps,
-            "clocks": clocks,
+            "clocks": m["clocks"],
             "roofline": roofline,
         }
+        if not m["ok"]:
+            rc = 1
         if world == 1 and not args.no_secondary:
-            line["secondary"] = secondary_workloads(engine, synth, torch, peak_probe)
+            del m["x"]
+            extra += secondary_workloads(engine, synth, torch, tc_peak, peak_probe)
+        if extra:
+            line["config"]["secondary"] = extra
+            line["roofline"]["secondary"] = extra
         if world == 1 and not args.no_cpu_baseline:
+            x = synth.cfg_knn_rows(n, d, WORKLOADS[args.workload][4])
             line["cpu_baseline"] = cpu_baseline_leg(x, k, metric)
         emit(line)
     if world > 1:
         tdist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

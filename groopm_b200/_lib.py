@@ -79,6 +79,12 @@ SIGNATURES = {
     "gmd_median_workspace_bytes": (_sz, []),
     "gmd_median_dist_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "gmd_median_batch_f64": (_int, [_vp, _i64, _int, _int, _vp, _vp, _int, _vp, _vp]),
+    "gmd_nonfinite_f64": (_int, [_vp, _i64, _vp, _vp]),
+    "gmd_zero_async": (_int, [_vp, _sz, _vp]),
+    "gmd_bmu_small_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
+    "gmd_knn_small_max_candidates": (_int, []),
+    "gmd_knn_small_f64": (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp]),
+    "gmd_indptr_from_counts_i64": (_int, [_vp, _i64, _vp, _vp]),
     "gmd_som_update_f64": (_int, [_vp, _vp, _int, _int, _int, _vp, _i64, _vp, _vp, _int, _vp, _int, _vp, _vp]),
     "gmd_pick_form": (_int, [_int, _int]),
     "gmd_pick_kk": (_int, [_int]),

@@ -7,6 +7,8 @@
 #include "common.cuh"
 #include <math_constants.h>
 
+#include <algorithm>
+
 namespace {
 
 constexpr int PT = 32;  // pair tile edge
@@ -504,6 +506,192 @@ extern "C" int gmd_median_dist_f64(const double* A, int64_t mA, const double* B,
     }
     if (!(total & 1ull)) select_below_kernel<<<grid, block, 0, st>>>(A, mA, B, mB, D, metric, self, state);
     select_finish_kernel<<<1, 32, 0, st>>>(state, total, out_median);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+// ---- small helpers of the host layer (so that no eager PyTorch kernel sits on the pairwise paths)
+namespace {
+__global__ void __launch_bounds__(256) nonfinite_kernel(const double* __restrict__ X, long long n, int32_t* __restrict__ flag) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= !isfinite(X[i]);
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+
+// one block: out[0] = 0, out[i + 1] = in[0] + ... + in[i]
+__global__ void __launch_bounds__(1024) scan_i64_kernel(const long long* __restrict__ in, long long n,
+                                                        long long* __restrict__ out) {
+    __shared__ long long part[1024];
+    const int tid = threadIdx.x;
+    const long long per = (n + 1023) / 1024;
+    const long long a = min(n, tid * per), b = min(n, a + per);
+    long long sum = 0;
+    for (long long i = a; i < b; ++i) sum += in[i];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    long long run = part[tid] - sum;
+    if (tid == 0) out[0] = 0;
+    for (long long i = a; i < b; ++i) {
+        run += in[i];
+        out[i + 1] = run;
+    }
+}
+}  // namespace
+
+// ---- best-matching unit of a FEW vectors, straight in float64: argmin(cdist(nodes, [v])) as the reference
+// calls it per contig (torusMesh.py:127, som.py:351).  One block per vector, scipy's arithmetic, first minimum.
+// One launch and no staging: what a single bestMatch call costs is launch latency, not arithmetic.
+namespace {
+__global__ void __launch_bounds__(256) bmu_small_kernel(const double* __restrict__ nodes, long long M,
+                                                       const double* __restrict__ X, int D, int32_t* __restrict__ out_idx,
+                                                       double* __restrict__ out_dist, int32_t* __restrict__ flag) {
+    __shared__ double sd[8];
+    __shared__ long long si[8];
+    const double* v = X + (size_t)blockIdx.x * D;
+    double best = CUDART_INF;
+    long long bi = 0x7fffffffffffffffll;
+    bool bad = false;
+    for (long long j = threadIdx.x; j < M; j += blockDim.x) {
+        const double* c = nodes + (size_t)j * D;
+        double s = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double t = __dsub_rn(c[d], v[d]);
+            s = __dadd_rn(s, __dmul_rn(t, t));
+        }
+        const double dist = sqrt(s);
+        bad |= !(dist == dist) || dist == CUDART_INF;
+        if (dist < best || (dist == best && j < bi)) best = dist, bi = j;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const long long oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        if (od < best || (od == best && oi < bi)) best = od, bi = oi;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0 && flag) atomicExch(flag, 1);
+    if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = best, si[threadIdx.x >> 5] = bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (sd[w] < best || (sd[w] == best && si[w] < bi)) best = sd[w], bi = si[w];
+        out_idx[blockIdx.x] = (int32_t)bi;
+        if (out_dist) out_dist[blockIdx.x] = best;
+    }
+}
+}  // namespace
+
+extern "C" int gmd_bmu_small_f64(const double* nodes, int64_t M, const double* X, int64_t N, int D, int32_t* out_idx,
+                                 double* out_dist, int32_t* flag, void* stream) {
+    GMD_REQUIRE(nodes && X && out_idx && M > 0 && M < 0x7fffffffll && N > 0 && N <= 65535 && D >= 1, GMD_ERR_BAD_ARG,
+                "bmu_small: bad arguments");
+    if (flag) GMD_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), (cudaStream_t)stream));
+    bmu_small_kernel<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>(nodes, M, X, D, out_idx, out_dist, flag);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+// ---- k nearest candidates of a FEW query rows, straight in float64: KDTree(data).query(x, k) as
+// findMergeGroups calls it once per bin (refine.py:653-665).  One block per query: all distances into shared
+// memory (scipy's arithmetic), then k rounds of "smallest (distance, index) above the last one taken".
+namespace {
+constexpr int KNS_MAX_NC = 16384;   // candidates whose distances fit a block's shared memory
+__global__ void __launch_bounds__(256) knn_small_kernel(const double* __restrict__ Q, const double* __restrict__ C,
+                                                       int Nc, int D, int k, int metric, int32_t* __restrict__ out_idx,
+                                                       double* __restrict__ out_dist, int32_t* __restrict__ flag) {
+    extern __shared__ double kd[];                    // [Nc] distances of this query
+    __shared__ double rd[8];
+    __shared__ int ri[8];
+    __shared__ double last_d;
+    __shared__ int last_i;
+    const double* q = Q + (size_t)blockIdx.x * D;
+    bool bad = false;
+    for (int j = threadIdx.x; j < Nc; j += blockDim.x) {
+        const double* c = C + (size_t)j * D;
+        double s = 0.0;
+        if (metric == GMD_L2) {
+            for (int d = 0; d < D; ++d) {
+                const double t = __dsub_rn(q[d], c[d]);
+                s = __dadd_rn(s, __dmul_rn(t, t));
+            }
+            s = sqrt(s);
+        } else {
+            for (int d = 0; d < D; ++d) s = __dadd_rn(s, fabs(__dsub_rn(q[d], c[d])));
+        }
+        bad |= !(s == s) || s == CUDART_INF;
+        kd[j] = s;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0 && flag) atomicExch(flag, 1);
+    if (threadIdx.x == 0) last_d = -1.0, last_i = -1;
+    __syncthreads();
+    for (int r = 0; r < k; ++r) {
+        const double pd = last_d;
+        const int pi = last_i;
+        double best = CUDART_INF;
+        int bi = 0x7fffffff;
+        for (int j = threadIdx.x; j < Nc; j += blockDim.x) {
+            const double v = kd[j];
+            const bool after = v > pd || (v == pd && j > pi);       // not taken yet
+            if (after && (v < best || (v == best && j < bi))) best = v, bi = j;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (od < best || (od == best && oi < bi)) best = od, bi = oi;
+        }
+        if ((threadIdx.x & 31) == 0) rd[threadIdx.x >> 5] = best, ri[threadIdx.x >> 5] = bi;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w)
+                if (rd[w] < best || (rd[w] == best && ri[w] < bi)) best = rd[w], bi = ri[w];
+            out_idx[(size_t)blockIdx.x * k + r] = bi;
+            out_dist[(size_t)blockIdx.x * k + r] = best;
+            last_d = best, last_i = bi;
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+extern "C" int gmd_knn_small_max_candidates(void) { return KNS_MAX_NC; }
+
+extern "C" int gmd_knn_small_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
+                                 int32_t* out_idx, double* out_dist, int32_t* flag, void* stream) {
+    GMD_REQUIRE(Q && C && out_idx && out_dist && Nq > 0 && Nq <= 65535 && Nc > 0 && Nc <= KNS_MAX_NC && D >= 1 && k >= 1 &&
+                    k <= Nc,
+                GMD_ERR_BAD_ARG, "knn_small: bad arguments (Nq=%lld Nc=%lld k=%d)", (long long)Nq, (long long)Nc, k);
+    GMD_REQUIRE(metric == GMD_L2 || metric == GMD_L1, GMD_ERR_BAD_ARG, "knn_small: bad metric %d", metric);
+    if (flag) GMD_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), (cudaStream_t)stream));
+    const size_t smem = (size_t)Nc * sizeof(double);
+    GMD_CUDA_CHECK(cudaFuncSetAttribute(knn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_small_kernel<<<(unsigned)Nq, 256, smem, (cudaStream_t)stream>>>(Q, C, (int)Nc, D, k, metric, out_idx, out_dist, flag);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+extern "C" int gmd_zero_async(void* p, size_t bytes, void* stream) {
+    GMD_REQUIRE(p || bytes == 0, GMD_ERR_BAD_ARG, "zero_async: null pointer");
+    if (bytes) GMD_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+    return GMD_OK;
+}
+
+extern "C" int gmd_nonfinite_f64(const double* X, int64_t n, int32_t* flag, void* stream) {
+    GMD_REQUIRE(X && flag && n >= 0, GMD_ERR_BAD_ARG, "nonfinite: bad arguments");
+    if (n == 0) return GMD_OK;
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    nonfinite_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, flag);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
+
+extern "C" int gmd_indptr_from_counts_i64(const int64_t* counts, int64_t n, int64_t* indptr, void* stream) {
+    GMD_REQUIRE(counts && indptr && n > 0, GMD_ERR_BAD_ARG, "indptr_from_counts: bad arguments");
+    scan_i64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const long long*)counts, n, (long long*)indptr);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
 }

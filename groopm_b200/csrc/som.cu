@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(128) som_update_kernel(const double* __restric
                 for (int b = 0; b < 3; ++b) {
                     const int dc = dc0 + (b - 1) * cols;
                     if (dc < -sr || dc > sr) continue;
-                    const double s = stamp[(dr + sr) * sw + (dc + sr)];
+                    // som.py:360-363 multiplies dimensions 0..3 by the stamp, by name; any further dimension
+                    // of the patch keeps the whole difference
+                    const double s = dim < 4 ? stamp[(dr + sr) * sw + (dc + sr)] : 1.0;
                     P[a][b] = __dadd_rn(P[a][b], __dmul_rn(tneg, s));  // *= stamp ; deltasheet += patch
                 }
             }

@@ -25,9 +25,57 @@ def best_match(flat_nodes, target_vector, rows: int, columns: int):
     return [row, col]
 
 
+class BestMatcher:
+    """TorusMesh.bestMatch (torusMesh.py:123-130) for a mesh whose ``flatNodes`` stay put between calls -- what
+    ``fixFlatNodes`` (torusMesh.py:103) leaves behind: the nodes are uploaded ONCE, and every call costs a
+    32-byte copy, one kernel launch (``gmd_bmu_small_f64``) and a 4-byte read.  ``matcher(v) -> [row, col]``
+    with the reference's ``col = loc - row*rows`` arithmetic; ``matcher.many(vectors)`` for a batch."""
+
+    def __init__(self, flat_nodes, rows: int, columns: int, device=None):
+        import torch
+
+        fn = np.ascontiguousarray(flat_nodes, dtype=np.float64)
+        if fn.ndim != 2:
+            raise ValueError("XA must be a 2-dimensional array.")
+        self.rows, self.columns = int(rows), int(columns)
+        self._dev = engine._device(device)
+        self._nodes = torch.from_numpy(fn).to(self._dev)
+        self._v_host = torch.empty((1, fn.shape[1]), dtype=torch.float64, pin_memory=True)
+        self._v = torch.empty((1, fn.shape[1]), dtype=torch.float64, device=self._dev)
+        self._out = torch.empty(2, dtype=torch.int32, device=self._dev)      # [loc, non-finite flag]
+        self._out_host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+        self._lib = engine._lib.lib()
+
+    def __call__(self, target_vector):
+        import torch
+
+        v = np.asarray(target_vector, dtype=np.float64).reshape(1, -1)
+        if v.shape[1] != self._nodes.shape[1]:
+            raise ValueError("XA and XB must have the same number of columns "
+                             "(i.e. feature dimension.)")
+        self._v_host.numpy()[:] = v
+        with torch.cuda.device(self._dev):
+            st = engine._stream_ptr()
+            self._v.copy_(self._v_host, non_blocking=True)
+            engine._lib.check(self._lib.gmd_bmu_small_f64(self._nodes.data_ptr(), self._nodes.shape[0], self._v.data_ptr(),
+                                                          1, v.shape[1], self._out.data_ptr(), 0,
+                                                          self._out.data_ptr() + 4, st))
+            self._out_host.copy_(self._out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        loc, bad = int(self._out_host[0]), int(self._out_host[1])
+        if bad:
+            raise FloatingPointError("non-finite value in an input profile")
+        row = int(loc / self.columns)
+        return [row, loc - (row * self.rows)]
+
+    def many(self, vectors):
+        return best_match_many(self._nodes, vectors, self.rows, self.columns)
+
+
 def best_match_many(flat_nodes, vectors, rows: int, columns: int):
     """bestMatch for every row of ``vectors`` in one launch -> (row[], col[]) int64."""
-    loc = np.asarray(engine.bmu(flat_nodes, vectors)).astype(np.int64)
+    loc = engine.bmu(flat_nodes, vectors)
+    loc = (loc.cpu().numpy() if hasattr(loc, "cpu") else np.asarray(loc)).astype(np.int64)
     row = (loc / columns).astype(np.int64)
     col = loc - row * rows
     return row, col
@@ -43,7 +91,8 @@ def classify_contigs(flat_nodes, block, bin_assignments, rows: int, columns: int
 def som_train_bmus(flat_nodes, train_vectors, index_array):
     """The inner ``argmin(cdist(flat_nodes, [trainVector[j]]))`` of SOM.train
     (som.py:348-353) for all j of one iteration (nodes are frozen inside it)
-    -> (row[], col[]) with ``col = loc - row*cols`` as at som.py:352-353."""
+    -> flat locations ``loc`` [len(index_array)] int64; the caller's ``row = int(loc/cols)``,
+    ``col = loc - row*cols`` (som.py:352-353) follow from them."""
     tv = np.asarray(train_vectors, dtype=np.float64)[np.asarray(index_array)]
     return np.asarray(engine.bmu(flat_nodes, tv)).astype(np.int64)
 
@@ -77,6 +126,7 @@ class KDTree:
         if self.data.ndim != 2:
             raise ValueError("data must be 2 dimensions")
         self.n, self.m = self.data.shape
+        self._dev_data = None                               # uploaded on the first query, then resident
 
     def query(self, x, k=1, p=2):
         if p != 2:
@@ -87,8 +137,15 @@ class KDTree:
         if xq.shape[-1] != self.m:
             raise ValueError(f"x must consist of vectors of length {self.m} but has shape {xa.shape}")
         kk = min(int(k), self.n)
-        idx, dist = engine.knn(xq, self.data, k=kk, metric="euclidean")
-        idx = idx.astype(np.intp)
+        import torch
+
+        if self._dev_data is None:
+            self._dev_data = torch.from_numpy(self.data).to(engine._device())
+        # the tree's points stay on the device; only the query rows travel (refine.py:664-665 calls this once
+        # per bin in a Python loop)
+        xd = torch.from_numpy(np.ascontiguousarray(xq)).to(self._dev_data.device)
+        idx_d, dist_d = engine.knn(xd, self._dev_data, k=kk, metric="euclidean")
+        idx, dist = idx_d.cpu().numpy().astype(np.intp), dist_d.cpu().numpy()
         if kk < k:  # scipy pads missing neighbours with (inf, n)
             pad = k - kk
             dist = np.concatenate([dist, np.full((len(xq), pad), np.inf)], axis=1)

@@ -165,8 +165,8 @@ class KnnPipeline:
 
     # -- stages (each a single C-ABI call on the current stream)
     def reset(self):
-        self.stats.zero_()
-        self.flags.zero_()
+        _lib.check(self.lib.gmd_zero_async(_ptr(self.stats), 16, _stream_ptr()))
+        _lib.check(self.lib.gmd_zero_async(_ptr(self.flags), 16, _stream_ptr()))
 
     def col_mean(self, c: torch.Tensor):
         _lib.check(self.lib.gmd_col_mean_f64(_ptr(c), self.nc, self.d, _ptr(self.center), _stream_ptr()))
@@ -308,6 +308,36 @@ class KnnPipeline:
         return 7 if self.same else 8
 
 
+# Pipelines own every device buffer of a shape (hundreds of MB at 1 M rows): the reference calls these entry
+# points in loops over bins and iterations with one shape, so the last few are kept.
+_PIPES: "dict[tuple, KnnPipeline]" = {}
+_PIPES_MAX = 4
+
+
+def _pipeline(nq, nc, d, k, metric, form, same, dev, order, prune) -> KnnPipeline:
+    key = (int(nq), int(nc), int(d), int(k), _metric(metric), form, bool(same), str(dev), order, prune)
+    pipe = _PIPES.pop(key, None)
+    if pipe is None:
+        pipe = KnnPipeline(nq, nc, d, k, metric, form, same=same, device=dev, order=order, prune=prune)
+        while len(_PIPES) >= _PIPES_MAX:
+            _PIPES.pop(next(iter(_PIPES)))
+    _PIPES[key] = pipe                                      # most recently used last
+    return pipe
+
+
+def clear_cache():
+    """Drop the cached pipelines (and their device buffers)."""
+    _PIPES.clear()
+
+
+def _host_copy(t: torch.Tensor) -> torch.Tensor:
+    """Device tensor -> pinned host tensor, asynchronously on the current stream (torch keeps the pinned
+    blocks it has handed out, so repeated calls of one shape do not page-lock memory again)."""
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    return h
+
+
 def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, device=None,
         return_info: bool = False, order: Optional[bool] = None, prune: Optional[bool] = None):
     """k nearest rows of ``c`` for every row of ``q``; ascending (distance, index).
@@ -325,18 +355,37 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
                          "(i.e. feature dimension.)")
     if qt.shape[0] == 0 or ct.shape[0] == 0 or qt.shape[1] == 0:
         raise ValueError("empty profile set")
-    dev = qt.device if qt.is_cuda else _device(device)
+    dev = qt.device if qt.is_cuda else (ct.device if ct.is_cuda else _device(device))
     with torch.cuda.device(dev):
         qd = qt.to(dev, non_blocking=True)
         cd = qd if same else ct.to(dev, non_blocking=True)
-        pipe = KnnPipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, form, same=same, device=dev,
-                           order=order, prune=prune)
+        if (form is None and not return_info and qd.shape[0] <= SMALL_KNN_ROWS and 1 <= k <= cd.shape[0]
+                and cd.shape[0] <= _lib.lib().gmd_knn_small_max_candidates()):
+            # a few query rows against a small candidate set (a KDTree.query call per bin, refine.py:664-665):
+            # one float64 kernel, no staging
+            n = qd.shape[0]
+            idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+            dist = torch.empty((n, k), dtype=torch.float64, device=dev)
+            flag = torch.empty(1, dtype=torch.int32, device=dev)
+            _lib.check(_lib.lib().gmd_knn_small_f64(_ptr(qd), n, _ptr(cd), cd.shape[0], qd.shape[1], int(k),
+                                                    _metric(metric), _ptr(idx), _ptr(dist), _ptr(flag), _stream_ptr()))
+            if q_np:
+                idx_h, dist_h, flag_h = _host_copy(idx), _host_copy(dist), _host_copy(flag)
+                torch.cuda.current_stream().synchronize()
+                bad, idx, dist = int(flag_h[0]), idx_h.numpy(), dist_h.numpy()
+            else:
+                bad = int(flag.item())
+            if bad:
+                raise FloatingPointError("non-finite value in an input profile")
+            return idx, dist
+        pipe = _pipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, form, same, dev, order, prune)
         idx, dist = pipe.run(qd, cd)
         if q_np:
-            idx_h, dist_h = idx.cpu().numpy(), dist.cpu().numpy()  # synchronises
-            if pipe.saw_nonfinite():
+            idx_h, dist_h, flags_h = _host_copy(idx), _host_copy(dist), _host_copy(pipe.flags)
+            torch.cuda.current_stream().synchronize()
+            if int(flags_h[0]):
                 raise FloatingPointError("non-finite value in an input profile")
-            out = (idx_h, dist_h)
+            out = (idx_h.numpy(), dist_h.numpy())
         else:
             if pipe.saw_nonfinite():
                 raise FloatingPointError("non-finite value in an input profile")
@@ -348,9 +397,39 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
         return out
 
 
+SMALL_BMU_ROWS = 256     # up to this many vectors go to the one-launch float64 kernel
+SMALL_KNN_ROWS = 64      # up to this many query rows (against a small candidate set) likewise
+
+
 def bmu(nodes, x, device=None, return_dist: bool = False):
     """Flat best-matching-unit index of every row of ``x`` on ``nodes`` [M, D]:
-    ``argmin(cdist(nodes, [x_i]))`` (torusMesh.py:127, som.py:351), first minimum."""
+    ``argmin(cdist(nodes, [x_i]))`` (torusMesh.py:127, som.py:351), first minimum.
+    A handful of vectors (the per-contig bestMatch call) takes one float64 kernel launch
+    (``gmd_bmu_small_f64``); batches go through the staged k = 1 pipeline."""
+    xt, x_np = _as_rows(x, "XA")
+    nt, _ = _as_rows(nodes, "XB")
+    if xt.shape[1] != nt.shape[1]:
+        raise ValueError("XA and XB must have the same number of columns "
+                         "(i.e. feature dimension.)")
+    if 0 < xt.shape[0] <= SMALL_BMU_ROWS and nt.shape[0] > 0:
+        dev = xt.device if xt.is_cuda else (nt.device if nt.is_cuda else _device(device))
+        with torch.cuda.device(dev):
+            xd, nd = _to_dev(xt, dev), _to_dev(nt, dev)
+            n = xd.shape[0]
+            loc = torch.empty(n, dtype=torch.int32, device=dev)
+            dist = torch.empty(n, dtype=torch.float64, device=dev)
+            flag = torch.empty(1, dtype=torch.int32, device=dev)
+            _lib.check(_lib.lib().gmd_bmu_small_f64(_ptr(nd), nd.shape[0], _ptr(xd), n, xd.shape[1], _ptr(loc),
+                                                    _ptr(dist), _ptr(flag), _stream_ptr()))
+            if x_np:
+                loc_h, dist_h, flag_h = _host_copy(loc), _host_copy(dist), _host_copy(flag)
+                torch.cuda.current_stream().synchronize()
+                bad, loc, dist = int(flag_h[0]), loc_h.numpy(), dist_h.numpy()
+            else:
+                bad = int(flag.item())
+            if bad:
+                raise FloatingPointError("non-finite value in an input profile")
+            return (loc, dist) if return_dist else loc
     idx, dist = knn(x, nodes, k=1, metric="euclidean", device=device)
     if return_dist:
         return idx[:, 0], dist[:, 0]
@@ -421,9 +500,15 @@ def _out(t: torch.Tensor, as_numpy: bool):
 
 
 def _check_finite(*tensors):
+    """np.seterr(all='raise') semantics of the reference (torusMesh.py:57): a NaN / Inf profile is a
+    FloatingPointError.  One flag kernel per array and one 4-byte read."""
+    lib = _lib.lib()
+    flag = torch.empty(1, dtype=torch.int32, device=tensors[0].device)
+    _lib.check(lib.gmd_zero_async(_ptr(flag), 4, _stream_ptr()))
     for t in tensors:
-        if not bool(torch.isfinite(t).all().item()):
-            raise FloatingPointError("non-finite value in an input profile")
+        _lib.check(lib.gmd_nonfinite_f64(_ptr(t), t.numel(), _ptr(flag), _stream_ptr()))
+    if int(flag.item()):
+        raise FloatingPointError("non-finite value in an input profile")
 
 
 def cdist(xa, xb, metric="euclidean", device=None):
@@ -542,8 +627,8 @@ def radius_neighbours(x, radius: float, metric="cityblock", return_dist: bool = 
             raise FloatingPointError("radius is NaN")
         counts = torch.empty(n, dtype=torch.int64, device=dev)
         _lib.check(lib.gmd_radius_count_f64(_ptr(xd), n, d, m, float(radius), _ptr(counts), _stream_ptr()))
-        indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(counts, 0, out=indptr[1:])
+        indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        _lib.check(lib.gmd_indptr_from_counts_i64(_ptr(counts), n, _ptr(indptr), _stream_ptr()))
         nnz = int(indptr[-1].item())
         indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
         dists = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev) if return_dist else None
@@ -721,6 +806,9 @@ def som_train(nodes, train_vectors, weights=None, iterations: int = 1000, vector
     tv = np.ascontiguousarray(train_vectors, dtype=np.float64)
     if tv.ndim != 2 or tv.shape[1] != dim:
         raise ValueError("training vectors must be [n, dimension] with the mesh's dimension")
+    if dim < 4:
+        # the reference scales weights_patch[:, :, 0..3] by name (som.py:360-363)
+        raise IndexError(f"index 3 is out of bounds for axis 2 with size {dim}")
     if not (np.isfinite(w_host).all() and np.isfinite(tv).all()):
         raise FloatingPointError("non-finite value in the SOM weights or training vectors")
     if radius == 0.0:
@@ -748,9 +836,13 @@ def som_train(nodes, train_vectors, weights=None, iterations: int = 1000, vector
                 raise ValueError("mask must be [rows, cols]")
             mask_any = bool(m.any())
             mask_d = torch.from_numpy(m).to(dev)
+        loc = torch.empty(max(cut_off, 1), dtype=torch.int32, device=dev)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        small = 0 < cut_off <= 65535                         # one float64 kernel per iteration (gmd_bmu_small_f64)
         pipe = None
-        if cut_off > 0:
+        if cut_off > 0 and not small:
             pipe = KnnPipeline(cut_off, rows * cols, dim, 1, "euclidean", same=False, device=dev)
+        bad = False
         for i in range(1, iterations + 1):
             radius_decaying = radius * np.exp(-1.0 * i / time_constant)
             if radius_decaying < 2:
@@ -764,13 +856,20 @@ def som_train(nodes, train_vectors, weights=None, iterations: int = 1000, vector
                 continue
             idx_d = torch.from_numpy(np.ascontiguousarray(index_array, dtype=np.int32)).to(dev)
             q = x.index_select(0, idx_d.long())
-            loc, _ = pipe.run(q, flat_search)                # [T, 1] int32 BMU on the frozen weights
+            if small:
+                # [T] int32 BMU on the frozen weights, scipy's arithmetic, first minimum
+                _lib.check(lib.gmd_bmu_small_f64(_ptr(flat_search), rows * cols, _ptr(q), cut_off, dim, _ptr(loc), 0,
+                                                 _ptr(flag), _stream_ptr()))
+                if i == 1:
+                    bad = bool(flag.item())                  # inputs were checked on the host; once is enough
+            else:
+                loc, _ = pipe.run(q, flat_search)            # [T, 1] int32 BMU on the frozen weights
             stamp_d = torch.from_numpy(stamp).to(dev)
             _lib.check(lib.gmd_som_update_f64(_ptr(w), _ptr(w), rows, cols, dim, _ptr(x), n, _ptr(idx_d), _ptr(loc),
                                               cut_off, _ptr(stamp_d), sr, _ptr(mask_d), _stream_ptr()))
             if mask is not None and not mask_any:
                 pass                                          # nothing moved, flat_nodes not refreshed either
         out = w.cpu().numpy()
-        if pipe is not None and pipe.saw_nonfinite():
+        if bad or (pipe is not None and pipe.saw_nonfinite()):
             raise FloatingPointError("non-finite value reached the BMU search")
     return out

@@ -344,6 +344,27 @@ GMD_API int gmd_median_dist_f64(const double* A, int64_t mA, const double* B, in
 GMD_API int gmd_median_batch_f64(const double* X, int64_t N, int D, int metric, const int32_t* rows,
                          const int32_t* jobs, int n_jobs, double* out, void* stream);
 
+/* Host-layer helpers: flag[0] <- 1 if any of the n values is NaN / Inf (the reference runs under
+ * np.seterr(all='raise'), torusMesh.py:57: a non-finite profile is a FloatingPointError there);
+ * indptr[0] = 0, indptr[i + 1] = counts[0] + ... + counts[i] (the CSR row pointer between
+ * gmd_radius_count_f64 and gmd_radius_fill_f64).                                        */
+GMD_API int gmd_nonfinite_f64(const double* X, int64_t n, int32_t* flag, void* stream);
+GMD_API int gmd_zero_async(void* p, size_t bytes, void* stream);
+/* argmin(cdist(nodes, [X_i])) for a FEW vectors (N <= 65535), straight in float64 with scipy's arithmetic,
+ * one block per vector, first minimum: the per-contig bestMatch call (torusMesh.py:123-130) and the BMUs
+ * of one SOM.train iteration (som.py:348-353) without tile staging -- one launch.  flag (nullable) <- 1 if
+ * a distance is NaN / Inf.                                                                */
+GMD_API int gmd_bmu_small_f64(const double* nodes, int64_t M, const double* X, int64_t N, int D, int32_t* out_idx,
+                      double* out_dist, int32_t* flag, void* stream);
+/* The k nearest candidates of a FEW query rows against at most gmd_knn_small_max_candidates() rows, straight
+ * in float64 (one block per query, distances in shared memory, k rounds of selection): the per-bin
+ * KDTree(data).query(x, k=6) of findMergeGroups (refine.py:653-665) in one launch.  Ascending (distance,
+ * index); out_idx [Nq, k], out_dist [Nq, k].                                               */
+GMD_API int gmd_knn_small_max_candidates(void);
+GMD_API int gmd_knn_small_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
+                      int32_t* out_idx, double* out_dist, int32_t* flag, void* stream);
+GMD_API int gmd_indptr_from_counts_i64(const int64_t* counts, int64_t n, int64_t* indptr, void* stream);
+
 /* One iteration of SOM.train's weight update (som.py:328-384) for the T training vectors
  * X[index[t]] whose best-matching units on the frozen weights are loc[t] (flat node index,
  * row = loc / cols): every node gathers  -(w - x) * stamp  over the 3 x 3 torus tiling in the

@@ -308,7 +308,10 @@ def som_train(nodes: np.ndarray, train_vectors: np.ndarray, weights=None, iterat
             r0, r1 = rows + row - sr, rows + row + sr + 1
             c0, c1 = cols + col - sr, cols + col + sr + 1
             patch = -1 * (sheet[r0:r1, c0:c1] - tv[j])
-            patch *= stamp[:, :, None]
+            # som.py:360-363 scales dimensions 0..3 by name: a mesh of fewer than four dimensions raises
+            # IndexError there, dimensions past the fourth keep the whole difference
+            for dd in range(4):
+                patch[:, :, dd] *= stamp
             delta[r0:r1, c0:c1] += patch
         delta[:, cols:2 * cols] += delta[:, 0:cols]
         delta[:, cols:2 * cols] += delta[:, 2 * cols:3 * cols]
