@@ -45,6 +45,10 @@
 namespace gmd_tc {
 
 constexpr int LCAP = 1024;                     // tiles per round
+// Parked hits per selection thread (template parameter TQP): 16 where the shared memory allows, else 12.  Deeper
+// queues even out the lanes of a warp (a drain lasts as long as its fullest queue: 9 slots 7.7 ms, 12 5.7 ms,
+// 16 5.0 ms for the 1M x 30 scan), but a threshold is only refreshed when its queue is folded and a stale one
+// parks more: queues of 48 in an L2-resident scratch took 7.9 ms.
 constexpr int WMAX = 32;                       // tiles of the opening window
 constexpr int META_MAX = GMD_MAX_D + 4;        // centroid + radius of the query tile in shared memory
 constexpr float LB_REL = 1.0f / 16384.0f;      // relative slack on every FP32-evaluated term of a bound
@@ -85,7 +89,7 @@ __device__ __forceinline__ float ball_bound(float d2, float rsum) {
     return sqrtf(d2) * (1.0f - LB_REL) - rsum * (1.0f + LB_REL) - LB_ABS;
 }
 
-template <int NKB, int QT>
+template <int NKB, int QT, int TQP>
 __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(const PruneParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr int PTHREADS = prune_threads(QT);
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int nkb = NKB;
     constexpr int TILE_B = tile_bytes(nkb);
-    const int ns = p.ns, kk = p.kk, KQ = heap2_slots(kk), D = p.D;
+    const int ns = p.ns, kk = p.kk, KQ = heap8_slots(kk), D = p.D;
     const int nw = (p.ntiles_c + 31) >> 5;
     unsigned char* Aimg = base;                            // QT query tiles
     unsigned char* Bst = base + QT * TILE_B;
@@ -115,8 +119,8 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
     uint64_t* tempty = bars + 2 * NS_MAX + NACC;
     uint64_t* qbar = bars + 2 * NS_MAX + 2 * NACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS_MAX + 2 * NACC + 2);
-    uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NS_MAX + 2 * NACC + 4);   // [QT][TQ][TM]
-    float* hvals = reinterpret_cast<float*>(queues + QT * TQ * TM);                // [QT][TM][KQ] values of the top-kk sets
+    uint2* queues = reinterpret_cast<uint2*>(bars + 2 * NS_MAX + 2 * NACC + 4);   // [QT][TQP][TM]
+    float* hvals = reinterpret_cast<float*>(queues + QT * TQP * TM);                // [QT][TM][KQ] values of the top-kk sets
     uint32_t* hidx = reinterpret_cast<uint32_t*>(hvals + (size_t)QT * TM * KQ);    // [QT][TM][KQ] their candidates
     uint32_t* tlist = hidx + (size_t)QT * TM * KQ;                                 // [LCAP] tiles of the round / groups
     float* mq = reinterpret_cast<float*>(tlist + LCAP);                        // [QT][META_MAX] centroid, radius
@@ -128,6 +132,16 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr unsigned FULLW = 0xFFFFFFFFu;
     const float INF = __int_as_float(0x7f800000);
+#ifdef GMD_TC_PROBES
+    // developer build only: SM cycles of thread 0 (a selection thread) per phase, summed over the CTAs in
+    // counters[4..]: wait for an accumulator, read it, trees + vote, parking, drains; drain calls; entries folded
+    long long pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROBE_T(var) const long long var = clock64()
+#define PROBE_ADD(i, v) pk[i] += (v)
+#else
+#define PROBE_T(var)
+#define PROBE_ADD(i, v)
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < ns; ++s) {
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
     const int row = quarter * 32 + lane;                   // only meaningful for the selection warps
     float* hv = hvals + ((size_t)qsel * TM + row) * KQ;
     uint32_t* hx = hidx + ((size_t)qsel * TM + row) * KQ;
-    uint2* myq = queues + (size_t)qsel * TQ * TM + row;
+    uint2* myq = queues + (size_t)qsel * TQP * TM + row;   // slot r at myq[r * TM]: conflict-free
     int qcnt = 0, hn = 0;                                  // parked hits; entries in the top-kk set
     float thr = INF;                                       // threshold (s units)
     float uthr = -INF;                                     // the same in u = -s / 2 units
@@ -393,11 +407,15 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
                 qnv = reinterpret_cast<const float*>(Aimg + (size_t)qsel * TILE_B + (size_t)nkb * KB_B)[row];
             }
             auto drain = [&]() {
-                const Drain2 ds = drain_fill2(hv, hx, kk, hn, thr, myq, qcnt);
+                PROBE_T(d0);
+                PROBE_ADD(5, 1);
+                PROBE_ADD(6, qcnt);
+                const Drain2 ds = drain_fill8(hv, hx, kk, hn, thr, myq, TM, qcnt);
                 thr = ds.thr;
                 hn = ds.hn;
                 qcnt = 0;
                 uthr = -0.5f * thr;
+                PROBE_ADD(4, clock64() - d0);
             };
             // 64 columns at a time (one tcgen05.ld.x64): maxima of the 8 groups of 8 columns as shallow trees,
             // ONE vote, then 8 values at a time: park what beats the (possibly stale) threshold, drain all the
@@ -418,6 +436,11 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
                 const float cm = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])),
                                        fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
                 if (!__any_sync(FULLW, cm > uthr)) return;
+                PROBE_T(p0);
+                PROBE_ADD(3, -(long long)0);
+#ifdef GMD_TC_PROBES
+                const long long dr0 = pk[4];
+#endif
                 unsigned mine = 0;
 #pragma unroll
                 for (int g = 0; g < 8; ++g) mine |= (gm[g] > uthr) ? (1u << g) : 0u;
@@ -434,27 +457,39 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
                                     ++qcnt;
                                 }
                             }
-                            if (__any_sync(FULLW, qcnt > TQ - 8)) drain();
+                            if (__any_sync(FULLW, qcnt > TQP - 8)) drain();
                         }
                     }
                 };
                 park(r0, hot & 15u, c0);
                 park(r1, hot >> 4, c0 + 32);
+#ifdef GMD_TC_PROBES
+                pk[3] += (clock64() - p0) - (pk[4] - dr0);
+#endif
             };
             for (long long t = tbase; t < tbase + cnt; ++t) {
                 const int a = (int)(t % NA);
+                PROBE_T(s0);
                 mbar_wait(&tdone[a], (uint32_t)(t / NA) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
+                PROBE_T(s1);
+                PROBE_ADD(0, s1 - s0);
                 const uint32_t cbase = tlist[t - tbase] * TM;
                 const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((a * QT + qsel) * TM);
                 uint32_t r0[32], r1[32];
                 tmem_ld64_sync(trow, r0, r1);
+                PROBE_T(s2);
+                PROBE_ADD(1, s2 - s1);
                 half_row(r0, r1, cbase);
+                PROBE_T(s3);
                 tmem_ld64_sync(trow + 64, r0, r1);
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[a]);
+                PROBE_T(s4);
+                PROBE_ADD(1, s4 - s3);
                 half_row(r0, r1, cbase + 64);
+                PROBE_ADD(2, (clock64() - s4) + (s3 - s2));       // trees + parking + drains of both halves
             }
             // end of the round: fold what is parked, publish the warp's largest threshold DISTANCE (scaled units;
             // padding rows do not count).  Non-negative floats (and +inf) order like their bit patterns.
@@ -486,8 +521,8 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int x = x0 + j;
-                const uint32_t li = x < hn ? hx[x + 3] : GMD_EMPTY_IDX;
-                vv[j] = x < hn ? hv[x + 3] : INF;
+                const uint32_t li = x < hn ? hx[x + 7] : GMD_EMPTY_IDX;
+                vv[j] = x < hn ? hv[x + 7] : INF;
                 oi[j] = GMD_EMPTY_IDX;
                 if (li != GMD_EMPTY_IDX && (long long)li < p.Nc_pos) oi[j] = p.perm_c ? p.perm_c[li] : li;
             }
@@ -508,6 +543,9 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
         if (p.counters) {
             atomicAdd(&p.counters[0], (unsigned long long)visited_tiles);
             atomicAdd(&p.counters[1], 1ull);
+#ifdef GMD_TC_PROBES
+            for (int x = 0; x < 8; ++x) atomicAdd(&p.counters[4 + x], (unsigned long long)pk[x]);
+#endif
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -532,9 +570,9 @@ __global__ void __launch_bounds__(256) group_meta_kernel(const float* __restrict
 
 namespace {
 // shared memory of one CTA (qt query tiles) without the ring and the two bitmasks
-size_t prune_fixed_smem(int nkb, int kk, int qt) {
+size_t prune_fixed_smem(int nkb, int kk, int qt, int tqp = 12) {
     using namespace gmd_tc;
-    return 1024 + (size_t)qt * tile_bytes(nkb) + 512 + (size_t)qt * TQ * TM * 8 + (size_t)qt * TM * heap2_slots(kk) * 8 +
+    return 1024 + (size_t)qt * tile_bytes(nkb) + 512 + (size_t)qt * tqp * TM * 8 + (size_t)qt * TM * heap8_slots(kk) * 8 +
            (size_t)LCAP * 4 + (size_t)qt * META_MAX * 4 + 128;
 }
 }  // namespace
@@ -583,7 +621,9 @@ extern "C" int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const v
     // two query tiles per CTA when there is one K block and both fit (GMD_TC_QT=1: developer switch)
     int qt = (nkb == 1 && prune_fixed_smem(nkb, kk, 2) + (size_t)nw * 8 + 2 * (size_t)KB_B <= GMD_SMEM_LIMIT) ? 2 : 1;
     if (const char* env = getenv("GMD_TC_QT")) qt = std::min(qt, std::max(1, atoi(env)));
-    const size_t fixed = prune_fixed_smem(nkb, kk, qt) + (size_t)nw * 8;
+    // queues of 16 where they fit beside at least nkb + 1 ring stages
+    const int tqp = prune_fixed_smem(nkb, kk, qt, 16) + (size_t)nw * 8 + (size_t)std::max(2, nkb + 1) * KB_B <= GMD_SMEM_LIMIT ? 16 : 12;
+    const size_t fixed = prune_fixed_smem(nkb, kk, qt, tqp) + (size_t)nw * 8;
     const int na = qt == 2 ? 2 : NACC;
     const int ns = (int)std::min<size_t>(std::min(NS_MAX, na * nkb), (GMD_SMEM_LIMIT - fixed) / KB_B);
     GMD_REQUIRE(ns >= 2, GMD_ERR_UNSUPPORTED, "scan_tc_prune: D=%d kk=%d needs more than 227 KB of shared memory", D, kk);
@@ -624,11 +664,14 @@ extern "C" int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const v
     };
     int rc;
     switch (nkb) {
-        case 1: rc = qt == 2 ? launch(scan_tc_prune_kernel<1, 2>, 2) : launch(scan_tc_prune_kernel<1, 1>, 1); break;
-        case 2: rc = launch(scan_tc_prune_kernel<2, 1>, 1); break;
-        case 3: rc = launch(scan_tc_prune_kernel<3, 1>, 1); break;
-        case 4: rc = launch(scan_tc_prune_kernel<4, 1>, 1); break;
-        default: rc = launch(scan_tc_prune_kernel<5, 1>, 1); break;
+        case 1:
+            rc = qt == 2 ? (tqp == 16 ? launch(scan_tc_prune_kernel<1, 2, 16>, 2) : launch(scan_tc_prune_kernel<1, 2, 12>, 2))
+                         : (tqp == 16 ? launch(scan_tc_prune_kernel<1, 1, 16>, 1) : launch(scan_tc_prune_kernel<1, 1, 12>, 1));
+            break;
+        case 2: rc = tqp == 16 ? launch(scan_tc_prune_kernel<2, 1, 16>, 1) : launch(scan_tc_prune_kernel<2, 1, 12>, 1); break;
+        case 3: rc = tqp == 16 ? launch(scan_tc_prune_kernel<3, 1, 16>, 1) : launch(scan_tc_prune_kernel<3, 1, 12>, 1); break;
+        case 4: rc = tqp == 16 ? launch(scan_tc_prune_kernel<4, 1, 16>, 1) : launch(scan_tc_prune_kernel<4, 1, 12>, 1); break;
+        default: rc = tqp == 16 ? launch(scan_tc_prune_kernel<5, 1, 16>, 1) : launch(scan_tc_prune_kernel<5, 1, 12>, 1); break;
     }
     if (rc != GMD_OK) return rc;
     GMD_CUDA_CHECK(cudaGetLastError());

@@ -200,33 +200,56 @@ static __device__ GMD_DRAIN_INLINE DrainState drain_fill(uint64_t* h, int kk, in
     return st;
 }
 
-// ---- split top-kk set of the pruned scan: values and indices in two arrays, a 4-ary MAX-heap ordered by the
-// VALUE alone.  Node n lives in slot n + 3 of a 16-byte aligned block, so that the four children of node i
-// (nodes 4i + 1 .. 4i + 4) are slots 4i + 4 .. 4i + 7: one 128-bit load; slots past the last node hold -inf
-// and are never the largest child.  A level of a sift is then one LDS.128, a handful of compares and three
-// 32-bit accesses instead of four 64-bit loads and 64-bit compares / selects.  Ordering by value only is
-// enough here: which of several EQUAL values stays is immaterial to the proposals' guarantee (everything
-// not proposed has a value >= tau), and a tie at the k-th place fails the certificate's strict
-// inequality and goes to the exact pass, which applies the lowest-index rule.
-__host__ __device__ constexpr int heap2_slots(int kk) { return ((kk + 3) + 3) / 4 * 4; }
+// ---- split top-kk set of the pruned scan: values and indices in two arrays, an 8-ary MAX-heap ordered by the
+// VALUE alone.  Node n lives in slot n + 7 of a 16-byte aligned block, so that the eight children of node i
+// (nodes 8i + 1 .. 8i + 8) are slots 8i + 8 .. 8i + 15: two 128-bit loads; slots past the last node hold -inf
+// and are never the largest child.  With kk <= 72 the heap has two levels below the root, and a drain keeps
+// the root and the whole first level in REGISTERS while it folds its entries: an insertion is then a max-of-8
+// in registers, at most ONE dependent shared-memory round trip (the chosen child's eight children) and two
+// 32-bit stores -- the 4-ary u64 heap of scan_tc.cu walks three levels of dependent loads, 64-bit compares and
+// selects per insertion, which is what bounds a scan that is shown little but its queries' own neighbourhood.
+// Ordering by value only is enough here: which of several EQUAL values stays is immaterial to the proposals'
+// guarantee (everything not proposed has a value >= tau), and a tie at the k-th place fails the certificate's
+// strict inequality and goes to the exact pass, which applies the lowest-index rule.
+__host__ __device__ constexpr int heap8_slots(int kk) {
+    int s = (kk + 15 + 3) / 4 * 4;      // node kk - 1 in slot kk + 6; a child block may run 8 slots past it
+    if ((s / 4) % 2 == 0) s += 4;       // an odd number of 16-byte units per thread: conflict-free quarter-warps
+    return s;
+}
 
-__device__ __forceinline__ void heap2_sift(float* hv, uint32_t* hx, int kk, int pos, float v, uint32_t idx) {
+__device__ __forceinline__ void argmax8(const float (&c)[8], float& m, int& at) {
+    const bool b01 = c[1] > c[0], b23 = c[3] > c[2], b45 = c[5] > c[4], b67 = c[7] > c[6];
+    const float m01 = b01 ? c[1] : c[0], m23 = b23 ? c[3] : c[2], m45 = b45 ? c[5] : c[4], m67 = b67 ? c[7] : c[6];
+    const int i01 = b01 ? 1 : 0, i23 = b23 ? 3 : 2, i45 = b45 ? 5 : 4, i67 = b67 ? 7 : 6;
+    const bool bl = m23 > m01, bh = m67 > m45;
+    const float ml = bl ? m23 : m01, mh = bh ? m67 : m45;
+    const int il = bl ? i23 : i01, ih = bh ? i67 : i45;
+    const bool bt = mh > ml;
+    m = bt ? mh : ml;
+    at = bt ? ih : il;
+}
+__device__ __forceinline__ void load8(const float* p, float (&c)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
+}
+
+// sift the pair (v, idx) down from node pos, everything in shared memory (building the heap)
+__device__ __forceinline__ void heap8_sift(float* hv, uint32_t* hx, int kk, int pos, float v, uint32_t idx) {
     while (true) {
-        const int c = 4 * pos + 1;
+        const int c = 8 * pos + 1;
         if (c >= kk) break;
-        const float4 cv = *reinterpret_cast<const float4*>(hv + c + 3);
-        const bool b01 = cv.y > cv.x, b23 = cv.w > cv.z;
-        const float m01 = b01 ? cv.y : cv.x, m23 = b23 ? cv.w : cv.z;
-        const bool hi = m23 > m01;
-        const float m = hi ? m23 : m01;
+        float cv[8];
+        load8(hv + c + 7, cv);
+        float m;
+        int at;
+        argmax8(cv, m, at);
         if (m <= v) break;
-        const int ch = c + (hi ? 2 + (int)b23 : (int)b01);
-        hv[pos + 3] = m;
-        hx[pos + 3] = hx[ch + 3];
-        pos = ch;
+        hv[pos + 7] = m;
+        hx[pos + 7] = hx[c + at + 7];
+        pos = c + at;
     }
-    hv[pos + 3] = v;
-    hx[pos + 3] = idx;
+    hv[pos + 7] = v;
+    hx[pos + 7] = idx;
 }
 
 struct Drain2 {
@@ -235,22 +258,76 @@ struct Drain2 {
 };
 // Fold a thread's parked hits (q[r * TM] = (index, value bits)) into its set.  While the set holds fewer
 // than kk entries they are appended; the kk-th one turns the array into a heap (one bottom-up pass).
-static __device__ __noinline__ Drain2 drain_fill2(float* hv, uint32_t* hx, int kk, int hn, float thr, const uint2* q,
-                                                  int n) {
-    for (int r = 0; r < n; ++r) {
-        const uint2 e = q[r * TM];
-        const float v = __uint_as_float(e.y);
-        if (hn < kk) {
-            hv[hn + 3] = v;
-            hx[hn + 3] = e.x;
-            if (++hn == kk) {
-                for (int pos = (kk - 2) / 4; pos >= 0; --pos) heap2_sift(hv, hx, kk, pos, hv[pos + 3], hx[pos + 3]);
-                thr = hv[3];
-            }
-        } else if (v < thr) {
-            heap2_sift(hv, hx, kk, 0, v, e.x);
-            thr = hv[3];
+// thr: the threshold = the root's value once the set is full (+inf before).  kk <= 72.
+static __device__ __noinline__ Drain2 drain_fill8(float* hv, uint32_t* hx, int kk, int hn, float thr, const uint2* q,
+                                                  int stride, int n) {
+    int r = 0;
+    for (; r < n && hn < kk; ++r) {
+        const uint2 e = q[r * stride];
+        hv[hn + 7] = __uint_as_float(e.y);
+        hx[hn + 7] = e.x;
+        if (++hn == kk) {
+            for (int pos = (kk - 2) / 8; pos >= 0; --pos) heap8_sift(hv, hx, kk, pos, hv[pos + 7], hx[pos + 7]);
+            thr = hv[7];
         }
+    }
+    if (r < n) {
+        // the heap is live: root and first level in registers for the rest of the drain
+        float rv = hv[7], c[8];
+        uint32_t rx = hx[7], cx[8];
+        load8(hv + 8, c);
+        {
+            const uint4 a = *reinterpret_cast<const uint4*>(hx + 8), b = *reinterpret_cast<const uint4*>(hx + 12);
+            cx[0] = a.x, cx[1] = a.y, cx[2] = a.z, cx[3] = a.w, cx[4] = b.x, cx[5] = b.y, cx[6] = b.z, cx[7] = b.w;
+        }
+        uint2 e = q[r * stride];
+        for (; r < n; ++r) {
+            const uint2 cur = e;
+            if (r + 1 < n) e = q[(r + 1) * stride];         // the next entry travels while this one is folded
+            const float v = __uint_as_float(cur.y);
+            if (!(v < rv)) continue;
+            float m;
+            int ch;
+            argmax8(c, m, ch);
+            if (m <= v) {                                   // larger than every child: it is the new root
+                rv = v;
+                rx = cur.x;
+                continue;
+            }
+            uint32_t mx = cx[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) mx = ch == i ? cx[i] : mx;
+            rv = m;                                         // the largest child moves up
+            rx = mx;
+            float nv = v;                                   // what takes that child's place
+            uint32_t nx = cur.x;
+            const int first = 8 * (ch + 1) + 1;             // its own children: nodes first .. first + 7
+            if (first < kk) {
+                float g[8];
+                load8(hv + first + 7, g);
+                float gm;
+                int gi;
+                argmax8(g, gm, gi);
+                if (gm > v) {
+                    nv = gm;
+                    nx = hx[first + 7 + gi];
+                    hv[first + 7 + gi] = v;
+                    hx[first + 7 + gi] = cur.x;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                c[i] = ch == i ? nv : c[i];
+                cx[i] = ch == i ? nx : cx[i];
+            }
+        }
+        hv[7] = rv;
+        hx[7] = rx;
+        *reinterpret_cast<float4*>(hv + 8) = make_float4(c[0], c[1], c[2], c[3]);
+        *reinterpret_cast<float4*>(hv + 12) = make_float4(c[4], c[5], c[6], c[7]);
+        *reinterpret_cast<uint4*>(hx + 8) = make_uint4(cx[0], cx[1], cx[2], cx[3]);
+        *reinterpret_cast<uint4*>(hx + 12) = make_uint4(cx[4], cx[5], cx[6], cx[7]);
+        thr = rv;
     }
     Drain2 st;
     st.thr = thr;

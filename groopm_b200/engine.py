@@ -289,7 +289,10 @@ class KnnPipeline:
         ntc = -(-g.npos_c // 128)
         return {"tiles_visited": visited, "query_tiles": ctas, "groups": g.ngroups,
                 "candidate_tiles": ntc, "groups_surviving_per_query_tile": groups / max(ctas, 1),
-                "visited_fraction": visited / max(1, ctas * ntc)}
+                "visited_fraction": visited / max(1, ctas * ntc),
+                # only a -DGMD_TC_PROBES build fills these: thread 0's SM cycles per CTA and phase
+                "probes": {n: c[4 + i] / max(ctas, 1) for i, n in enumerate(
+                    ("wait", "load", "select", "park", "drain", "drains", "entries", "-"))}}
 
     # launches of the engine's own kernels in one run() (col_mean, prep x1/2, scan, refine, exact)
     @property
