@@ -434,27 +434,15 @@ def engine_arm(args):
         pipe = engine.KnnPipeline(max(n_local, 1), n, d, k, metric, same=(world == 1), device=dev, **kw)
         out_idx_host = torch.empty((n_local, k), dtype=torch.int32).pin_memory()
         out_dist_host = torch.empty((n_local, k), dtype=torch.float64).pin_memory()
-        scan_ev = []
+        scan_ev = pipe.scan_events = []
 
         def step(src_dev):
             """One pass of the hot path for this rank's rows; returns device (idx, dist)."""
             if world == 1:
-                q = c = src_dev
-            else:
-                c = gdist.gather_rows(src_dev, n)
-                q = c[r0:r1]                                  # a run of the candidates' rows: the staging shares the keys
-            pipe.reset()
-            pipe.col_mean(c)
-            pipe.prep_candidates(c)
-            pipe.prep_queries(q)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            pipe.scan()
-            e1.record()
-            scan_ev.append((e0, e1))
-            pipe.refine(q, c)
-            pipe.exact_rows(q, c)
-            return pipe.out_idx, pipe.out_dist
+                return pipe.run(src_dev, src_dev)
+            # all-gather of the rows, leaders, nearest-leader search of this rank's rows + all-gather of the keys,
+            # the rest of the staging, scan, re-rank: dist.sharded_knn
+            return gdist.sharded_knn(src_dev, n, k, metric, pipeline=pipe)
 
         def e2e_step():
             if world == 1:
@@ -463,7 +451,7 @@ def engine_arm(args):
                 return engine.knn(x_host.numpy(), None, k=k, metric=metric, prune=prune,
                                   **({"form": _lib.FORM_TC, "order": True} if prune is False else {}))
             xd = x_host.to(dev, non_blocking=True)           # H2D of this rank's profiles
-            idx, dist_ = gdist.sharded_knn(xd, n, k, metric, pipeline=pipe)
+            idx, dist_ = step(xd)
             out_idx_host.copy_(idx[:n_local], non_blocking=True)   # D2H of this rank's result
             out_dist_host.copy_(dist_[:n_local], non_blocking=True)
             torch.cuda.current_stream().synchronize()

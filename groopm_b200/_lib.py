@@ -61,6 +61,10 @@ SIGNATURES = {
     "gmd_tc_grouped_tiles_bytes": (_sz, [_i64, _i64, _int]),
     "gmd_tc_grouped_workspace_bytes": (_sz, [_i64, _i64, _int]),
     "gmd_tc_stage_grouped_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "gmd_tc_grouped_leaders_f64": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _sz, C.POINTER(C.c_int32),
+                                          C.POINTER(_vp), _vp]),
+    "gmd_tc_stage_grouped_ext_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.c_int32,
+                                            _vp, _vp, _vp, _vp]),
     "gmd_scan_tc_prune_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp,
                                      _int, _vp, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "gmd_scan_tc_grouped_f32": (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

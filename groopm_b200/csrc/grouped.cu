@@ -137,30 +137,58 @@ extern "C" size_t gmd_tc_grouped_workspace_bytes(int64_t Nq, int64_t Nc, int D) 
     return carve(nullptr, Nq, Nc, D, 0).bytes;
 }
 
-extern "C" int gmd_tc_stage_grouped_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
-                                        const double* center, const float* stats_c, const float* stats_q, void* qtiles,
-                                        void* ctiles, void* workspace, size_t workspace_bytes, gmd_grouped* out,
-                                        void* stream) {
+// Row-sharded callers split the staging in two: gmd_tc_grouped_leaders_f64 picks the leaders (identical on
+// every rank: the kernels are deterministic) and hands back their rows; the caller finds the nearest leader of
+// ITS rows only (this library's k = 1 pipeline), all-gathers (index, distance) of all rows and passes them to
+// gmd_tc_stage_grouped_f64 as nearest_idx / nearest_dist -- the nearest-leader pass over every candidate row is
+// then the one stage of the staging that is not repeated on every GPU.
+extern "C" int gmd_tc_grouped_leaders_f64(const double* C, int64_t Nq, int64_t Nc, int D, const double* center,
+                                          void* workspace, size_t workspace_bytes, int32_t* nlead_host,
+                                          const double** lead_rows_dev, void* stream) {
+    GMD_REQUIRE(C && center && workspace && nlead_host && lead_rows_dev && Nq > 0 && Nc > 0 && D >= 1 && D <= GMD_MAX_D,
+                GMD_ERR_BAD_ARG, "grouped_leaders: bad arguments");
+    Layout L = carve(workspace, Nq, Nc, D, 1);
+    GMD_REQUIRE(L.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "grouped_leaders: workspace %zu B < required %zu B",
+                workspace_bytes, L.bytes);
+    *lead_rows_dev = L.lead_rows;
+    return gmd_group_leaders_f64(C, Nc, D, center, L.ns, L.cap, 2.0f, L.Lt, L.lead_row, L.lead_rows, L.info, L.lead_ws,
+                                 L.lead_ws_bytes, nlead_host, stream);
+}
+
+static int stage_grouped(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, const double* center,
+                         const float* stats_c, const float* stats_q, void* qtiles, void* ctiles, void* workspace,
+                         size_t workspace_bytes, int32_t nlead_given, const int32_t* nearest_idx,
+                         const double* nearest_dist, gmd_grouped* out, void* stream) {
     GMD_REQUIRE(Q && C && center && stats_c && stats_q && qtiles && ctiles && workspace && out, GMD_ERR_BAD_ARG,
                 "stage_grouped: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1 && D <= GMD_MAX_D, GMD_ERR_BAD_ARG, "stage_grouped: bad sizes");
     int64_t q_row0;
-    const int relation = relation_of(Q, Nq, C, Nc, D, &q_row0);
+    int relation = relation_of(Q, Nq, C, Nc, D, &q_row0);
+    const bool external = nearest_idx != nullptr;
+    // (the split staging lays the workspace out for "queries are a run of the candidates' rows")
+    GMD_REQUIRE(!external || (relation == 1 && nearest_dist && nlead_given >= 1), GMD_ERR_BAD_ARG,
+                "stage_grouped: an external nearest-leader result needs queries that are a run of the candidates' rows");
     Layout L = carve(workspace, Nq, Nc, D, relation);
     GMD_REQUIRE(L.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "stage_grouped: workspace %zu B < required %zu B",
                 workspace_bytes, L.bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const int TM = gmd_tc::TM;
     int rc;
-    int32_t nlead = 0;
-    if ((rc = gmd_group_leaders_f64(C, Nc, D, center, L.ns, L.cap, 2.0f, L.Lt, L.lead_row, L.lead_rows, L.info, L.lead_ws,
-                                    L.lead_ws_bytes, &nlead, stream)) != GMD_OK)
-        return rc;
-    // nearest leader (+ exact float64 distance to it) of every candidate row, and of the queries if they
-    // are rows of their own
-    if ((rc = gmd_knn_f64(C, Nc, L.lead_rows, nlead, D, 1, GMD_L2, GMD_FORM_AUTO, L.idx_c, L.dist_c, L.knn_ws,
-                          L.knn_ws_bytes, nullptr, stream)) != GMD_OK)
-        return rc;
+    int32_t nlead = nlead_given;
+    if (external) {
+        GMD_REQUIRE(nlead <= L.cap, GMD_ERR_BAD_ARG, "stage_grouped: %d leaders exceed the capacity %d", nlead, L.cap);
+        GMD_CUDA_CHECK(cudaMemcpyAsync(L.idx_c, nearest_idx, (size_t)Nc * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        GMD_CUDA_CHECK(cudaMemcpyAsync(L.dist_c, nearest_dist, (size_t)Nc * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        if ((rc = gmd_group_leaders_f64(C, Nc, D, center, L.ns, L.cap, 2.0f, L.Lt, L.lead_row, L.lead_rows, L.info,
+                                        L.lead_ws, L.lead_ws_bytes, &nlead, stream)) != GMD_OK)
+            return rc;
+        // nearest leader (+ exact float64 distance to it) of every candidate row, and of the queries if they
+        // are rows of their own
+        if ((rc = gmd_knn_f64(C, Nc, L.lead_rows, nlead, D, 1, GMD_L2, GMD_FORM_AUTO, L.idx_c, L.dist_c, L.knn_ws,
+                              L.knn_ws_bytes, nullptr, stream)) != GMD_OK)
+            return rc;
+    }
     const int64_t npos_c = gmd_group_positions(Nc, nlead, TM);
     if ((rc = gmd_group_order(L.idx_c, L.dist_c, Nc, nlead, L.info, TM, L.key_c, L.grad, L.perm_c, npos_c, L.gstart_c,
                               L.tgroup_c, L.order_ws, L.order_ws_bytes, stream)) != GMD_OK)
@@ -212,6 +240,24 @@ extern "C" int gmd_tc_stage_grouped_f64(const double* Q, int64_t Nq, const doubl
     out->tmeta_c = L.tmeta_c;
     out->counters = L.counters;
     return GMD_OK;
+}
+
+extern "C" int gmd_tc_stage_grouped_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                                        const double* center, const float* stats_c, const float* stats_q, void* qtiles,
+                                        void* ctiles, void* workspace, size_t workspace_bytes, gmd_grouped* out,
+                                        void* stream) {
+    return stage_grouped(Q, Nq, C, Nc, D, center, stats_c, stats_q, qtiles, ctiles, workspace, workspace_bytes, 0, nullptr,
+                         nullptr, out, stream);
+}
+
+extern "C" int gmd_tc_stage_grouped_ext_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                                            const double* center, const float* stats_c, const float* stats_q,
+                                            void* qtiles, void* ctiles, void* workspace, size_t workspace_bytes,
+                                            int32_t nlead, const int32_t* nearest_idx, const double* nearest_dist,
+                                            gmd_grouped* out, void* stream) {
+    GMD_REQUIRE(nearest_idx && nearest_dist, GMD_ERR_BAD_ARG, "stage_grouped_ext: null nearest-leader arrays");
+    return stage_grouped(Q, Nq, C, Nc, D, center, stats_c, stats_q, qtiles, ctiles, workspace, workspace_bytes, nlead,
+                         nearest_idx, nearest_dist, out, stream);
 }
 
 extern "C" int gmd_scan_tc_grouped_f32(const void* qtiles, const void* ctiles, int D, int kk, int64_t c_index_offset,

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict_
     for (int j = threadIdx.x; j < ns; j += blockDim.x) {
         const float* b = S + (size_t)j * D;
         float d2 = 0.0f;
+#pragma unroll 6
         for (int d = 0; d < D; ++d) {
             const float t = a[d] - b[d];
             d2 = fmaf(t, t, d2);
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict_
 // (compacted by the block first), tested against the leaders from index info[2] on (pass A's count).
 __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __restrict__ S, int ns, int n1,
                                                              long long stride, int D, const float* __restrict__ nn,
-                                                             int nprobe, float rfac, int cap, int B,
+                                                             int nprobe, float rfac, int cap, int B, int capS,
                                                              const unsigned char* __restrict__ flags,
                                                              int32_t* __restrict__ list, float* __restrict__ L,
                                                              int32_t* __restrict__ lead_row,
@@ -130,6 +131,9 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
     int* cov = reinterpret_cast<int*>(sT + (size_t)D * B);   // [B]
     int* fresh = cov + B;                              // [B] batch members that became leaders (batch index)
     int* sidx = fresh + B;                             // [B] sample index of a batch member
+    // the first capS leaders are mirrored in shared memory: the global rows are written while the kernel runs,
+    // and a freshly written line is an L2 round trip for every reader
+    float* Ls = reinterpret_cast<float*>(sidx + B);    // [capS][D]
     __shared__ float vals[LEAD_PROBES];
     __shared__ int part[LEAD_THREADS];
     __shared__ int nlead_s, nlist_s;
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
         __syncthreads();
         nlist = nlist_s;
         j0 = info[0];
+        for (int e = tid; e < min(j0, capS) * D; e += LEAD_THREADS) Ls[e] = L[e];   // pass A's leaders
     }
     __syncthreads();
     const float R2 = R2_s;
@@ -202,8 +207,9 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
         if (b < nb) {
             bool hit = false;
             for (int j = j0 + share; j < nl && !hit; j += shares) {
-                const float* l = L + (size_t)j * D;    // the same row for the whole warp: broadcast
+                const float* l = j < capS ? Ls + (size_t)j * D : L + (size_t)j * D;   // one row for the whole warp: broadcast
                 float d2 = 0.0f;
+#pragma unroll 6
                 for (int d = 0; d < D; ++d) {
                     const float t = sT[(size_t)d * B + b] - l[d];
                     d2 = fmaf(t, t, d2);
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
                 for (int x = lane; x < nf; x += 32) {
                     const int o = fresh[x];
                     float d2 = 0.0f;
+#pragma unroll 6
                     for (int d = 0; d < D; ++d) {
                         const float t = sT[(size_t)d * B + r] - sT[(size_t)d * B + o];
                         d2 = fmaf(t, t, d2);
@@ -230,7 +237,11 @@ __global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __res
                 }
                 if (__any_sync(0xFFFFFFFFu, near)) continue;
                 const int j = nlead_s + nf;
-                for (int d = lane; d < D; d += 32) L[(size_t)j * D + d] = sT[(size_t)d * B + r];
+                for (int d = lane; d < D; d += 32) {
+                    const float v = sT[(size_t)d * B + r];
+                    L[(size_t)j * D + d] = v;
+                    if (j < capS) Ls[(size_t)j * D + d] = v;
+                }
                 if (lane == 0) {
                     lead_row[j] = (int32_t)((long long)sidx[r] * stride);
                     fresh[nf] = r;
@@ -264,6 +275,7 @@ __global__ void __launch_bounds__(256) cover_kernel(const float* __restrict__ S,
         if (j < nl) {
             const float* l = L + (size_t)j * D;
             d2 = 0.0f;
+#pragma unroll 6
             for (int d = 0; d < D; ++d) {
                 const float t = a[d] - l[d];
                 d2 = fmaf(t, t, d2);
@@ -424,18 +436,20 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
     // the batch against the leaders the batch has produced, so its batches are small; pass C meets mostly
     // members of the few clusters pass A missed, which the parallel test against pass C's leaders covers.
     const int B = D <= 48 ? 256 : (D <= 96 ? 128 : 64), BA = 32;
-    const size_t lsm = ((size_t)D * B + 3 * (size_t)B) * sizeof(float);
+    const size_t batch_b = ((size_t)D * B + 3 * (size_t)B) * sizeof(float);
+    const int capS = (int)std::min<size_t>((size_t)cap, (200 * 1024 - batch_b) / ((size_t)D * sizeof(float)));
+    const size_t lsm = batch_b + (size_t)capS * D * sizeof(float);
     GMD_CUDA_CHECK(cudaFuncSetAttribute(leader_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
     unsigned char* flags = (unsigned char*)(nn + LEAD_PROBES);  // [ns]
     int32_t* list = (int32_t*)(flags + (((size_t)ns + 15) & ~(size_t)15));   // [ns]
     const int n1 = std::min(ns, 1024);                        // pass A: the samples clustered before any is known
-    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, BA, nullptr, list, L, lead_row,
-                                               info);
+    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, BA, capS, nullptr, list, L,
+                                               lead_row, info);
     GMD_CUDA_CHECK(cudaGetLastError());
     if (n1 < ns) {
         cover_kernel<<<(unsigned)(((size_t)(ns - n1) * 32 + 255) / 256), 256, 0, st>>>(S, ns, n1, D, L, info, flags);
         GMD_CUDA_CHECK(cudaGetLastError());
-        leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, B, flags, list, L,
+        leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, B, capS, flags, list, L,
                                                    lead_row, info);
         GMD_CUDA_CHECK(cudaGetLastError());
     }

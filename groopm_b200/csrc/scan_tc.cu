@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
         s_src[threadIdx.x] = src;
         double n2 = 0.0;
         if (src >= 0) {
+#pragma unroll 6
             for (int k = 0; k < D; ++k) {
                 const double v = (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale);
                 n2 += v * v;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
     if (threadIdx.x < TM && s_src[threadIdx.x] >= 0) {
         const long long src = s_src[threadIdx.x];
         double d2 = 0.0;
+#pragma unroll 6
         for (int k = 0; k < D; ++k) {
             const double u = (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale) - (double)s_m[k];
             d2 += u * u;

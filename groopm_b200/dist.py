@@ -3,11 +3,15 @@
 One process per GPU (torchrun).  Every query row's top-k depends only on that row
 and the full candidate set, so the contigs are block-sharded: rank g owns rows
 [g*per, (g+1)*per), computes the neighbours of ITS rows against ALL rows, and no
-cross-rank merge is needed.  The only exchange is one all-gather of the float64
+cross-rank merge is needed.  The exchange is one all-gather of the float64
 profile rows over NCCL/NVLink (N*D*8 bytes: 240 MB for 1 M x 30), after which each
-rank stages the candidate tiles locally and scans them for its own rows.
-Candidate indices are global row numbers, so the lowest-index tie rule is the same
-for every GPU count.
+rank runs the engine's default pipeline -- for large Euclidean problems the grouped
+staging and the pruned tensor-core scan -- on its run of the rows.  The staging's one
+pass over EVERY row, the nearest-leader search, is split as well: every rank searches
+its own rows and two small all-gathers (4 + 8 bytes per row) put the keys together; the
+leaders themselves come out identical on every rank (deterministic kernels on identical
+rows).  Candidate indices are global row numbers, so the lowest-index tie rule is the
+same for every GPU count.
 """
 from __future__ import annotations
 
@@ -35,7 +39,7 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def gather_rows(x_local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
-    """All-gather the row shards into the full [n_total, D] matrix on every rank.
+    """All-gather the row shards into the full [n_total, ...] array on every rank.
 
     Works on NCCL (CUDA tensors) and gloo (CPU tensors, used by the CPU tests)."""
     world = dist.get_world_size(group)
@@ -44,17 +48,41 @@ def gather_rows(x_local: torch.Tensor, n_total: int, group=None) -> torch.Tensor
     r0, r1 = shard_bounds(n_total, world, rank)
     if x_local.shape[0] != r1 - r0:
         raise ValueError(f"rank {rank} holds {x_local.shape[0]} rows, its shard is [{r0}, {r1})")
-    d = x_local.shape[1]
-    full = torch.empty((world * per, d), dtype=x_local.dtype, device=x_local.device)
+    tail = tuple(x_local.shape[1:])
+    full = torch.empty((world * per,) + tail, dtype=x_local.dtype, device=x_local.device)
     if x_local.shape[0] == per:
         mine = x_local.contiguous()
     else:
-        mine = torch.zeros((per, d), dtype=x_local.dtype, device=x_local.device)
+        mine = torch.zeros((per,) + tail, dtype=x_local.dtype, device=x_local.device)
         mine[: x_local.shape[0]] = x_local
     dist.all_gather_into_tensor(full, mine, group=group)
     # only the last non-empty shard is short, so the first n_total rows are exactly the
-    # global matrix in row order
+    # global array in row order
     return full[:n_total]
+
+
+_ASSIGN_PIPES: dict = {}
+
+
+def _nearest_leader_sharded(lead: torch.Tensor, full: torch.Tensor, r0: int, r1: int, group):
+    """(index, float64 distance) of every row's nearest leader, every rank searching its own rows
+    [r0, r1) with the engine's k = 1 pipeline; two all-gathers put the shards together."""
+    from .engine import KnnPipeline
+
+    n, d = full.shape
+    dev = full.device
+    if r1 > r0:
+        key = (r1 - r0, lead.shape[0], d, str(dev))
+        pipe = _ASSIGN_PIPES.get(key)
+        if pipe is None:
+            _ASSIGN_PIPES.clear()                     # the number of leaders is stable for a data set: keep one
+            pipe = _ASSIGN_PIPES[key] = KnnPipeline(r1 - r0, lead.shape[0], d, 1, "euclidean", same=False, device=dev)
+        idx, dd = pipe.run(full[r0:r1], lead.contiguous())
+        idx, dd = idx.reshape(-1), dd.reshape(-1)
+    else:
+        idx = torch.empty(0, dtype=torch.int32, device=dev)
+        dd = torch.empty(0, dtype=torch.float64, device=dev)
+    return gather_rows(idx, n, group).contiguous(), gather_rows(dd, n, group).contiguous()
 
 
 def sharded_knn(x_local: torch.Tensor, n_total: int, k: int, metric="euclidean", group=None,
@@ -70,11 +98,29 @@ def sharded_knn(x_local: torch.Tensor, n_total: int, k: int, metric="euclidean",
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     r0, r1 = shard_bounds(n_total, world, rank)
-    if r1 == r0:
-        e = dict(device=x_local.device)
-        return torch.empty((0, k), dtype=torch.int32, **e), torch.empty((0, k), dtype=torch.float64, **e)
-    q = full[r0:r1]
-    if pipeline is None:
+    if pipeline is None and r1 > r0:
         pipeline = KnnPipeline(r1 - r0, n_total, full.shape[1], k, metric, form, same=False,
                                device=x_local.device)
-    return pipeline.run(q, full)
+    # the split staging needs every rank in its collectives: agree on it once per pipeline (ranks without rows
+    # go along with whatever the others do)
+    mode = getattr(pipeline, "_shard_mode", None) if pipeline is not None else None
+    if mode is None:
+        mine = 1 if (pipeline is None or (pipeline.prune and 0 < r1 - r0 < n_total)) else 0
+        t = torch.tensor([mine], dtype=torch.int32, device=x_local.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        mode = bool(t.item()) and world > 1
+        if pipeline is not None:
+            pipeline._shard_mode = mode
+    if r1 == r0:
+        if mode:
+            # no rows here, but the others' all-gathers of the nearest-leader keys need this rank
+            _nearest_leader_sharded(torch.empty((1, full.shape[1]), dtype=torch.float64, device=full.device), full, r0, r1,
+                                    group)
+        e = dict(device=x_local.device)
+        return torch.empty((0, k), dtype=torch.int32, **e), torch.empty((0, k), dtype=torch.float64, **e)
+    q = full[r0:r1]                                   # a run of the candidates' rows: the staging shares the keys
+    pipeline.shard_assign = (lambda lead: _nearest_leader_sharded(lead, full, r0, r1, group)) if mode else None
+    try:
+        return pipeline.run(q, full)
+    finally:
+        pipeline.shard_assign = None

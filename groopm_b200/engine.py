@@ -160,6 +160,10 @@ class KnnPipeline:
             self.grouped_ws = torch.empty(self.lib.gmd_tc_grouped_workspace_bytes(self.nq, self.nc, self.d),
                                           dtype=torch.uint8, **e)
             self.grouped = _lib.Grouped()
+        # row-sharded callers (dist.py) hand in a function that finds the nearest leader of all rows with the work
+        # split over the ranks: lead_rows [nlead, D] -> (index int32 [nc], distance float64 [nc])
+        self.shard_assign = None
+        self.scan_events = None     # a list: run() appends a (start, end) CUDA event pair around every scan launch
         self.out_idx = torch.empty((self.nq, self.k), dtype=torch.int32, **e)
         self.out_dist = torch.empty((self.nq, self.k), dtype=torch.float64, **e)
 
@@ -189,6 +193,23 @@ class KnnPipeline:
                                                      _stream_ptr()))
             # pass 2 for both roles, now that both sets' norms are known
             c = self._tc_c
+            if self.prune and self.shard_assign is not None:
+                # the same staging in two halves: leaders here, nearest leaders by the caller (every rank its
+                # own rows, all-gathered), the rest here
+                nlead = C.c_int32(0)
+                lead_ptr = C.c_void_p(0)
+                _lib.check(self.lib.gmd_tc_grouped_leaders_f64(
+                    _ptr(c), self.nq, self.nc, self.d, _ptr(self.center), _ptr(self.grouped_ws),
+                    self.grouped_ws.numel(), C.byref(nlead), C.byref(lead_ptr), _stream_ptr()))
+                off = lead_ptr.value - self.grouped_ws.data_ptr()
+                lead = self.grouped_ws[off:off + nlead.value * self.d * 8].view(torch.float64).view(nlead.value, self.d)
+                near_idx, near_dist = self.shard_assign(lead)
+                _lib.check(self.lib.gmd_tc_stage_grouped_ext_f64(
+                    _ptr(q), self.nq, _ptr(c), self.nc, self.d, _ptr(self.center), _ptr(self.stats), sq,
+                    _ptr(self.qtiles), _ptr(self.ctiles), _ptr(self.grouped_ws), self.grouped_ws.numel(),
+                    nlead.value, _ptr(near_idx), _ptr(near_dist), C.byref(self.grouped), _stream_ptr()))
+                self._tc_c = None
+                return
             if self.prune:
                 # leaders, nearest-leader keys, padded counting sort, tiles + balls: one C call (it
                 # synchronises the stream once, to learn the number of leaders)
@@ -264,7 +285,14 @@ class KnnPipeline:
             self.col_mean(c)
             self.prep_candidates(c)
             self.prep_queries(q)
-            self.scan()
+            if self.scan_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self.scan()
+                e1.record()
+                self.scan_events.append((e0, e1))
+            else:
+                self.scan()
             self.refine(q, c)
             self.exact_rows(q, c)
         return self.out_idx, self.out_dist

@@ -239,6 +239,18 @@ GMD_API size_t gmd_tc_grouped_workspace_bytes(int64_t Nq, int64_t Nc, int D);
 GMD_API int gmd_tc_stage_grouped_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
                      const double* center, const float* stats_c, const float* stats_q, void* qtiles, void* ctiles,
                      void* workspace, size_t workspace_bytes, gmd_grouped* out, void* stream);
+/* The staging in two halves, for row-sharded callers (queries = a run of the candidates' rows on every
+ * GPU): gmd_tc_grouped_leaders_f64 picks the leaders into the workspace (same result on every rank) and
+ * returns their number and device rows; the caller finds the nearest leader of ITS rows, all-gathers
+ * (index, float64 distance) over the ranks and hands the full arrays to gmd_tc_stage_grouped_ext_f64, which
+ * does the rest.  Same workspace (gmd_tc_grouped_workspace_bytes) for both calls.                    */
+GMD_API int gmd_tc_grouped_leaders_f64(const double* C, int64_t Nq, int64_t Nc, int D, const double* center,
+                     void* workspace, size_t workspace_bytes, int32_t* nlead_host, const double** lead_rows_dev,
+                     void* stream);
+GMD_API int gmd_tc_stage_grouped_ext_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                     const double* center, const float* stats_c, const float* stats_q, void* qtiles, void* ctiles,
+                     void* workspace, size_t workspace_bytes, int32_t nlead, const int32_t* nearest_idx,
+                     const double* nearest_dist, gmd_grouped* out, void* stream);
 GMD_API int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const void* ctiles, int64_t Nc_pos, int D, int kk,
                      int64_t c_index_offset, const float* stats_c, const float* stats_q,
                      const uint32_t* perm_q, const uint32_t* perm_c, const int32_t* tgroup_q,

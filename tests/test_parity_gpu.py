@@ -12,6 +12,7 @@ import torch
 from scipy.spatial.distance import cdist as sp_cdist, pdist as sp_pdist
 
 import oracle
+import par_oracle
 from groopm_b200 import _lib, dropin, engine, synth
 
 pytestmark = pytest.mark.gpu
@@ -396,11 +397,12 @@ def test_cfg4_raw_signatures_100k_d136(cuda):
     idx32, dist32, info32 = engine.knn(sigs, None, k=16, form=_lib.FORM_EXPANDED, return_info=True)
     assert info32["form"] == _lib.FORM_EXPANDED    # the FP32 scan proposes, float64 decides: same answer
     assert np.array_equal(idx, idx32) and np.array_equal(dist, dist32)
-    rows = np.sort(np.random.default_rng(4).choice(len(sigs), 256, replace=False))
-    od, oi = oracle.knn(sigs[rows], sigs, 16)
+    rows = np.sort(np.random.default_rng(4).choice(len(sigs), 2048, replace=False))   # 2 048 sampled rows
+    od, oi = par_oracle.knn(sigs[rows], sigs, 16)
     assert_knn_parity(sigs[rows], sigs, idx[rows], dist[rows], oi, od)
+    assert np.array_equal(idx[rows], oi) and np.array_equal(dist[rows], od)
     l1_idx, l1_dist = engine.knn(sigs[rows], sigs, k=16, metric="cityblock")
-    od1, oi1 = oracle.knn(sigs[rows], sigs, 16, "cityblock")
+    od1, oi1 = par_oracle.knn(sigs[rows], sigs, 16, "cityblock")
     assert_knn_parity(sigs[rows], sigs, l1_idx, l1_dist, oi1, od1, "cityblock")
     for a, b in ((0, 1), (7, 3)):
         ba, bb = sigs[a * 2000:(a + 1) * 2000], sigs[b * 2000:(b + 1) * 2000]
@@ -411,11 +413,13 @@ def test_cfg2_full_100k_d10_k16(cuda):
     x = synth.cfg_knn_rows(100_000, 10, 2)
     idx, dist, info = engine.knn(x, None, k=16, return_info=True)
     _graph_properties(x, idx, dist, 16)
-    rows = np.sort(np.random.default_rng(2).choice(len(x), 512, replace=False))
-    od, oi = oracle.knn(x[rows], x, 16)
+    assert info["pruned"]                              # the engine's default at this size
+    rows = np.sort(np.random.default_rng(2).choice(len(x), 4096, replace=False))
+    od, oi = par_oracle.knn(x[rows], x, 16)
     assert_knn_parity(x[rows], x, idx[rows], dist[rows], oi, od)
+    assert np.array_equal(idx[rows], oi) and np.array_equal(dist[rows], od)
     l1_idx, l1_dist = engine.knn(x[rows], x, k=16, metric="cityblock")
-    od1, oi1 = oracle.knn(x[rows], x, 16, "cityblock")
+    od1, oi1 = par_oracle.knn(x[rows], x, 16, "cityblock")
     assert_knn_parity(x[rows], x, l1_idx, l1_dist, oi1, od1, "cityblock")
 
 
@@ -433,9 +437,11 @@ def test_cfg5_full_1m_d30_k32(cuda):
     x = synth.cfg_knn_rows(1_000_000, 30, 5)
     idx, dist, info = engine.knn(x, None, k=32, return_info=True)
     _graph_properties(x, idx, dist, 32)
-    rows = np.sort(np.random.default_rng(5).choice(len(x), 96, replace=False))
-    od, oi = oracle.knn(x[rows], x, 32)
+    assert info["pruned"]
+    rows = np.sort(np.random.default_rng(5).choice(len(x), 4096, replace=False))        # 4 096 sampled rows
+    od, oi = par_oracle.knn(x[rows], x, 32)
     assert_knn_parity(x[rows], x, idx[rows], dist[rows], oi, od)
+    assert np.array_equal(idx[rows], oi) and np.array_equal(dist[rows], od)
 
 
 def test_batched_medians_vs_oracle(cuda):

@@ -182,3 +182,47 @@ def test_cfg5_1m_what_the_bench_times(cuda):
     rows = np.sort(np.random.default_rng(5).choice(n, 2048, replace=False))
     od, oi = par_oracle.knn(x[rows], x, k)
     assert np.array_equal(idx[rows].cpu().numpy(), oi) and np.array_equal(dist[rows].cpu().numpy(), od)
+
+
+# ------------------------------------------------------------------ the certificate under attack
+def _adversarial(kind, n, d, rng):
+    if kind == "decades":                        # column scales over 12 decades: most columns vanish in FP16 hi/lo
+        x = rng.standard_normal((n, d)) * (10.0 ** rng.uniform(-6, 6, size=d))
+    elif kind == "near_duplicates":              # clusters 1e-7 wide around points of norm ~10: below FP32 resolution
+        base = rng.standard_normal((40, d)) * 3.0
+        x = base[rng.integers(0, 40, size=n)] + 1e-7 * rng.standard_normal((n, d))
+    elif kind == "far_pair":                     # two tight clusters 1e6 apart: the centring leaves norms of 5e5
+        x = 1e-3 * rng.standard_normal((n, d))
+        x[n // 2:] += 1e6
+    elif kind == "denormals":                    # half of the columns hold denormal-range values
+        x = rng.standard_normal((n, d))
+        x[:, ::2] *= 1e-38
+    elif kind == "sphere":                       # every row at the largest norm, neighbours nearly tied
+        x = rng.standard_normal((n, d))
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        x *= 1000.0
+    elif kind == "lattice":                      # exact ties everywhere: integer lattice points
+        x = rng.integers(0, 4, size=(n, d)).astype(np.float64)
+    else:
+        raise AssertionError(kind)
+    return np.ascontiguousarray(x)
+
+
+@pytest.mark.parametrize("prune", [False, True])
+@pytest.mark.parametrize("kind,n,d,k", [
+    ("decades", 4000, 12, 8), ("decades", 3000, 33, 5), ("near_duplicates", 5000, 4, 16), ("near_duplicates", 3000, 136, 6),
+    ("far_pair", 3000, 8, 10), ("denormals", 4000, 10, 12), ("sphere", 5000, 30, 32), ("sphere", 2500, 136, 4),
+    ("lattice", 4000, 6, 20),
+])
+def test_certificate_holds_under_adversarial_inputs(cuda, kind, n, d, k, prune):
+    """Inputs built to make the tensor-core scan's FP32-class values useless -- column scales over twelve
+    decades, clusters narrower than the FP32 resolution of their coordinates, a common offset the centring
+    cannot remove, denormal-range columns, rows of equal (maximal) norm with nearly tied neighbours, a lattice
+    of exact ties.  Whatever the scan proposes, the certificate must either prove the float64 result or send
+    the row to the exact pass: the answer is the oracle's, bit for bit, with the lowest-index tie rule."""
+    x = _adversarial(kind, n, d, np.random.default_rng(zlib.crc32(f"{kind}{n}{d}".encode())))
+    idx, dist, info = engine.knn(x, None, k=k, form=_lib.FORM_TC, prune=prune, return_info=True)
+    od, oi = par_oracle.knn(x, x, k)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    if kind in ("near_duplicates", "far_pair", "lattice"):
+        assert info["exact_rows"] > 0            # these cannot be certified from FP32-class values
