@@ -15,6 +15,15 @@
 
 #include "common.cuh"
 
+// distance shells of a group: count, and width in units of the leader radius R
+// (in high dimensions d(q, c)^2 ~ |q - L|^2 + |c - L|^2 inside a group, so the rows nearest their leader are near
+// everybody: thin shells put them first in the group's window and the thresholds tighten sooner -- 8 shells of
+// R / 2: scan 5.03 ms, 64 of R / 16: 4.80 ms at 1M x 30)
+#ifndef GMD_SHELLS
+#define GMD_SHELLS 64
+#define GMD_SHELL_WIDTH 0.0625
+#endif
+
 namespace {
 
 __global__ void __launch_bounds__(256) key_hist_kernel(const int32_t* __restrict__ key, long long N, int nkeys,
@@ -106,156 +115,143 @@ __global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict_
     }
 }
 
-// Leader clustering of the samples: a sample becomes a leader unless an earlier leader lies within
-// R = rfac x median(nn) of it (at most cap leaders).  Greedy and order dependent, hence one block -- but only
-// for the part that has to be: pass A clusters the first n1 samples (all their candidate leaders are
-// unknown), cover_kernel then tests every other sample against pass A's leaders on the whole GPU, and pass C
-// clusters the samples that are still uncovered, testing them against pass C's own leaders only.
-// Inside a pass the samples go through in batches of B: all threads test the batch against the leaders
-// that exist (thread = one sample x a share of the leaders; the batch sits dimension-major in shared
-// memory, the leader rows are warp-wide broadcasts), then warp 0 walks the uncovered samples in order and
-// tests each against the leaders the batch itself has produced so far.
-// out: L [cap][D] centred FP32 leader rows, lead_row[cap] (row of X), info[0] = leaders,
-// info[1] = float bits of R.
-// pass A: flags null, samples [0, n1), j0 = 0, computes R.  pass C: samples {i >= n1 : flags[i] != 0} in order
-// (compacted by the block first), tested against the leaders from index info[2] on (pass A's count).
-__global__ void __launch_bounds__(LEAD_THREADS) leader_kernel(const float* __restrict__ S, int ns, int n1,
-                                                             long long stride, int D, const float* __restrict__ nn,
-                                                             int nprobe, float rfac, int cap, int B, int capS,
-                                                             const unsigned char* __restrict__ flags,
-                                                             int32_t* __restrict__ list, float* __restrict__ L,
-                                                             int32_t* __restrict__ lead_row,
+// Leader clustering of the samples: in sample order, a sample becomes a leader unless an earlier LEADER lies
+// within R = rfac x median(nn) of it (at most cap leaders).  Greedy and order dependent -- but only the
+// decision is: which pairs of samples lie within R of each other is a plain all-pairs question, answered
+// by the whole GPU into a bit matrix (adjacency_kernel), and the greedy pass (resolve_kernel, one block)
+// then walks the samples with 32-bit ANDs against the mask of the leaders so far.
+//   pass A   the first n1 samples among themselves;
+//   cover    every other sample against pass A's leaders (cover_kernel, whole GPU);
+//   pass C   the samples still uncovered, among themselves (they are far from all of pass A's leaders).
+// info[0] = leaders, info[1] = float bits of R, info[2] = pass A's leaders, info[3] = uncovered samples.
+
+// R from the nearest-sample distances of the probes: the median of the finite ones, by rank counting
+__global__ void __launch_bounds__(LEAD_PROBES) radius_kernel(const float* __restrict__ nn, int nprobe, float rfac,
                                                              int32_t* __restrict__ info) {
-    extern __shared__ float lsm[];
-    float* sT = lsm;                                   // [D][B] the batch, dimension-major
-    int* cov = reinterpret_cast<int*>(sT + (size_t)D * B);   // [B]
-    int* fresh = cov + B;                              // [B] batch members that became leaders (batch index)
-    int* sidx = fresh + B;                             // [B] sample index of a batch member
-    // the first capS leaders are mirrored in shared memory: the global rows are written while the kernel runs,
-    // and a freshly written line is an L2 round trip for every reader
-    float* Ls = reinterpret_cast<float*>(sidx + B);    // [capS][D]
     __shared__ float vals[LEAD_PROBES];
-    __shared__ int part[LEAD_THREADS];
-    __shared__ int nlead_s, nlist_s;
-    __shared__ float R2_s;
-    const int tid = threadIdx.x, lane = tid & 31;
-    int j0 = 0, nlist;
-    if (!flags) {
-        // ---- pass A: median of the finite nearest-sample distances, by rank counting
-        const bool probe = tid < nprobe;
-        const float v = probe ? nn[tid] : __int_as_float(0x7f800000);
-        if (tid < LEAD_PROBES) vals[tid] = v;
-        if (tid == 0) nlead_s = 0, R2_s = 0.0f;
-        const int nfin = __syncthreads_count(probe && v < __int_as_float(0x7f800000));
-        if (probe && nfin > 0) {
-            int rank = 0;
-            for (int j = 0; j < nprobe; ++j) rank += (vals[j] < v || (vals[j] == v && j < tid)) ? 1 : 0;
-            if (rank == nfin / 2) {
-                const float R = rfac * v;
-                R2_s = R * R;
-                info[1] = __float_as_int(R);
-            }
-        } else if (tid == 0 && nfin == 0) {
-            info[1] = 0;
-        }
-        nlist = n1;
-    } else {
-        // ---- pass C: ordered compaction of the uncovered samples
-        const int per = (ns - n1 + LEAD_THREADS - 1) / LEAD_THREADS;
-        const int a = min(ns, n1 + tid * per), b = min(ns, a + per);
-        int c = 0;
-        for (int i = a; i < b; ++i) c += flags[i] ? 1 : 0;
-        part[tid] = c;
-        __syncthreads();
-        for (int o = 1; o < LEAD_THREADS; o <<= 1) {
-            const int v = tid >= o ? part[tid - o] : 0;
-            __syncthreads();
-            part[tid] += v;
-            __syncthreads();
-        }
-        int pos = part[tid] - c;
-        for (int i = a; i < b; ++i)
-            if (flags[i]) list[pos++] = i;
-        if (tid == LEAD_THREADS - 1) nlist_s = part[tid];
-        if (tid == 0) {
-            nlead_s = info[0];
-            const float R = __int_as_float(info[1]);
-            R2_s = R * R;
-        }
-        __syncthreads();
-        nlist = nlist_s;
-        j0 = info[0];
-        for (int e = tid; e < min(j0, capS) * D; e += LEAD_THREADS) Ls[e] = L[e];   // pass A's leaders
+    const int tid = threadIdx.x;
+    const bool probe = tid < nprobe;
+    const float v = probe ? nn[tid] : __int_as_float(0x7f800000);
+    vals[tid] = v;
+    if (tid == 0) info[0] = 0, info[1] = 0, info[2] = 0, info[3] = 0;
+    const int nfin = __syncthreads_count(probe && v < __int_as_float(0x7f800000));
+    if (probe && nfin > 0) {
+        int rank = 0;
+        for (int j = 0; j < nprobe; ++j) rank += (vals[j] < v || (vals[j] == v && j < tid)) ? 1 : 0;
+        if (rank == nfin / 2) info[1] = __float_as_int(rfac * v);
+    }
+}
+
+// bits[i][c] bit l  <-  |s_i - s_j| <= R for j = 32 c + l, over the n samples list[0..n) (list null: samples
+// 0..n-1; n_dev non-null: n is read from the device).  One block per 8 rows i; a warp takes 32 columns at a time,
+// lane = column, the 8 rows broadcast from shared memory, one ballot per row.
+__global__ void __launch_bounds__(256) adjacency_kernel(const float* __restrict__ S, const int32_t* __restrict__ list,
+                                                       const int32_t* __restrict__ n_dev, int n_max, int D,
+                                                       const int32_t* __restrict__ info, uint32_t* __restrict__ bits,
+                                                       int wpr) {
+    extern __shared__ float rows[];                      // [8][D]
+    const int n = n_dev ? min(*n_dev, n_max) : n_max;
+    const int i0 = blockIdx.x * 8;
+    if (i0 >= n) return;
+    const int nr = min(8, n - i0);
+    for (int e = threadIdx.x; e < nr * D; e += blockDim.x) {
+        const int r = e / D, d = e - r * D;
+        const int si = list ? list[i0 + r] : i0 + r;
+        rows[e] = S[(size_t)si * D + d];
     }
     __syncthreads();
-    const float R2 = R2_s;
-    const int shares = LEAD_THREADS / B;               // threads per sample, each takes every shares-th leader
-    const int b = tid % B, share = tid / B;
-    for (int i0 = 0; i0 < nlist; i0 += B) {
-        const int nb = min(B, nlist - i0);
-        for (int e = tid; e < B; e += LEAD_THREADS) {
-            cov[e] = 0;
-            if (e < nb) sidx[e] = flags ? list[i0 + e] : i0 + e;
-        }
-        __syncthreads();
-        for (int e = tid; e < nb * D; e += LEAD_THREADS) {
-            const int r = e / D, d = e - r * D;
-            sT[(size_t)d * B + r] = S[(size_t)sidx[r] * D + d];
-        }
-        __syncthreads();
-        const int nl = nlead_s;
-        if (b < nb) {
-            bool hit = false;
-            for (int j = j0 + share; j < nl && !hit; j += shares) {
-                const float* l = j < capS ? Ls + (size_t)j * D : L + (size_t)j * D;   // one row for the whole warp: broadcast
-                float d2 = 0.0f;
-#pragma unroll 6
-                for (int d = 0; d < D; ++d) {
-                    const float t = sT[(size_t)d * B + b] - l[d];
-                    d2 = fmaf(t, t, d2);
+    const float R = __int_as_float(info[1]), R2 = R * R;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // only the columns below the block's last row matter (a sample is tested against EARLIER leaders)
+    const int ncol = min(n, i0 + nr);
+    for (int c = warp; c * 32 < ncol; c += 8) {
+        const int j = c * 32 + lane;
+        float d2[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) d2[r] = 0.0f;
+        if (j < n) {
+            const float* b = S + (size_t)(list ? list[j] : j) * D;
+#pragma unroll 4
+            for (int d = 0; d < D; ++d) {
+                const float v = b[d];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float t = rows[r * D + d] - v;
+                    d2[r] = fmaf(t, t, d2[r]);
                 }
-                hit = d2 <= R2;
             }
-            if (hit) cov[b] = 1;
         }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const unsigned w = __ballot_sync(0xFFFFFFFFu, j < n && d2[r] <= R2);
+            if (lane == 0 && r < nr) bits[(size_t)(i0 + r) * wpr + c] = w;
+        }
+    }
+}
+
+// The greedy pass over the n samples of list (null: 0..n-1), one block: 32 rows of the bit matrix are staged in
+// shared memory at a time, then warp 0 decides them in order -- sample i is a leader iff no bit of row i below
+// column i meets the leader mask.  New leaders are appended to L / lead_row from info[0] on.
+__global__ void __launch_bounds__(LEAD_THREADS) resolve_kernel(const float* __restrict__ S, const int32_t* __restrict__ list,
+                                                              const int32_t* __restrict__ n_dev, int n_max, int D,
+                                                              const uint32_t* __restrict__ bits, int wpr, int cap,
+                                                              long long stride, float* __restrict__ L,
+                                                              int32_t* __restrict__ lead_row, int32_t* __restrict__ info,
+                                                              int pass) {
+    extern __shared__ uint32_t rsm[];
+    uint32_t* mask = rsm;                                // [wpr] leaders among the samples decided so far
+    uint32_t* chunk = rsm + wpr;                         // [32][wpr]
+    __shared__ int picked[32];
+    __shared__ int npicked, nlead_s;
+    const int n = n_dev ? min(*n_dev, n_max) : n_max;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int w = tid; w < wpr; w += LEAD_THREADS) mask[w] = 0u;
+    if (tid == 0) nlead_s = info[0];
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int nr = min(32, n - i0);
+        const int nwords = (i0 + nr + 31) >> 5;          // columns below the chunk's last row
+        for (int e = tid; e < nr * nwords; e += LEAD_THREADS) {
+            const int r = e / nwords, w = e - r * nwords;
+            chunk[r * wpr + w] = bits[(size_t)(i0 + r) * wpr + w];
+        }
+        if (tid == 0) npicked = 0;
         __syncthreads();
         if (tid < 32) {
-            int nf = 0;                                // leaders this batch has produced (warp-uniform)
-            for (int r = 0; r < nb; ++r) {
-                if (cov[r]) continue;
-                if (nlead_s + nf >= cap) break;
+            for (int r = 0; r < nr; ++r) {
+                const int i = i0 + r;
+                if (nlead_s + npicked >= cap) break;
                 bool near = false;
-                for (int x = lane; x < nf; x += 32) {
-                    const int o = fresh[x];
-                    float d2 = 0.0f;
-#pragma unroll 6
-                    for (int d = 0; d < D; ++d) {
-                        const float t = sT[(size_t)d * B + r] - sT[(size_t)d * B + o];
-                        d2 = fmaf(t, t, d2);
-                    }
-                    near |= d2 <= R2;
+                for (int w = lane; w * 32 < i; w += 32) {
+                    uint32_t m = mask[w];
+                    if (w == (i >> 5)) m &= (1u << (i & 31)) - 1u;      // columns below i only
+                    near |= (chunk[r * wpr + w] & m) != 0u;
                 }
                 if (__any_sync(0xFFFFFFFFu, near)) continue;
-                const int j = nlead_s + nf;
-                for (int d = lane; d < D; d += 32) {
-                    const float v = sT[(size_t)d * B + r];
-                    L[(size_t)j * D + d] = v;
-                    if (j < capS) Ls[(size_t)j * D + d] = v;
-                }
                 if (lane == 0) {
-                    lead_row[j] = (int32_t)((long long)sidx[r] * stride);
-                    fresh[nf] = r;
+                    mask[i >> 5] |= 1u << (i & 31);
+                    picked[npicked] = i;
+                    npicked = npicked + 1;
                 }
                 __syncwarp();
-                ++nf;
             }
-            if (lane == 0) nlead_s += nf;
         }
+        __syncthreads();
+        // the chunk's new leaders: rows copied by everybody
+        const int np = npicked, base = nlead_s;
+        for (int e = tid; e < np * D; e += LEAD_THREADS) {
+            const int x = e / D, d = e - x * D;
+            const int si = list ? list[picked[x]] : picked[x];
+            L[(size_t)(base + x) * D + d] = S[(size_t)si * D + d];
+            if (d == 0) lead_row[base + x] = (int32_t)((long long)si * stride);
+        }
+        __syncthreads();
+        if (tid == 0) nlead_s = base + np;
         __syncthreads();
     }
     if (tid == 0) {
         info[0] = nlead_s;
-        if (!flags) info[2] = nlead_s;
+        if (pass == 0) info[2] = nlead_s;
     }
 }
 
@@ -286,6 +282,29 @@ __global__ void __launch_bounds__(256) cover_kernel(const float* __restrict__ S,
     if (lane == 0) flags[i] = hit ? 0 : 1;
 }
 
+// ordered list of the uncovered samples i >= n1 (one block); info[3] = their number
+__global__ void __launch_bounds__(LEAD_THREADS) uncovered_kernel(const unsigned char* __restrict__ flags, int ns, int n1,
+                                                                int32_t* __restrict__ list, int32_t* __restrict__ info) {
+    __shared__ int part[LEAD_THREADS];
+    const int tid = threadIdx.x;
+    const int per = (ns - n1 + LEAD_THREADS - 1) / LEAD_THREADS;
+    const int a = min(ns, n1 + tid * per), b = min(ns, a + per);
+    int c = 0;
+    for (int i = a; i < b; ++i) c += flags[i] ? 1 : 0;
+    part[tid] = c;
+    __syncthreads();
+    for (int o = 1; o < LEAD_THREADS; o <<= 1) {
+        const int v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int pos = part[tid] - c;
+    for (int i = a; i < b; ++i)
+        if (flags[i]) list[pos++] = i;
+    if (tid == LEAD_THREADS - 1) info[3] = part[tid];
+}
+
 // leader rows of X, float64 row-major (the candidate set of the nearest-leader search)
 __global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restrict__ X, const int32_t* __restrict__ rows,
                                                          int n, int D, double* __restrict__ out) {
@@ -307,7 +326,7 @@ __global__ void __launch_bounds__(256) group_key_kernel(const int32_t* __restric
     const float R = __int_as_float(info[1]);
     int b = NB - 1;
     if (d == d && R > 0.0f) {
-        const double s = d / (0.5 * (double)R);
+        const double s = d / ((double)R * GMD_SHELL_WIDTH);
         b = s < (double)(NB - 1) ? (int)s : NB - 1;
     } else if (d == 0.0) {
         b = 0;
@@ -394,7 +413,7 @@ extern "C" int gmd_order_by_key(const int32_t* key, int64_t N, int nkeys, uint32
 }
 
 // ---------------------------------------------------------------- grouped order (pruned scan)
-extern "C" int gmd_group_shells(void) { return 8; }
+extern "C" int gmd_group_shells(void) { return GMD_SHELLS; }
 
 // sample count and leader capacity for N rows: ~8 samples per group of ~1000 rows, so that every
 // cluster of that size is met by the sample
@@ -407,9 +426,19 @@ extern "C" void gmd_group_params(int64_t N, int* ns, int* cap) {
     if (*cap > *ns) *cap = *ns;
 }
 
+namespace {
+int lead_n1(int ns) { return std::min(ns, 2048); }       // pass A: the samples clustered before any leader is known
+size_t lead_bits_words(int ns) {
+    // the larger of the two bit matrices: pass A (n1 x n1) and pass C (at most ns - n1 uncovered samples)
+    const size_t n1 = lead_n1(ns), n2 = (size_t)ns - n1;
+    return std::max(n1 * ((n1 + 31) / 32), n2 * ((n2 + 31) / 32));
+}
+}  // namespace
+
 extern "C" size_t gmd_group_leaders_workspace_bytes(int ns, int D) {
-    // samples, nearest-sample distances, uncovered flags, list of uncovered samples
-    return ((size_t)ns * D + LEAD_PROBES) * sizeof(float) + (((size_t)ns + 15) & ~(size_t)15) + (size_t)ns * sizeof(int32_t);
+    // samples, nearest-sample distances, uncovered flags, list of uncovered samples, bit matrix
+    return ((size_t)ns * D + LEAD_PROBES) * sizeof(float) + (((size_t)ns + 15) & ~(size_t)15) + (size_t)ns * sizeof(int32_t) +
+           lead_bits_words(ns) * sizeof(uint32_t);
 }
 
 extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const double* center, int ns, int cap, float rfac,
@@ -417,14 +446,17 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
                                      size_t workspace_bytes, int32_t* nlead_host, void* stream) {
     GMD_REQUIRE(X && L && lead_row && lead_rows && info && workspace && nlead_host, GMD_ERR_BAD_ARG,
                 "group_leaders: null pointer");
-    GMD_REQUIRE(N > 0 && D >= 1 && D <= GMD_MAX_D && ns >= 1 && ns <= N && cap >= 1 && rfac > 0.0f, GMD_ERR_BAD_ARG,
-                "group_leaders: bad sizes (N=%lld ns=%d cap=%d)", (long long)N, ns, cap);
+    GMD_REQUIRE(N > 0 && D >= 1 && D <= GMD_MAX_D && ns >= 1 && ns <= N && ns <= 16384 && cap >= 1 && rfac > 0.0f,
+                GMD_ERR_BAD_ARG, "group_leaders: bad sizes (N=%lld ns=%d cap=%d)", (long long)N, ns, cap);
     GMD_REQUIRE(workspace_bytes >= gmd_group_leaders_workspace_bytes(ns, D), GMD_ERR_WORKSPACE,
                 "group_leaders: workspace %zu B < required %zu B", workspace_bytes,
                 gmd_group_leaders_workspace_bytes(ns, D));
     cudaStream_t st = (cudaStream_t)stream;
     float* S = (float*)workspace;
     float* nn = S + (size_t)ns * D;
+    unsigned char* flags = (unsigned char*)(nn + LEAD_PROBES);               // [ns]
+    int32_t* list = (int32_t*)(flags + (((size_t)ns + 15) & ~(size_t)15));   // [ns]
+    uint32_t* bits = (uint32_t*)(list + ns);
     const long long stride = N / ns;
     const int nprobe = std::min(ns, LEAD_PROBES);
     const long long ne = (long long)ns * D;
@@ -432,26 +464,29 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
     GMD_CUDA_CHECK(cudaGetLastError());
     sample_nn_kernel<<<(unsigned)nprobe, 256, 0, st>>>(S, ns, D, nprobe, nn);
     GMD_CUDA_CHECK(cudaGetLastError());
-    // batch: [D][B] floats of shared memory.  Pass A meets mostly new clusters -- its cost is warp 0's walk over
-    // the batch against the leaders the batch has produced, so its batches are small; pass C meets mostly
-    // members of the few clusters pass A missed, which the parallel test against pass C's leaders covers.
-    const int B = D <= 48 ? 256 : (D <= 96 ? 128 : 64), BA = 32;
-    const size_t batch_b = ((size_t)D * B + 3 * (size_t)B) * sizeof(float);
-    const int capS = (int)std::min<size_t>((size_t)cap, (200 * 1024 - batch_b) / ((size_t)D * sizeof(float)));
-    const size_t lsm = batch_b + (size_t)capS * D * sizeof(float);
-    GMD_CUDA_CHECK(cudaFuncSetAttribute(leader_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-    unsigned char* flags = (unsigned char*)(nn + LEAD_PROBES);  // [ns]
-    int32_t* list = (int32_t*)(flags + (((size_t)ns + 15) & ~(size_t)15));   // [ns]
-    const int n1 = std::min(ns, 1024);                        // pass A: the samples clustered before any is known
-    leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, BA, capS, nullptr, list, L,
-                                               lead_row, info);
+    radius_kernel<<<1, LEAD_PROBES, 0, st>>>(nn, nprobe, rfac, info);
     GMD_CUDA_CHECK(cudaGetLastError());
+    const size_t adj_smem = (size_t)8 * D * sizeof(float);
+    auto pass = [&](const int32_t* lst, const int32_t* n_dev, int n_max, int which) -> int {
+        if (n_max <= 0) return GMD_OK;
+        const int wpr = (n_max + 31) / 32;
+        adjacency_kernel<<<(unsigned)((n_max + 7) / 8), 256, adj_smem, st>>>(S, lst, n_dev, n_max, D, info, bits, wpr);
+        GMD_CUDA_CHECK(cudaGetLastError());
+        const size_t rs = (size_t)33 * wpr * sizeof(uint32_t);
+        GMD_CUDA_CHECK(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        resolve_kernel<<<1, LEAD_THREADS, rs, st>>>(S, lst, n_dev, n_max, D, bits, wpr, cap, stride, L, lead_row, info, which);
+        GMD_CUDA_CHECK(cudaGetLastError());
+        return GMD_OK;
+    };
+    const int n1 = lead_n1(ns);
+    int rc;
+    if ((rc = pass(nullptr, nullptr, n1, 0)) != GMD_OK) return rc;
     if (n1 < ns) {
         cover_kernel<<<(unsigned)(((size_t)(ns - n1) * 32 + 255) / 256), 256, 0, st>>>(S, ns, n1, D, L, info, flags);
         GMD_CUDA_CHECK(cudaGetLastError());
-        leader_kernel<<<1, LEAD_THREADS, lsm, st>>>(S, ns, n1, stride, D, nn, nprobe, rfac, cap, B, capS, flags, list, L,
-                                                   lead_row, info);
+        uncovered_kernel<<<1, LEAD_THREADS, 0, st>>>(flags, ns, n1, list, info);
         GMD_CUDA_CHECK(cudaGetLastError());
+        if ((rc = pass(list, info + 3, ns - n1, 1)) != GMD_OK) return rc;
     }
     int32_t h[2] = {0, 0};
     GMD_CUDA_CHECK(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -184,7 +184,7 @@ GMD_API int gmd_scan_tc_sweep_f32(const void* qtiles, int64_t Nq, const void* ct
  * lead_rows [cap][D] float64 copies (the candidate set of the nearest-leader search, which is this
  * library's own k = 1 pipeline), info [2] = {leaders, float bits of the radius}.
  * gmd_group_order: given every row's nearest leader and float64 distance to it, keys the rows by
- * (leader, distance shell of width radius / 2; gmd_group_shells() shells), counting-sorts them with every
+ * (leader, distance shell of width radius / 16; gmd_group_shells() shells), counting-sorts them with every
  * leader's group padded to whole `tile`-row tiles:  perm[position] = row, 0xFFFFFFFF = padding
  * (npos >= gmd_group_positions(N, ngroups, tile) positions), gstart [ngroups + 1] first tile of a group,
  * tgroup [npos / tile] group of a tile (-1: padding only), grad [ngroups] (nullable) largest member
