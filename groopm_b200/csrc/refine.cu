@@ -8,9 +8,10 @@
 //
 // Certificate.  A candidate the scan did NOT propose sits in some full split list
 // whose kk-th FP32 value is tau_s, so its FP32 value is >= tau = min_s tau_s and its
-// true float64 distance is >= lower(tau) where lower() subtracts a rigorous bound on
+// true float64 distance is >= lower(tau) where lower() subtracts a bound on
 // (a) float64->float32 rounding of the centred rows, |d - d~| <= u(||q|| + ||c||),
-// and (b) the FP32 accumulation error of the scan's form.  If the k-th float64
+// and (b) the accumulation error of the scan's form (for the tensor-core form: derived below without
+// assumptions about the hardware's internal summation; tests/test_prune_gpu.py attacks it).  If the k-th float64
 // distance is strictly below lower(tau) the top-k is provably the exact one.
 // Otherwise the row goes to exact_rows_kernel, a float64 scan of every candidate.
 #include "common.cuh"
@@ -162,16 +163,19 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
             const double e2 = (2.0 * D + 8.0) * U32 * nn * nn;
             lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
         } else if (form == GMD_FORM_TC) {
-            // 3 x FP16 dot product of rows scaled by 2^e: representation (3 x 2^-22) and accumulation
-            // error measured at 2^-21.9 |q||c| (tools/tc_probe16.cu); bounded here by 2^-18 |q||c| <=
-            // 2^-20 nn^2, doubled by the factor -2, plus the norm column (hi + lo: 2^-22 ||c||^2) and the
-            // FP32 roundings of the write-out: 64 x 2^-24 nn^2 in all.  FP16 subnormals add an absolute
-            // 2^-25 per element in scaled units: 2^-24 sqrt(D) nn 2^-e on the value ranked by.  With
-            // nkb = ceil((D + 1) / 32) K blocks the accumulator takes 6 nkb partial sums: the bound
-            // scales with nkb.
+            // 3 x FP16 dot product of rows scaled by 2^e.  A bound that does not lean on how the tensor core
+            // accumulates (that is undocumented): with v = hi + lo + r, |r| <= 2^-22 |v| (two roundings to an 11-bit
+            // significand), the computed  hi.hi' + hi.lo' + lo.hi'  differs from q.c by
+            //   the two representation residues and the dropped lo.lo' term   <= 3 x 2^-22 |q||c|
+            //   FP32 accumulation: the 16-bit x 16-bit products are exact in FP32; if EVERY one of the 96 nkb
+            //   additions into the accumulator rounded (or truncated: one ulp) on a partial sum <= |q||c|   <= 96 nkb 2^-23 |q||c|
+            // (measured, tools/tc_probe16.cu: 2^-21.9 |q||c|, forty times less).  The ranked value is -2 x that, its norm
+            // column carries 2^-22 ||c||^2, the write-out rounds twice more: with |q||c| <= nn^2 / 4 the sum is below
+            // (2 (3 x 2^-22 + 96 nkb 2^-23) / 4 + 2^-21) nn^2 <= 128 nkb 2^-24 nn^2.  FP16 subnormals add an
+            // absolute 2^-25 per element in scaled units: 2^-24 sqrt(D) nn 2^-e on the value ranked by.
             const double nn = (sqrt(n2) + sqrt((double)fmaxf(stats[0], stats[2]))) * 1.000001;
             const double floor_term = ldexp(sqrt((double)D) * nn, -24 - gmd_tc_exponent(stats[0], stats[2]));
-            const double e2 = 64.0 * ((D + 32) / 32) * U32 * nn * nn + floor_term;
+            const double e2 = 128.0 * ((D + 32) / 32) * U32 * nn * nn + floor_term;
             lower = sqrt(fmax(tau - e2, 0.0)) - 1.01 * U32 * nn;
         } else if (form == GMD_FORM_DIRECT_L2) {
             const double nn = (sqrt(n2) + sqrt((double)stats[0])) * 1.000001;

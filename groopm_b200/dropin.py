@@ -141,6 +141,10 @@ class KDTree:
 
         if self._dev_data is None:
             self._dev_data = torch.from_numpy(self.data).to(engine._device())
+        if single and self.n <= engine._lib.lib().gmd_knn_small_max_candidates():
+            # one vector against a small tree (refine.py:664-665 calls this once per bin): staging buffers are kept,
+            # the call is a 24-byte copy, one kernel launch (gmd_knn_small_f64) and one read-back
+            return self._query_one(xq, int(k), kk)
         # the tree's points stay on the device; only the query rows travel (refine.py:664-665 calls this once
         # per bin in a Python loop)
         xd = torch.from_numpy(np.ascontiguousarray(xq)).to(self._dev_data.device)
@@ -155,6 +159,43 @@ class KDTree:
         if single:
             return dist[0], idx[0]
         return dist, idx
+
+
+def _kdtree_query_one(self, xq, k, kk):
+    import torch
+
+    dev = self._dev_data.device
+    st = getattr(self, "_one", None)
+    if st is None or st[0] != kk:
+        st = self._one = (kk, torch.empty((1, self.m), dtype=torch.float64, pin_memory=True),
+                          torch.empty((1, self.m), dtype=torch.float64, device=dev),
+                          torch.empty(3 * kk + 2, dtype=torch.float64, device=dev),      # dist [kk] | idx, flag (as int32)
+                          torch.empty(3 * kk + 2, dtype=torch.float64, pin_memory=True))
+    _, v_host, v_dev, out_dev, out_host = st
+    v_host.numpy()[:] = xq
+    with torch.cuda.device(dev):
+        v_dev.copy_(v_host, non_blocking=True)
+        base = out_dev.data_ptr()
+        engine._lib.check(engine._lib.lib().gmd_knn_small_f64(
+            v_dev.data_ptr(), 1, self._dev_data.data_ptr(), self.n, self.m, kk, engine._lib.L2,
+            base + 8 * kk, base, base + 8 * kk + 4 * kk, engine._stream_ptr()))
+        out_host.copy_(out_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    raw = out_host.numpy()
+    dist = raw[:kk].copy()
+    ints = raw[kk:].view(np.int32)
+    idx = ints[:kk].astype(np.intp)
+    if int(ints[kk]):
+        raise FloatingPointError("non-finite value in an input profile")
+    if kk < k:  # scipy pads missing neighbours with (inf, n)
+        dist = np.concatenate([dist, np.full(k - kk, np.inf)])
+        idx = np.concatenate([idx, np.full(k - kk, self.n, dtype=np.intp)])
+    if k == 1:
+        return dist[0], idx[0]
+    return dist, idx
+
+
+KDTree._query_one = _kdtree_query_one
 
 
 def k_dist(bin_k_vals):

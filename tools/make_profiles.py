@@ -50,7 +50,7 @@ def launches(csv_path, out_path, cmd):
         lines.append(f"| `{k}` | {a[0]} | {a[1] / 1e6:.3f} | {100 * a[1] / tot:.2f} % | {a[2]} | {a[3]} |")
     lines += ["", f"Total device time in the capture: {tot / 1e6:.1f} ms over {sum(a[0] for a in agg.values())} launches.", ""]
     Path(out_path).write_text("\n".join(lines))
-    print("\n".join(lines))
+    print(f"wrote {out_path}")
 
 
 WANT = OrderedDict([
@@ -127,7 +127,7 @@ def full(rep, out_path, workload, cmd):
             out.append(f"| {op} | {o[0]:.3g} | {100 * o[0] / ti:.1f} % | {100 * o[1] / tot:.1f} % |")
         out.append("")
     Path(out_path).write_text("\n".join(out))
-    print("\n".join(out))
+    print(f"wrote {out_path}")
     if workload and traffic is not None:
         tj = ROOT / "profiles" / "scan_traffic.json"
         d = json.loads(tj.read_text()) if tj.exists() else {}
