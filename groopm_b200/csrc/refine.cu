@@ -65,7 +65,15 @@ __device__ __forceinline__ bool key_less(double da, uint32_t ia, double db, uint
 
 // G lanes per query row (G = 32, or 8 when there are at most 8 proposals per row: the k = 1
 // scan), 32 / G rows per warp.
-template <int G>
+//
+// NCH > 0 (G = 16, D even, D <= 32 NCH, rows 16-byte aligned) reads the candidate rows ACROSS the lanes of a
+// group instead of one row per lane.  The gather of one row per lane is bound by the L1 tag stage (ncu, 1 M x 40
+// proposals x 30 dimensions: l1tex 94 % busy, 13 sectors per request, one tag look-up per 16 bytes loaded = 15 per
+// row); with lane p loading the 16 bytes of dimension pair p a row costs the 2-3 lines it spans.  The lane that
+// loads a pair also holds the query's pair in registers and forms the term ((a - b)^2 or |a - b|); the terms of 16
+// rows go through shared memory (row stride an odd number of 16-byte units: conflict-free both ways) to the lane
+// that owns the row, which adds them in dimension order -- the same operations in the same order as dist64.
+template <int G, int NCH, int METRIC>
 __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ Q, long long Nq,
                                                      const double* __restrict__ C, int D,
                                                      const double* __restrict__ center, int k, int kk, int nsplit,
@@ -106,7 +114,83 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
         for (int sp = sl; sp < nsplit; sp += G) tau32 = fminf(tau32, cand_tau[(size_t)q * nsplit + sp]);
     for (int o = G / 2; o > 0; o >>= 1) tau32 = fminf(tau32, __shfl_xor_sync(FULL, tau32, o));
 
-    {
+    if constexpr (NCH > 0) {
+        static_assert(NCH == 0 || G == 16, "the row-across-lanes gather is written for 16 lanes per query");
+        const int P = D >> 1;                          // dimension pairs per row
+        const int PS2 = 2 * (P | 1);                   // row stride of the term block, doubles
+        size_t off = ((size_t)nslots * m * 3 + 1) / 2 * sizeof(double);
+        off = (off + 15) & ~(size_t)15;
+        double* tt = reinterpret_cast<double*>(sm_raw + off) + (size_t)slot * 16 * PS2;
+        // lanes past the last pair (and empty proposals, and dead groups) load a valid address and drop the result
+        double2 qv[NCH];
+        const char* cb[NCH];
+        unsigned keep[NCH];
+        unsigned tw[NCH];
+        const unsigned rowb = (unsigned)D * 8u;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int pp = sl + 16 * ch;
+            keep[ch] = pp < P ? 1u : 0u;
+            const int pc = keep[ch] ? pp : P - 1;
+            qv[ch] = *reinterpret_cast<const double2*>(qrow + 2 * pc);
+            cb[ch] = reinterpret_cast<const char*>(C + 2 * pc);
+            tw[ch] = (unsigned)__cvta_generic_to_shared(tt + 2 * pc);
+        }
+        const float* cv = cand_val + (size_t)(live ? q : 0) * m;
+        for (int b0 = 0; b0 < m; b0 += 16) {
+            uint32_t my = GMD_EMPTY_IDX;
+            if (live && b0 + sl < m) {
+                my = ci[b0 + sl];
+                if (nsplit > 1 && my != GMD_EMPTY_IDX && cv[b0 + sl] > tau32) my = GMD_EMPTY_IDX;
+            }
+            const uint32_t my_row = my == GMD_EMPTY_IDX ? 0u : my;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (b0 + 8 * h >= m) break;            // uniform
+                double2 v[8][NCH];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned long long ro =
+                        (unsigned long long)__shfl_sync(FULL, my_row, 8 * h + j, 16) * (unsigned long long)rowb;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)   // volatile: all the loads of a half issue before its first store
+                        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];"
+                                     : "=d"(v[j][ch].x), "=d"(v[j][ch].y) : "l"(cb[ch] + ro));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        const double t0 = __dsub_rn(qv[ch].x, v[j][ch].x), t1 = __dsub_rn(qv[ch].y, v[j][ch].y);
+                        const double2 w = METRIC == GMD_L2 ? make_double2(__dmul_rn(t0, t0), __dmul_rn(t1, t1))
+                                                           : make_double2(fabs(t0), fabs(t1));
+                        // predicated, not branched around: the lanes past the last pair did the same arithmetic
+                        asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.v2.f64 [%1], {%2, %3}; }"
+                                     :: "r"(keep[ch]), "r"(tw[ch] + (unsigned)((8 * h + j) * PS2 * 8)), "d"(w.x), "d"(w.y)
+                                     : "memory");
+                    }
+                }
+            }
+            __syncwarp();
+            double d = CUDART_INF;
+            if (my != GMD_EMPTY_IDX) {
+                const double2* row = reinterpret_cast<const double2*>(tt + (size_t)sl * PS2);
+                double acc = 0.0;
+#pragma unroll 5
+                for (int pp = 0; pp < P; ++pp) {
+                    const double2 w = row[pp];
+                    acc = __dadd_rn(acc, w.x);
+                    acc = __dadd_rn(acc, w.y);
+                }
+                d = METRIC == GMD_L2 ? sqrt(acc) : acc;
+            }
+            if (live && b0 + sl < m) {
+                sd[b0 + sl] = d;
+                si[b0 + sl] = my;
+            }
+            __syncwarp();
+        }
+    } else {
         if (live) {
             const float* cv = cand_val + (size_t)q * m;
             for (int x = sl; x < m; x += G) {
@@ -125,8 +209,70 @@ __global__ void __launch_bounds__(128) refine_kernel(const double* __restrict__ 
         __syncwarp();
     }
 
+    // ---- ranks.  Fast path: a lane keeps its (up to four) entries in registers and counts, for every entry of the
+    // row, the distances strictly below its own; if the counts of the real entries are all different (an OR of
+    // one bit per count) no two distances tie and the count IS the rank by (distance, index).  Rows with equal
+    // distances (duplicate contigs) and rows with more than 64 proposals take the general loop.
     double kth = CUDART_INF;
-    if (live) {
+    bool ranked = false;
+    if (m <= 4 * G && m <= 64) {
+        double dx[4];
+        uint32_t ix[4];
+        int rk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = sl + j * G;
+            const bool in = live && x < m;
+            dx[j] = in ? sd[x] : CUDART_INF;
+            ix[j] = in ? si[x] : GMD_EMPTY_IDX;
+            rk[j] = 0;
+        }
+        const int nx = (m + G - 1) / G;                // uniform
+        if (nx <= 2) {
+#pragma unroll 4
+            for (int y = 0; y < m; ++y) {
+                const double dy = sd[y];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) rk[j] += dy < dx[j] ? 1 : 0;
+            }
+        } else if (nx == 3) {
+#pragma unroll 4
+            for (int y = 0; y < m; ++y) {
+                const double dy = sd[y];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) rk[j] += dy < dx[j] ? 1 : 0;
+            }
+        } else {
+#pragma unroll 4
+            for (int y = 0; y < m; ++y) {
+                const double dy = sd[y];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rk[j] += dy < dx[j] ? 1 : 0;
+            }
+        }
+        unsigned long long mask = 0ull;
+        int real = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (ix[j] != GMD_EMPTY_IDX) mask |= 1ull << rk[j], ++real;
+        unsigned lo = (unsigned)mask, hi = (unsigned)(mask >> 32);
+        for (int o = G / 2; o > 0; o >>= 1) {
+            lo |= __shfl_xor_sync(FULL, lo, o);
+            hi |= __shfl_xor_sync(FULL, hi, o);
+            real += __shfl_xor_sync(FULL, real, o);
+        }
+        ranked = __popc(lo) + __popc(hi) == real;      // uniform inside the group
+        if (ranked && live) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (ix[j] != GMD_EMPTY_IDX && rk[j] < k) {
+                    out_idx[(size_t)q * k + rk[j]] = (int32_t)ix[j];
+                    out_dist[(size_t)q * k + rk[j]] = dx[j];
+                    if (rk[j] == k - 1) kth = dx[j];
+                }
+        }
+    }
+    if (live && !ranked) {
         for (int x = sl; x < m; x += G) {
             const double d = sd[x];
             const uint32_t idx = si[x];
@@ -439,10 +585,28 @@ extern "C" int gmd_refine_topk_order_f64(const double* Q, int64_t Nq, const doub
         const int g = atoi(env);
         if (g == 8 || g == 16 || g == 32) G = g;
     }
+    // rows read across the lanes of a group (see refine_kernel): even D up to 64, 16-byte aligned rows
+    int nch = 0;
+    // (not for the k = 1 scan's 8 proposals: half the lanes of a group would idle; measured slower)
+    if (m > 8 && D % 2 == 0 && D <= 64 && ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(C)) % 16) == 0)
+        nch = D <= 32 ? 1 : 2;
+    if (const char* env = getenv("GMD_REFINE_ACROSS"))  // developer switch
+        if (atoi(env) == 0) nch = 0;
+    if (nch) G = 16;
     const int rows_per_block = wpb * (32 / G);
-    const size_t smem = (size_t)rows_per_block * kk * nsplit * (sizeof(double) + sizeof(uint32_t));
+    size_t smem = (size_t)rows_per_block * kk * nsplit * (sizeof(double) + sizeof(uint32_t));
+    if (nch) {
+        smem = ((size_t)rows_per_block * m * 3 + 1) / 2 * sizeof(double);
+        smem = (smem + 15) & ~(size_t)15;
+        smem += (size_t)rows_per_block * 16 * 2 * ((D / 2) | 1) * sizeof(double);
+    }
     GMD_REQUIRE(smem <= 200 * 1024, GMD_ERR_UNSUPPORTED, "refine: kk*nsplit=%d too large", kk * nsplit);
-    auto kern = G == 8 ? refine_kernel<8> : (G == 16 ? refine_kernel<16> : refine_kernel<32>);
+    const bool l2 = metric == GMD_L2;
+    auto kern = nch == 1 ? (l2 ? refine_kernel<16, 1, GMD_L2> : refine_kernel<16, 1, GMD_L1>)
+              : nch == 2 ? (l2 ? refine_kernel<16, 2, GMD_L2> : refine_kernel<16, 2, GMD_L1>)
+              : G == 8   ? refine_kernel<8, 0, -1>
+              : G == 16  ? refine_kernel<16, 0, -1>
+                         : refine_kernel<32, 0, -1>;
     GMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nslots = qorder ? nqpos : Nq;
     GMD_REQUIRE(nslots > 0, GMD_ERR_BAD_ARG, "refine: empty query order");
