@@ -260,6 +260,41 @@ extern "C" int gmd_tc_stage_grouped_ext_f64(const double* Q, int64_t Nq, const d
                          nearest_idx, nearest_dist, out, stream);
 }
 
+// A staging (gmd_tc_stage_grouped_f64 / _ext_) whose queries were a run of the candidates' rows keeps the
+// candidates' side in the workspace: leaders, nearest-leader keys, order, tiles, balls.  This call re-stages only
+// the QUERY side for another run of the same length (Q = C + r0 * D): keys of the run -> padded order -> query
+// tiles and their balls.  A caller that streams results back to the host walks the rows in runs this way, so
+// that the copy of one run's results overlaps the scan of the next (engine.knn on host arrays).
+extern "C" int gmd_tc_restage_queries_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                                          const double* center, const float* stats_c, const float* stats_q,
+                                          void* qtiles, void* workspace, size_t workspace_bytes, gmd_grouped* g,
+                                          void* stream) {
+    GMD_REQUIRE(Q && C && center && stats_c && stats_q && qtiles && workspace && g, GMD_ERR_BAD_ARG,
+                "restage_queries: null pointer");
+    GMD_REQUIRE(Nq > 0 && Nc > 0 && D >= 1 && D <= GMD_MAX_D, GMD_ERR_BAD_ARG, "restage_queries: bad sizes");
+    int64_t q_row0;
+    GMD_REQUIRE(relation_of(Q, Nq, C, Nc, D, &q_row0) == 1 && !g->same, GMD_ERR_BAD_ARG,
+                "restage_queries: the queries must be a run of the candidates' rows, as in the staging before");
+    Layout L = carve(workspace, Nq, Nc, D, 1);
+    GMD_REQUIRE(L.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "restage_queries: workspace %zu B < required %zu B",
+                workspace_bytes, L.bytes);
+    GMD_REQUIRE(g->perm_c == L.perm_c && g->perm_q == L.perm_q && g->ngroups >= 1 && g->ngroups <= L.cap,
+                GMD_ERR_BAD_ARG, "restage_queries: the descriptor does not belong to this workspace and shape");
+    const int TM = gmd_tc::TM;
+    const int nlead = g->ngroups;
+    const int64_t npos_q = gmd_group_positions(Nq, nlead, TM);
+    const int nt_q = (int)(L.cap_pos_q / TM);
+    int rc;
+    if ((rc = gmd_group_order(L.idx_c + q_row0, L.dist_c + q_row0, Nq, nlead, L.info, TM, L.key_q, nullptr, L.perm_q,
+                              npos_q, L.gstart_q, L.tgroup_q, L.order_ws, L.order_ws_bytes, stream)) != GMD_OK)
+        return rc;
+    if ((rc = gmd_prep_tc_grouped_f64(Q, npos_q, D, center, 0, stats_c, stats_q, L.perm_q, qtiles, L.tmeta_q, nt_q,
+                                      stream)) != GMD_OK)
+        return rc;
+    g->npos_q = npos_q;
+    return GMD_OK;
+}
+
 extern "C" int gmd_scan_tc_grouped_f32(const void* qtiles, const void* ctiles, int D, int kk, int64_t c_index_offset,
                                        const float* stats_c, const float* stats_q, const gmd_grouped* g,
                                        uint32_t* cand_idx, float* cand_val, float* cand_tau, void* stream) {

@@ -260,22 +260,43 @@ class KnnPipeline:
                                               self.form, self.kk, self.nsplit, 0, _ptr(self.cand_idx),
                                               _ptr(self.cand_val), _ptr(self.cand_tau), _stream_ptr()))
 
-    def refine(self, q: torch.Tensor, c: torch.Tensor):
+    def refine(self, q: torch.Tensor, c: torch.Tensor, out=None):
         # after a pruned scan the queries are re-ranked in their staging order (candidate rows stay in L2)
         qorder, nqpos = (self.grouped.perm_q, self.grouped.npos_q) if self.prune else (0, 0)
+        out_idx, out_dist = out or (self.out_idx, self.out_dist)
         _lib.check(self.lib.gmd_refine_topk_order_f64(
             _ptr(q), self.nq, _ptr(c), self.nc, self.d, _ptr(self.center), self.k, self.kk, self.nsplit,
             self.metric, self.form, _ptr(self.cand_idx), _ptr(self.cand_val), _ptr(self.cand_tau), _ptr(self.stats),
-            _ptr(self.out_idx), _ptr(self.out_dist), _ptr(self.flags) + 4, _ptr(self.fail_rows), qorder, nqpos,
+            _ptr(out_idx), _ptr(out_dist), _ptr(self.flags) + 4, _ptr(self.fail_rows), qorder, nqpos,
             _stream_ptr()))
 
-    def exact_rows(self, q: torch.Tensor, c: torch.Tensor):
+    def exact_rows(self, q: torch.Tensor, c: torch.Tensor, out=None):
+        out_idx, out_dist = out or (self.out_idx, self.out_dist)
         _lib.check(self.lib.gmd_exact_rows_f64(
             _ptr(q), self.nq, _ptr(c), self.nc, self.d, self.k, self.metric, _ptr(self.flags) + 4,
-            _ptr(self.fail_rows), _ptr(self.out_idx), _ptr(self.out_dist), _ptr(self.exact_ws),
+            _ptr(self.fail_rows), _ptr(out_idx), _ptr(out_dist), _ptr(self.exact_ws),
             self.exact_ws.numel() * 4, _stream_ptr()))
 
-    def run(self, q: torch.Tensor, c: torch.Tensor):
+    def run_next(self, q: torch.Tensor, c: torch.Tensor, out=None):
+        """The pipeline again for ANOTHER run of ``c``'s rows of the same length (``q = c[r0:r0 + nq]``) after a
+        ``run`` whose queries were such a run: the candidates' staging is kept, only the query side is staged
+        (gmd_tc_restage_queries_f64), then scan -> refine -> exact rows into ``out`` (default: the pipeline's)."""
+        if not self.prune or self.same:
+            raise ValueError("run_next needs the pruned scan with queries that are a run of the candidates' rows")
+        if tuple(q.shape) != (self.nq, self.d) or q.dtype != torch.float64 or not q.is_contiguous():
+            raise ValueError(f"q: expected contiguous float64 [{self.nq}, {self.d}]")
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.gmd_zero_async(_ptr(self.flags) + 4, 4, _stream_ptr()))   # the rejected-row count
+            _lib.check(self.lib.gmd_tc_restage_queries_f64(
+                _ptr(q), self.nq, _ptr(c), self.nc, self.d, _ptr(self.center), _ptr(self.stats), _ptr(self.stats) + 8,
+                _ptr(self.qtiles), _ptr(self.grouped_ws), self.grouped_ws.numel(), C.byref(self.grouped),
+                _stream_ptr()))
+            self.scan()
+            self.refine(q, c, out)
+            self.exact_rows(q, c, out)
+        return out or (self.out_idx, self.out_dist)
+
+    def run(self, q: torch.Tensor, c: torch.Tensor, out=None):
         """q [Nq, D], c [Nc, D] float64 on this pipeline's device -> (out_idx, out_dist) device tensors."""
         for name, t, n in (("q", q, self.nq), ("c", c, self.nc)):
             if t.device != self.dev or t.dtype != torch.float64 or not t.is_contiguous() or tuple(t.shape) != (n, self.d):
@@ -293,9 +314,9 @@ class KnnPipeline:
                 self.scan_events.append((e0, e1))
             else:
                 self.scan()
-            self.refine(q, c)
-            self.exact_rows(q, c)
-        return self.out_idx, self.out_dist
+            self.refine(q, c, out)
+            self.exact_rows(q, c, out)
+        return out or (self.out_idx, self.out_dist)
 
     # -- diagnostics (synchronise)
     def exact_row_count(self) -> int:
@@ -409,6 +430,10 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
             if bad:
                 raise FloatingPointError("non-finite value in an input profile")
             return idx, dist
+        if q_np and same and form is None and not return_info and order is None and prune is None:
+            streamed = _knn_streamed(qd, k, metric, dev)
+            if streamed is not None:
+                return streamed
         pipe = _pipeline(qd.shape[0], cd.shape[0], qd.shape[1], k, metric, form, same, dev, order, prune)
         idx, dist = pipe.run(qd, cd)
         if q_np:
@@ -426,6 +451,57 @@ def knn(q, c=None, k: int = 1, metric="euclidean", form: Optional[int] = None, d
                            "nsplit": pipe.nsplit, "ordered": pipe.order, "pruned": pipe.prune,
                            **({"prune": pipe.prune_stats()} if pipe.prune else {})},)
         return out
+
+
+STREAM_MIN_ROWS = 262144  # all-pairs problems on host arrays from this size on return their results in runs
+STREAM_RUNS = 4
+
+
+def _knn_streamed(xd: torch.Tensor, k: int, metric, dev, runs: int = STREAM_RUNS, min_rows: int = STREAM_MIN_ROWS):
+    """All-pairs k-NN of device rows ``xd`` with the results going to pinned host arrays while the scan is still
+    running: the rows are walked in ``runs`` runs (queries = a run of the candidates' rows, the candidates staged
+    once), and the device-to-host copy of a run's indices and distances (12 k bytes per row: 384 MB at 1 M rows,
+    k = 32 -- as long as the whole scan) overlaps the next run's scan and re-rank on a second stream.  Same values
+    as one pass (every row's result is the exact one).  None if the shape is not one for the pruned scan."""
+    n, d = xd.shape
+    runs = int(runs)
+    if runs < 2 or n < max(int(min_rows), 2 * runs):
+        return None
+    lib = _lib.lib()
+    m = -(-n // runs)
+    if not (lib.gmd_use_tc_scan(m, n, k, _metric(metric), d) and lib.gmd_use_tc_prune(m, n, k, _metric(metric), d)):
+        return None
+    pipe = _pipeline(m, n, d, k, metric, None, False, dev, None, None)
+    if not pipe.prune:
+        return None
+    if getattr(pipe, "_stream_out", None) is None:
+        pipe._stream_out = [(torch.empty_like(pipe.out_idx), torch.empty_like(pipe.out_dist)) for _ in range(2)]
+        pipe._stream_copy = torch.cuda.Stream(device=dev)
+    idx_h = torch.empty((n, k), dtype=torch.int32, pin_memory=True)
+    dist_h = torch.empty((n, k), dtype=torch.float64, pin_memory=True)
+    main = torch.cuda.current_stream()
+    copied = [None, None]
+    for i in range(runs):
+        r0 = min(i * m, n - m)                 # the last run overlaps its predecessor instead of being shorter
+        out = pipe._stream_out[i & 1]
+        if copied[i & 1] is not None:
+            main.wait_event(copied[i & 1])     # the buffers of run i - 2 must have left the device
+        q = xd[r0:r0 + m]
+        (pipe.run if i == 0 else pipe.run_next)(q, xd, out)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(pipe._stream_copy):
+            pipe._stream_copy.wait_event(done)
+            idx_h[r0:r0 + m].copy_(out[0], non_blocking=True)
+            dist_h[r0:r0 + m].copy_(out[1], non_blocking=True)
+            copied[i & 1] = torch.cuda.Event()
+            copied[i & 1].record(pipe._stream_copy)
+    flags_h = _host_copy(pipe.flags)
+    main.synchronize()
+    pipe._stream_copy.synchronize()
+    if int(flags_h[0]):
+        raise FloatingPointError("non-finite value in an input profile")
+    return idx_h.numpy(), dist_h.numpy()
 
 
 SMALL_BMU_ROWS = 256     # up to this many vectors go to the one-launch float64 kernel

@@ -251,6 +251,12 @@ GMD_API int gmd_tc_stage_grouped_ext_f64(const double* Q, int64_t Nq, const doub
                      const double* center, const float* stats_c, const float* stats_q, void* qtiles, void* ctiles,
                      void* workspace, size_t workspace_bytes, int32_t nlead, const int32_t* nearest_idx,
                      const double* nearest_dist, gmd_grouped* out, void* stream);
+/* Re-stages only the QUERY side of a staging whose queries were a run of the candidates' rows, for another run of
+ * the same length (Q = C + r0 * D): the candidates' order, tiles and balls stay.  For callers that walk the rows
+ * in runs so that the copy-out of one run overlaps the scan of the next.                                     */
+GMD_API int gmd_tc_restage_queries_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
+                     const double* center, const float* stats_c, const float* stats_q, void* qtiles,
+                     void* workspace, size_t workspace_bytes, gmd_grouped* g, void* stream);
 GMD_API int gmd_scan_tc_prune_f32(const void* qtiles, int64_t Nq_pos, const void* ctiles, int64_t Nc_pos, int D, int kk,
                      int64_t c_index_offset, const float* stats_c, const float* stats_q,
                      const uint32_t* perm_q, const uint32_t* perm_c, const int32_t* tgroup_q,

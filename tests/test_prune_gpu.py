@@ -182,6 +182,34 @@ def test_cfg5_1m_what_the_bench_times(cuda):
     rows = np.sort(np.random.default_rng(5).choice(n, 2048, replace=False))
     od, oi = par_oracle.knn(x[rows], x, k)
     assert np.array_equal(idx[rows].cpu().numpy(), oi) and np.array_equal(dist[rows].cpu().numpy(), od)
+    # the end-to-end call bench.py times (host arrays in and out: the rows walked in runs, copies overlapped)
+    del pipe, full, idx0, dist0
+    engine.clear_cache()
+    hi, hd = engine.knn(x, k=k)
+    assert np.array_equal(hi, idx.cpu().numpy()) and np.array_equal(hd, dist.cpu().numpy())
+
+
+@pytest.mark.parametrize("kind,n,d,k,runs", [
+    ("clusters", 140001, 30, 32, 4), ("ties", 20001, 12, 16, 3), ("uniform", 9000, 8, 5, 2), ("outliers", 30011, 30, 32, 7),
+])
+def test_results_streamed_in_runs_equal_one_pass(cuda, monkeypatch, kind, n, d, k, runs):
+    """engine.knn on host arrays walks the rows in runs (candidates staged once, the query side re-staged per run:
+    gmd_tc_restage_queries_f64) and copies a run's results out while the next is scanned: same indices and
+    distances as one pass over all rows, ragged last run included; a sample against the oracle."""
+    monkeypatch.setenv("GMD_TC", "1")
+    monkeypatch.setenv("GMD_TC_PRUNE", "1")
+    engine.clear_cache()
+    x = _layout(kind, n, d, np.random.default_rng(zlib.crc32(kind.encode()) + n))
+    xd = torch.from_numpy(x).cuda()
+    got = engine._knn_streamed(xd, k, "euclidean", xd.device, runs=runs, min_rows=0)
+    assert got is not None
+    idx, dist, info = engine.knn(xd, k=k, return_info=True)
+    assert info["pruned"]
+    assert np.array_equal(got[0], idx.cpu().numpy()) and np.array_equal(got[1], dist.cpu().numpy())
+    rows = np.sort(np.random.default_rng(1).choice(n, 512, replace=False))
+    od, oi = par_oracle.knn(x[rows], x, k)
+    assert np.array_equal(got[0][rows], oi) and np.array_equal(got[1][rows], od)
+    engine.clear_cache()
 
 
 # ------------------------------------------------------------------ the certificate under attack
