@@ -189,69 +189,79 @@ __global__ void __launch_bounds__(256) adjacency_kernel(const float* __restrict_
     }
 }
 
-// The greedy pass over the n samples of list (null: 0..n-1), one block: 32 rows of the bit matrix are staged in
-// shared memory at a time, then warp 0 decides them in order -- sample i is a leader iff no bit of row i below
-// column i meets the leader mask.  New leaders are appended to L / lead_row from info[0] on.
+// The greedy pass over the n samples of list (null: 0..n-1), one block.  Sample i is a leader iff no bit of row i
+// of the bit matrix below column i meets the mask of the leaders so far.  Warp 0 decides a chunk of 32 samples
+// at a time from shared memory while the other warps fetch the next chunk into the second buffer (one block
+// barrier per chunk, no global-memory round trip on the sequential path):
+//   lane r scans row r against the leaders of the EARLIER chunks, all 32 rows side by side;
+//   what is left is the chunk's own 32 x 32 block: a 32-step loop on registers (row r's word by shuffle,
+//   the chunk's leader bits in a uniform register).
+// The leaders' rows are copied by the whole block once all decisions are made.  New leaders are appended to
+// L / lead_row from info[0] on.
 __global__ void __launch_bounds__(LEAD_THREADS) resolve_kernel(const float* __restrict__ S, const int32_t* __restrict__ list,
                                                               const int32_t* __restrict__ n_dev, int n_max, int D,
                                                               const uint32_t* __restrict__ bits, int wpr, int cap,
                                                               long long stride, float* __restrict__ L,
-                                                              int32_t* __restrict__ lead_row, int32_t* __restrict__ info,
+                                                              int32_t* lead_row, int32_t* __restrict__ info,
                                                               int pass) {
     extern __shared__ uint32_t rsm[];
+    const int pitch = wpr | 1;                           // odd row pitch: lane r reading word w of row r is conflict-free
     uint32_t* mask = rsm;                                // [wpr] leaders among the samples decided so far
-    uint32_t* chunk = rsm + wpr;                         // [32][wpr]
-    __shared__ int picked[32];
-    __shared__ int npicked, nlead_s;
+    uint32_t* chunk = rsm + wpr;                         // [2][32][pitch]
+    __shared__ int nlead_s;
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     const int tid = threadIdx.x, lane = tid & 31;
+    const int base = info[0];
     for (int w = tid; w < wpr; w += LEAD_THREADS) mask[w] = 0u;
-    if (tid == 0) nlead_s = info[0];
-    __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += 32) {
+    if (tid == 0) nlead_s = base;
+    auto fetch = [&](int i0, uint32_t* buf, int t0, int nt) {
         const int nr = min(32, n - i0);
-        const int nwords = (i0 + nr + 31) >> 5;          // columns below the chunk's last row
-        for (int e = tid; e < nr * nwords; e += LEAD_THREADS) {
+        const int nwords = (i0 >> 5) + 1;                // columns up to the chunk's own word
+        for (int e = t0; e < nr * nwords; e += nt) {
             const int r = e / nwords, w = e - r * nwords;
-            chunk[r * wpr + w] = bits[(size_t)(i0 + r) * wpr + w];
+            buf[r * pitch + w] = bits[(size_t)(i0 + r) * wpr + w];
         }
-        if (tid == 0) npicked = 0;
-        __syncthreads();
-        if (tid < 32) {
+    };
+    if (n > 0) fetch(0, chunk, tid, LEAD_THREADS);
+    __syncthreads();
+    int nl = base;                                       // warp 0's running count (the same in all its lanes)
+    for (int i0 = 0, c = 0; i0 < n; i0 += 32, ++c) {
+        const uint32_t* cur = chunk + (size_t)(c & 1) * 32 * pitch;
+        if (tid >= 32) {
+            if (i0 + 32 < n) fetch(i0 + 32, chunk + (size_t)((c + 1) & 1) * 32 * pitch, tid - 32, LEAD_THREADS - 32);
+        } else if (nl < cap) {
+            const int nr = min(32, n - i0), wc = i0 >> 5;
+            const uint32_t* row = cur + lane * pitch;
+            uint32_t hit = 0u;
+#pragma unroll 4
+            for (int w = 0; w < wc; ++w) hit |= row[w] & mask[w];
+            const uint32_t own = lane < nr ? (row[wc] & ((1u << lane) - 1u)) : 0u;
+            const uint32_t cand = __ballot_sync(0xFFFFFFFFu, lane < nr && hit == 0u);
+            uint32_t lm = 0u;
+            int room = cap - nl;
             for (int r = 0; r < nr; ++r) {
-                const int i = i0 + r;
-                if (nlead_s + npicked >= cap) break;
-                bool near = false;
-                for (int w = lane; w * 32 < i; w += 32) {
-                    uint32_t m = mask[w];
-                    if (w == (i >> 5)) m &= (1u << (i & 31)) - 1u;      // columns below i only
-                    near |= (chunk[r * wpr + w] & m) != 0u;
-                }
-                if (__any_sync(0xFFFFFFFFu, near)) continue;
-                if (lane == 0) {
-                    mask[i >> 5] |= 1u << (i & 31);
-                    picked[npicked] = i;
-                    npicked = npicked + 1;
-                }
-                __syncwarp();
+                const uint32_t o = __shfl_sync(0xFFFFFFFFu, own, r);
+                if (((cand >> r) & 1u) && (o & lm) == 0u && room > 0) lm |= 1u << r, --room;
             }
+            if ((lm >> lane) & 1u)
+                lead_row[nl + __popc(lm & ((1u << lane) - 1u))] =
+                    (int32_t)((long long)(list ? list[i0 + lane] : i0 + lane) * stride);
+            if (lane == 0) mask[wc] = lm;
+            nl += __popc(lm);
+            if (lane == 0) nlead_s = nl;
         }
-        __syncthreads();
-        // the chunk's new leaders: rows copied by everybody
-        const int np = npicked, base = nlead_s;
-        for (int e = tid; e < np * D; e += LEAD_THREADS) {
-            const int x = e / D, d = e - x * D;
-            const int si = list ? list[picked[x]] : picked[x];
-            L[(size_t)(base + x) * D + d] = S[(size_t)si * D + d];
-            if (d == 0) lead_row[base + x] = (int32_t)((long long)si * stride);
-        }
-        __syncthreads();
-        if (tid == 0) nlead_s = base + np;
         __syncthreads();
     }
+    // the new leaders' rows (lead_row holds sample index x stride, written above by this block)
+    const int total = nlead_s;
+    for (int e = tid; e < (total - base) * D; e += LEAD_THREADS) {
+        const int x = e / D, d = e - x * D;
+        const long long si = (long long)lead_row[base + x] / stride;
+        L[(size_t)(base + x) * D + d] = S[(size_t)si * D + d];
+    }
     if (tid == 0) {
-        info[0] = nlead_s;
-        if (pass == 0) info[2] = nlead_s;
+        info[0] = total;
+        if (pass == 0) info[2] = total;
     }
 }
 
@@ -472,7 +482,7 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
         const int wpr = (n_max + 31) / 32;
         adjacency_kernel<<<(unsigned)((n_max + 7) / 8), 256, adj_smem, st>>>(S, lst, n_dev, n_max, D, info, bits, wpr);
         GMD_CUDA_CHECK(cudaGetLastError());
-        const size_t rs = (size_t)33 * wpr * sizeof(uint32_t);
+        const size_t rs = ((size_t)wpr + 64 * (size_t)(wpr | 1)) * sizeof(uint32_t);
         GMD_CUDA_CHECK(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         resolve_kernel<<<1, LEAD_THREADS, rs, st>>>(S, lst, n_dev, n_max, D, bits, wpr, cap, stride, L, lead_row, info, which);
         GMD_CUDA_CHECK(cudaGetLastError());
