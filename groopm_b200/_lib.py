@@ -65,6 +65,8 @@ SIGNATURES = {
                                           C.POINTER(_vp), _vp]),
     "gmd_tc_stage_grouped_ext_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.c_int32,
                                             _vp, _vp, _vp, _vp]),
+    "gmd_assign_leaders_f64": (_int, [_vp, _i64, _vp, _int, _int, _vp, _vp, _vp, _sz, _vp]),
+    "gmd_pick_proposal_f64": (_int, [_vp, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "gmd_tc_restage_queries_f64": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "gmd_scan_tc_prune_f32": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp,
                                      _int, _vp, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),

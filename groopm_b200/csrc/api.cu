@@ -114,9 +114,8 @@ extern "C" int gmd_scan_topk_f32(const float* qtiles, int64_t Nq, const float* c
     return GMD_ERR_BAD_ARG;
 }
 
-extern "C" int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc, int D,
-                                int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
-                                void* stream) {
+static int scan_bmu(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc, int D, int64_t c_index_offset,
+                    uint32_t* cand_idx, float* cand_val, float* cand_tau, uint32_t* best1, void* stream) {
     GMD_REQUIRE(qtiles && ctiles && cand_idx && cand_val && cand_tau, GMD_ERR_BAD_ARG, "bmu scan: null pointer");
     GMD_REQUIRE(Nq > 0 && Nc > 0 && Nc + c_index_offset < 0xFFFFFFFFll && Nc < (1ll << 29), GMD_ERR_BAD_ARG,
                 "bmu scan: bad sizes");
@@ -135,7 +134,14 @@ extern "C" int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ct
     p.cand_idx = cand_idx;
     p.cand_val = cand_val;
     p.cand_tau = cand_tau;
+    p.best1 = best1;
     return gmd_bmu_launch(DP, p, (cudaStream_t)stream);
+}
+
+extern "C" int gmd_scan_bmu_f32(const float* qtiles, int64_t Nq, const float* ctiles, int64_t Nc, int D,
+                                int64_t c_index_offset, uint32_t* cand_idx, float* cand_val, float* cand_tau,
+                                void* stream) {
+    return scan_bmu(qtiles, Nq, ctiles, Nc, D, c_index_offset, cand_idx, cand_val, cand_tau, nullptr, stream);
 }
 
 // ------------------------------------------------------------------ workspace layout
@@ -266,6 +272,36 @@ extern "C" int gmd_knn_f64(const double* Q, int64_t Nq, const double* C, int64_t
         GMD_CUDA_CHECK(cudaMemcpyAsync(info + 1, w.flags, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     }
     return GMD_OK;
+}
+
+// A leader for every row (the grouped staging of the pruned scan): the FP32 best-matching-unit scan's best
+// proposal and the exact float64 distance to it -- no re-rank, no certificate: the staging needs a good,
+// deterministic assignment with the true distance to the ASSIGNED leader (its balls are built from that), not the
+// proven nearest one.  Outside the BMU scan's range of D: the exact k = 1 pipeline.  Workspace:
+// gmd_knn_workspace_bytes(N, nlead, D, 1).
+extern "C" int gmd_assign_leaders_f64(const double* X, int64_t N, const double* L, int nlead, int D, int32_t* out_idx,
+                                      double* out_dist, void* workspace, size_t workspace_bytes, void* stream) {
+    GMD_REQUIRE(X && L && out_idx && out_dist && workspace, GMD_ERR_BAD_ARG, "assign_leaders: null pointer");
+    GMD_REQUIRE(N > 0 && nlead >= 1 && D >= 1 && D <= GMD_MAX_D, GMD_ERR_BAD_ARG, "assign_leaders: bad sizes");
+    if (!gmd_use_bmu_scan(1, GMD_L2, D))
+        return gmd_knn_f64(X, N, L, nlead, D, 1, GMD_L2, GMD_FORM_AUTO, out_idx, out_dist, workspace, workspace_bytes,
+                           nullptr, stream);
+    const int kk = gmd_scan::BMU_KK;
+    Workspace w = carve(workspace, N, nlead, D, kk, 1, false);
+    GMD_REQUIRE(w.bytes <= workspace_bytes, GMD_ERR_WORKSPACE, "assign_leaders: workspace %zu B < required %zu B",
+                workspace_bytes, w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    GMD_CUDA_CHECK(cudaMemsetAsync(w.stats, 0, sizeof(float) * 4, st));
+    GMD_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, sizeof(int32_t) * 4, st));
+    int rc;
+    if ((rc = gmd_col_mean_f64(L, nlead, D, w.center, stream)) != GMD_OK) return rc;
+    if ((rc = gmd_prep_f64(L, nlead, D, w.center, GMD_FORM_EXPANDED, w.ctiles, w.stats, w.flags, stream)) != GMD_OK) return rc;
+    if ((rc = gmd_prep_f64(X, N, D, w.center, GMD_FORM_EXPANDED, w.qtiles, w.stats + 2, w.flags, stream)) != GMD_OK) return rc;
+    // (the scan also names the best candidate of the winning cell, by its own FP32 arithmetic: fail_rows as scratch)
+    uint32_t* best1 = (uint32_t*)w.fail_rows;
+    if ((rc = scan_bmu(w.qtiles, N, w.ctiles, nlead, D, 0, w.cand_idx, w.cand_val, w.cand_tau, best1, stream)) != GMD_OK)
+        return rc;
+    return gmd_pick_proposal_f64(X, N, L, D, 1, best1, w.cand_val, out_idx, out_dist, stream);
 }
 
 // ------------------------------------------------------------------ host-level drop-ins

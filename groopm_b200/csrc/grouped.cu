@@ -183,10 +183,10 @@ static int stage_grouped(const double* Q, int64_t Nq, const double* C, int64_t N
         if ((rc = gmd_group_leaders_f64(C, Nc, D, center, L.ns, L.cap, 2.0f, L.Lt, L.lead_row, L.lead_rows, L.info,
                                         L.lead_ws, L.lead_ws_bytes, &nlead, stream)) != GMD_OK)
             return rc;
-        // nearest leader (+ exact float64 distance to it) of every candidate row, and of the queries if they
+        // a leader (+ exact float64 distance to it) for every candidate row, and for the queries if they
         // are rows of their own
-        if ((rc = gmd_knn_f64(C, Nc, L.lead_rows, nlead, D, 1, GMD_L2, GMD_FORM_AUTO, L.idx_c, L.dist_c, L.knn_ws,
-                              L.knn_ws_bytes, nullptr, stream)) != GMD_OK)
+        if ((rc = gmd_assign_leaders_f64(C, Nc, L.lead_rows, nlead, D, L.idx_c, L.dist_c, L.knn_ws, L.knn_ws_bytes,
+                                         stream)) != GMD_OK)
             return rc;
     }
     const int64_t npos_c = gmd_group_positions(Nc, nlead, TM);
@@ -200,8 +200,8 @@ static int stage_grouped(const double* Q, int64_t Nq, const double* C, int64_t N
         const int32_t* idx_q = L.idx_c + q_row0;
         const double* dist_q = L.dist_c + q_row0;
         if (relation == 0) {
-            if ((rc = gmd_knn_f64(Q, Nq, L.lead_rows, nlead, D, 1, GMD_L2, GMD_FORM_AUTO, L.idx_q, L.dist_q, L.knn_ws,
-                                  L.knn_ws_bytes, nullptr, stream)) != GMD_OK)
+            if ((rc = gmd_assign_leaders_f64(Q, Nq, L.lead_rows, nlead, D, L.idx_q, L.dist_q, L.knn_ws, L.knn_ws_bytes,
+                                             stream)) != GMD_OK)
                 return rc;
             idx_q = L.idx_q;
             dist_q = L.dist_q;

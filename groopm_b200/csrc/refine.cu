@@ -554,7 +554,40 @@ __global__ void __launch_bounds__(EX_THREADS) exact_rows_kernel(const double* __
     }
 }
 
+// One proposal per row, no certificate: the lowest (FP32 value, index) of the row's m proposals and the float64
+// distance to THAT candidate (scipy's arithmetic).  For callers that need a good assignment with an exact distance
+// to it, not the proven nearest (the grouped staging: any assignment gives valid balls).
+__global__ void __launch_bounds__(256) pick_kernel(const double* __restrict__ X, long long N,
+                                                   const double* __restrict__ C, int D, int m,
+                                                   const uint32_t* __restrict__ cand_idx,
+                                                   const float* __restrict__ cand_val, int32_t* __restrict__ out_idx,
+                                                   double* __restrict__ out_dist) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    float bv = CUDART_INF_F;
+    uint32_t bi = GMD_EMPTY_IDX;
+    for (int x = 0; x < m; ++x) {
+        const uint32_t i = cand_idx[(size_t)q * m + x];
+        const float v = cand_val[(size_t)q * m + x];
+        if (i != GMD_EMPTY_IDX && (bi == GMD_EMPTY_IDX || v < bv || (v == bv && i < bi))) bv = v, bi = i;
+    }
+    if (bi == GMD_EMPTY_IDX) bi = 0;                   // (cannot happen with at least one candidate)
+    out_idx[q] = (int32_t)bi;
+    out_dist[q] = dist64(X + (size_t)q * D, C + (size_t)bi * D, D, GMD_L2);
+}
+
 }  // namespace
+
+extern "C" int gmd_pick_proposal_f64(const double* X, int64_t N, const double* C, int D, int m,
+                                     const uint32_t* cand_idx, const float* cand_val, int32_t* out_idx,
+                                     double* out_dist, void* stream) {
+    GMD_REQUIRE(X && C && cand_idx && cand_val && out_idx && out_dist && N > 0 && D >= 1 && m >= 1, GMD_ERR_BAD_ARG,
+                "pick_proposal: bad arguments");
+    pick_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, N, C, D, m, cand_idx, cand_val, out_idx,
+                                                                             out_dist);
+    GMD_CUDA_CHECK(cudaGetLastError());
+    return GMD_OK;
+}
 
 extern "C" int gmd_refine_topk_order_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D,
                                          const double* center, int k, int kk, int nsplit, int metric, int form,

@@ -96,6 +96,7 @@ struct ScanParams {
     uint32_t* cand_idx;
     float* cand_val;
     float* cand_tau;
+    uint32_t* best1 = nullptr;   // BMU scan only, optional: [Nq] the winning cell's best candidate (FP32 arithmetic)
 };
 
 // Per-query running top-kk set: a 4-ary MAX-heap of u64 keys in shared memory (root = current
@@ -785,6 +786,27 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_bmu_kernel(const ScanPa
             p.cand_idx[ob] = real ? li + (uint32_t)p.c_index_offset : GMD_EMPTY_IDX;
             p.cand_val[ob] = real ? fmaxf(b1 + qnv, 0.0f) : INF;
             if (lc == 0) p.cand_tau[q] = (b2 < INF) ? fmaxf(b2 + qnv, 0.0f) : INF;
+        }
+        if (p.best1) {
+            // which of the winning cell's 8 candidates it was: lane lc recomputes candidate lc from the tile in
+            // global memory (L1/L2 hits: callers with a few hundred candidates), 3 shuffles pick the minimum
+            // (every lane of the warp takes part; rows past Nq compute on tile 0 and write nothing)
+            const uint32_t wt = k1 >> 3, wl = k1 & 7u;
+            const uint32_t li = wt * GMD_TW + (wl << 2) + (((uint32_t)lc >> 2) << 5) + ((uint32_t)lc & 3u);
+            const float* ct = p.ctiles + (size_t)wt * TILE_F + (li - wt * GMD_TW);
+            const float* qc = Qs + (warp >> 1) * TILE_F + (warp & 1) * 32 + ql;   // already scaled by -2
+            float v = ct[D * GMD_TW];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v = fmaf(qc[d * GMD_TW], ct[d * GMD_TW], v);
+            v = ((long long)li < p.Nc && b1 < INF) ? v : INF;
+            uint32_t bi = li;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const float ov = __shfl_xor_sync(FULL, v, o);
+                const uint32_t oi = __shfl_xor_sync(FULL, bi, o);
+                if (ov < v || (ov == v && oi < bi)) v = ov, bi = oi;
+            }
+            if (lc == 0 && q < p.Nq) p.best1[q] = bi + (uint32_t)p.c_index_offset;
         }
     }
 }

@@ -65,23 +65,29 @@ _ASSIGN_PIPES: dict = {}
 
 
 def _nearest_leader_sharded(lead: torch.Tensor, full: torch.Tensor, r0: int, r1: int, group):
-    """(index, float64 distance) of every row's nearest leader, every rank searching its own rows
-    [r0, r1) with the engine's k = 1 pipeline; two all-gathers put the shards together."""
-    from .engine import KnnPipeline
+    """(leader index, float64 distance to it) of every row, every rank assigning its own rows [r0, r1) with the
+    library's own assignment (gmd_assign_leaders_f64: the same call the single-GPU staging makes); two
+    all-gathers put the shards together."""
+    from . import _lib
+    from .engine import _ptr, _stream_ptr
 
     n, d = full.shape
     dev = full.device
-    if r1 > r0:
-        key = (r1 - r0, lead.shape[0], d, str(dev))
-        pipe = _ASSIGN_PIPES.get(key)
-        if pipe is None:
+    m = r1 - r0
+    idx = torch.empty(m, dtype=torch.int32, device=dev)
+    dd = torch.empty(m, dtype=torch.float64, device=dev)
+    if m > 0:
+        lib = _lib.lib()
+        lead = lead.contiguous()
+        key = (m, lead.shape[0], d, str(dev))
+        ws = _ASSIGN_PIPES.get(key)
+        if ws is None:
             _ASSIGN_PIPES.clear()                     # the number of leaders is stable for a data set: keep one
-            pipe = _ASSIGN_PIPES[key] = KnnPipeline(r1 - r0, lead.shape[0], d, 1, "euclidean", same=False, device=dev)
-        idx, dd = pipe.run(full[r0:r1], lead.contiguous())
-        idx, dd = idx.reshape(-1), dd.reshape(-1)
-    else:
-        idx = torch.empty(0, dtype=torch.int32, device=dev)
-        dd = torch.empty(0, dtype=torch.float64, device=dev)
+            ws = _ASSIGN_PIPES[key] = torch.empty(lib.gmd_knn_workspace_bytes(m, lead.shape[0], d, 1),
+                                                  dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gmd_assign_leaders_f64(_ptr(full[r0:r1]), m, _ptr(lead), lead.shape[0], d, _ptr(idx),
+                                                  _ptr(dd), _ptr(ws), ws.numel(), _stream_ptr()))
     return gather_rows(idx, n, group).contiguous(), gather_rows(dd, n, group).contiguous()
 
 

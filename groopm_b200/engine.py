@@ -348,11 +348,11 @@ class KnnPipeline:
     def launches_per_run(self) -> int:
         # the exact stage is three kernels: batched pass, its finish, one-row-per-block remainder
         if self.prune:
-            # col_mean, norms x1/2; leaders (samples, nearest sample, leader clustering, leader rows);
-            # nearest-leader search (col_mean, prep x2, scan, refine, exact x3); grouped sort (keys,
-            # histogram, padded scan, scatter, tile groups) once or twice; prep x2, group balls; scan,
-            # refine, exact x3.  (Queries that are no rows of the candidates add a second search: + 8.)
-            return (2 if self.same else 3) + 4 + 8 + 5 + 2 + 1 + 5 + (0 if self.same else 5)
+            # col_mean, norms x1/2; leaders (samples, nearest sample, radius, 2 x (bit matrix, greedy pass), cover,
+            # uncovered, leader rows: 10); assignment (col_mean, prep x2, BMU scan, pick: 5); grouped sort (keys,
+            # histogram, padded scan, scatter, tile groups: 5) once or twice; prep x2, group balls; scan, refine,
+            # exact x3.  (Queries that are no rows of the candidates add a second assignment, not counted.)
+            return (2 if self.same else 3) + 10 + 5 + 5 + 2 + 1 + 5 + (0 if self.same else 5)
         if self.tc:
             # col_mean, norms x1/2, prep x2, scan, refine, exact x3 (+ the key pipeline and 3 sort kernels)
             extra = (self.key_pipe.launches_per_run + 3) if self.order else 0

@@ -251,6 +251,13 @@ GMD_API int gmd_tc_stage_grouped_ext_f64(const double* Q, int64_t Nq, const doub
                      const double* center, const float* stats_c, const float* stats_q, void* qtiles, void* ctiles,
                      void* workspace, size_t workspace_bytes, int32_t nlead, const int32_t* nearest_idx,
                      const double* nearest_dist, gmd_grouped* out, void* stream);
+/* A leader for every row: best proposal of the FP32 best-matching-unit scan plus the exact float64 distance to it
+ * (no re-rank or certificate: the grouped staging needs a good deterministic assignment and the true distance to the
+ * ASSIGNED leader, not the proven nearest).  Workspace: gmd_knn_workspace_bytes(N, nlead, D, 1).            */
+GMD_API int gmd_assign_leaders_f64(const double* X, int64_t N, const double* L, int nlead, int D, int32_t* out_idx,
+                     double* out_dist, void* workspace, size_t workspace_bytes, void* stream);
+GMD_API int gmd_pick_proposal_f64(const double* X, int64_t N, const double* C, int D, int m, const uint32_t* cand_idx,
+                     const float* cand_val, int32_t* out_idx, double* out_dist, void* stream);
 /* Re-stages only the QUERY side of a staging whose queries were a run of the candidates' rows, for another run of
  * the same length (Q = C + r0 * D): the candidates' order, tiles and balls stay.  For callers that walk the rows
  * in runs so that the copy-out of one run overlaps the scan of the next.                                     */
