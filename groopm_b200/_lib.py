@@ -55,6 +55,7 @@ SIGNATURES = {
     "gmd_group_order_workspace_bytes": (_sz, [_int]),
     "gmd_group_order": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "gmd_prep_tc_grouped_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "gmd_prep_tc_grouped_both_f64": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "gmd_tc_group_meta": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "gmd_use_tc_prune": (_int, [_i64, _i64, _int, _int, _int]),
     "gmd_tc_prune_max_tiles": (_sz, [_int, _int]),

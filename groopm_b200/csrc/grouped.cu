@@ -214,12 +214,23 @@ static int stage_grouped(const double* Q, int64_t Nq, const double* C, int64_t N
         tgroup_q = L.tgroup_q;
     }
     const int nt_c = (int)(L.cap_pos_c / TM), nt_q = (int)(L.cap_pos_q / TM);
-    if ((rc = gmd_prep_tc_grouped_f64(C, npos_c, D, center, 1, stats_c, stats_q, L.perm_c, ctiles, L.tmeta_c, nt_c,
-                                      stream)) != GMD_OK)
-        return rc;
-    if ((rc = gmd_prep_tc_grouped_f64(Q, npos_q, D, center, 0, stats_c, stats_q, perm_q, qtiles, L.tmeta_q, nt_q,
-                                      stream)) != GMD_OK)
-        return rc;
+    const float* tmeta_q = L.tmeta_q;
+    int nt_q_out = nt_q;
+    if (relation == 2) {
+        // the same rows in the same order on both sides: one pass writes both roles' tiles and one set of balls
+        if ((rc = gmd_prep_tc_grouped_both_f64(C, npos_c, D, center, stats_c, stats_q, L.perm_c, qtiles, ctiles, L.tmeta_c,
+                                               nt_c, stream)) != GMD_OK)
+            return rc;
+        tmeta_q = L.tmeta_c;
+        nt_q_out = nt_c;
+    } else {
+        if ((rc = gmd_prep_tc_grouped_f64(C, npos_c, D, center, 1, stats_c, stats_q, L.perm_c, ctiles, L.tmeta_c, nt_c,
+                                          stream)) != GMD_OK)
+            return rc;
+        if ((rc = gmd_prep_tc_grouped_f64(Q, npos_q, D, center, 0, stats_c, stats_q, perm_q, qtiles, L.tmeta_q, nt_q,
+                                          stream)) != GMD_OK)
+            return rc;
+    }
     if ((rc = gmd_tc_group_meta(L.Lt, L.grad, nlead, D, stats_c, stats_q, L.gmeta, L.cap, stream)) != GMD_OK)
         return rc;
     GMD_CUDA_CHECK(cudaMemsetAsync(L.counters, 0, 16 * sizeof(uint64_t), st));
@@ -227,7 +238,7 @@ static int stage_grouped(const double* Q, int64_t Nq, const double* C, int64_t N
     out->npos_c = npos_c;
     out->ngroups = nlead;
     out->ng_alloc = L.cap;
-    out->nt_alloc_q = nt_q;
+    out->nt_alloc_q = nt_q_out;
     out->nt_alloc_c = nt_c;
     out->same = relation == 2;
     out->reserved = 0;
@@ -236,7 +247,7 @@ static int stage_grouped(const double* Q, int64_t Nq, const double* C, int64_t N
     out->tgroup_q = tgroup_q;
     out->gstart_c = L.gstart_c;
     out->gmeta = L.gmeta;
-    out->tmeta_q = L.tmeta_q;
+    out->tmeta_q = tmeta_q;
     out->tmeta_c = L.tmeta_c;
     out->counters = L.counters;
     return GMD_OK;

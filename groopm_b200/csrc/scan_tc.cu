@@ -89,21 +89,28 @@ __global__ void __launch_bounds__(256) tc_norms_kernel(const double* __restrict_
 // tmeta (nullable): [D + 1][nt_alloc] ball of the tile in scaled units -- centroid of its real rows and
 // the largest distance of one of them to it, rounded up (-1 for a tile of padding only).  Any centre
 // gives a valid ball; the radius is taken against the centre exactly as stored.
+// The rows of a tile are read from global memory ONCE (a warp per row: coalesced 8 D bytes), kept in shared
+// memory as the scaled FP32 values the images are made of, and everything else -- norms, hi / lo images written
+// as 16-byte chunks (a warp stores 512 contiguous bytes), centroid, radius -- works from there.  role 2 writes
+// both roles' tiles (tiles: queries, tiles2: candidates) for profiles that serve as both.
 __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__ X, long long Npos, int D, int nkb,
                                                       const uint32_t* __restrict__ perm,
                                                       const double* __restrict__ center, int role,
                                                       const float* __restrict__ stats_c, const float* __restrict__ stats_q,
-                                                      unsigned char* __restrict__ tiles, float* __restrict__ tmeta,
-                                                      int nt_alloc) {
+                                                      unsigned char* __restrict__ tiles, unsigned char* __restrict__ tiles2,
+                                                      float* __restrict__ tmeta, int nt_alloc) {
+    extern __shared__ __align__(16) float xs[];          // [TM][P], P = D | 1: conflict-free by row and by column
     __shared__ float s_n2[TM];
     __shared__ long long s_src[TM];                      // row of X, -1 for padding
     __shared__ float s_m[GMD_MAX_D];
     __shared__ int s_cnt, s_rad;
+    const int P = D | 1;
     const float scale = ldexpf(1.0f, gmd_tc_exponent(stats_c[0], stats_q[0]));
     const long long t = blockIdx.x, row0 = t * TM;
-    if (threadIdx.x == 0) s_cnt = 0, s_rad = 0;
-    if (threadIdx.x < TM) {
-        const long long pos = row0 + threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_cnt = 0, s_rad = 0;
+    if (tid < TM) {
+        const long long pos = row0 + tid;
         long long src = -1;
         if (pos < Npos) {
             if (perm) {
@@ -113,71 +120,91 @@ __global__ void __launch_bounds__(256) prep_tc_kernel(const double* __restrict__
                 src = pos;
             }
         }
-        s_src[threadIdx.x] = src;
+        s_src[tid] = src;
+    }
+    __syncthreads();
+    for (int r = warp; r < TM; r += 8) {
+        const long long src = s_src[r];
+        for (int k = lane; k < D; k += 32)
+            xs[r * P + k] = src >= 0 ? (float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale : 0.0f;   // exact: power of two
+    }
+    __syncthreads();
+    if (tid < TM) {
         double n2 = 0.0;
-        if (src >= 0) {
 #pragma unroll 6
-            for (int k = 0; k < D; ++k) {
-                const double v = (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale);
-                n2 += v * v;
+        for (int k = 0; k < D; ++k) {
+            const double v = (double)xs[tid * P + k];
+            n2 += v * v;
+        }
+        s_n2[tid] = (float)n2;
+        if (s_src[tid] >= 0) atomicAdd(&s_cnt, 1);
+    }
+    __syncthreads();
+    // images: item (row r, 16-byte chunk c of K block kb) = 8 consecutive columns; thread = 4 r + c
+    const size_t tb = (size_t)t * tile_bytes(nkb);
+    for (int kb = 0; kb < nkb; ++kb) {
+        for (int it = tid; it < TM * 4; it += 256) {
+            const int r = it >> 2, c = it & 3, k0 = kb * TK + c * 8;
+            const bool real = s_src[r] >= 0;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = k0 + j < D ? xs[r * P + k0 + j] : 0.0f;
+            const int off = (r >> 3) * 512 + (r & 7) * 64 + (((c ^ ((r >> 1) & 3)) & 3) << 4);
+            const bool has_d = D >= k0 && D < k0 + 8;
+            auto put = [&](unsigned char* base, float cold) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const float a = (has_d && k0 + j == D) ? cold : v[j];
+                    const float b = (has_d && k0 + j + 1 == D) ? cold : v[j + 1];
+                    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+                    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+                    hi[j >> 1] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+                    lo[j >> 1] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+                }
+                unsigned char* img = base + tb + (size_t)kb * KB_B + off;
+                *reinterpret_cast<uint4*>(img) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(img + IMG_B) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            };
+            const float qcol = QCOL, ccol = real ? -s_n2[r] / (2.0f * QCOL) : PAD_COL;
+            if (role == 0) {
+                put(tiles, qcol);
+            } else if (role == 1) {
+                put(tiles, ccol);
+            } else {
+                put(tiles, qcol);
+                put(tiles2, ccol);
             }
         }
-        s_n2[threadIdx.x] = (float)n2;
     }
-    __syncthreads();
-    unsigned char* tile = tiles + (size_t)t * tile_bytes(nkb);
-    const int KT = TK * nkb;
-    for (int e = threadIdx.x; e < TM * KT; e += blockDim.x) {
-        const int r = e / KT, k = e - r * KT;
-        const long long src = s_src[r];
-        float v = 0.0f;
-        if (src >= 0) {
-            if (k < D)
-                v = (float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale;   // exact: power of two
-            else if (k == D)
-                v = role == 0 ? QCOL : -s_n2[r] / (2.0f * QCOL);
-        } else if (k == D) {
-            v = role == 0 ? QCOL : PAD_COL;
-        }
-        const __half h = __float2half_rn(v);
-        // K block kb = k / 32; inside it the shared-memory image: 8-row groups of 512 B, 16-byte chunk c
-        // (8 halves) of row r at c ^ ((r >> 1) & 3)
-        const int kb = k >> 5, kk = k & 31;
-        const int off = ((r >> 3) * 512 + (r & 7) * 64 + ((((kk >> 3) ^ ((r >> 1) & 3)) & 3) << 4) + (kk & 7) * 2) >> 1;
-        __half* hi = reinterpret_cast<__half*>(tile + (size_t)kb * KB_B);
-        hi[off] = h;
-        hi[IMG_B / 2 + off] = __float2half_rn(v - __half2float(h));
+    if (tid < TM) {
+        const float nv = s_src[tid] >= 0 ? s_n2[tid] : 0.0f;
+        reinterpret_cast<float*>(tiles + tb + (size_t)nkb * KB_B)[tid] = nv;
+        if (role == 2) reinterpret_cast<float*>(tiles2 + tb + (size_t)nkb * KB_B)[tid] = nv;
     }
-    float* nrm = reinterpret_cast<float*>(tile + (size_t)nkb * KB_B);
-    if (threadIdx.x < TM) nrm[threadIdx.x] = s_src[threadIdx.x] >= 0 ? s_n2[threadIdx.x] : 0.0f;
     if (!tmeta) return;
     // ---- the tile's ball
-    if (threadIdx.x < TM && s_src[threadIdx.x] >= 0) atomicAdd(&s_cnt, 1);
-    __syncthreads();
     const int cnt = s_cnt;
-    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    for (int k = tid; k < D; k += blockDim.x) {
         double sum = 0.0;
-        for (int r = 0; r < TM; ++r) {
-            const long long src = s_src[r];
-            if (src >= 0) sum += (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale);
-        }
+        for (int r = 0; r < TM; ++r)
+            if (s_src[r] >= 0) sum += (double)xs[r * P + k];
         const float m = cnt ? (float)(sum / cnt) : 0.0f;
         s_m[k] = m;
         tmeta[(size_t)k * nt_alloc + t] = m;
     }
     __syncthreads();
-    if (threadIdx.x < TM && s_src[threadIdx.x] >= 0) {
-        const long long src = s_src[threadIdx.x];
+    if (tid < TM && s_src[tid] >= 0) {
         double d2 = 0.0;
 #pragma unroll 6
         for (int k = 0; k < D; ++k) {
-            const double u = (double)((float)(X[(size_t)src * D + k] - (center ? center[k] : 0.0)) * scale) - (double)s_m[k];
+            const double u = (double)xs[tid * P + k] - (double)s_m[k];
             d2 += u * u;
         }
         atomicMax(&s_rad, __float_as_int(__double2float_ru(sqrt(d2) * (1.0 + 1e-9))));
     }
     __syncthreads();
-    if (threadIdx.x == 0) tmeta[(size_t)D * nt_alloc + t] = cnt ? __int_as_float(s_rad) : -1.0f;
+    if (tid == 0) tmeta[(size_t)D * nt_alloc + t] = cnt ? __int_as_float(s_rad) : -1.0f;
 }
 
 // ------------------------------------------------------------------ the scan
@@ -501,18 +528,35 @@ extern "C" int gmd_tc_norms_f64(const double* X, int64_t N, int D, const double*
     return GMD_OK;
 }
 
-extern "C" int gmd_prep_tc_grouped_f64(const double* X, int64_t Npos, int D, const double* center, int role,
-                                       const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
-                                       float* tmeta, int nt_alloc, void* stream) {
+static int prep_tc_launch(const double* X, int64_t Npos, int D, const double* center, int role, const float* stats_c,
+                          const float* stats_q, const uint32_t* perm, void* tiles, void* tiles2, float* tmeta,
+                          int nt_alloc, void* stream) {
     GMD_REQUIRE(X && tiles && stats_c && stats_q && Npos > 0 && D >= 1 && tc_nkb(D) <= gmd_tc::MAX_KB &&
-                    (role == 0 || role == 1),
+                    (role == 0 || role == 1 || (role == 2 && tiles2)),
                 GMD_ERR_BAD_ARG, "prep_tc: bad arguments");
     const unsigned grid = (unsigned)((Npos + gmd_tc::TM - 1) / gmd_tc::TM);
     GMD_REQUIRE(!tmeta || (int64_t)grid <= nt_alloc, GMD_ERR_BAD_ARG, "prep_tc: tile meta too small");
-    gmd_tc::prep_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, Npos, D, tc_nkb(D), perm, center, role, stats_c,
-                                                                  stats_q, (unsigned char*)tiles, tmeta, nt_alloc);
+    const size_t smem = (size_t)gmd_tc::TM * (D | 1) * sizeof(float);
+    GMD_CUDA_CHECK(cudaFuncSetAttribute(gmd_tc::prep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmd_tc::prep_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(X, Npos, D, tc_nkb(D), perm, center, role, stats_c,
+                                                                     stats_q, (unsigned char*)tiles, (unsigned char*)tiles2,
+                                                                     tmeta, nt_alloc);
     GMD_CUDA_CHECK(cudaGetLastError());
     return GMD_OK;
+}
+
+extern "C" int gmd_prep_tc_grouped_f64(const double* X, int64_t Npos, int D, const double* center, int role,
+                                       const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
+                                       float* tmeta, int nt_alloc, void* stream) {
+    GMD_REQUIRE(role == 0 || role == 1, GMD_ERR_BAD_ARG, "prep_tc: bad role %d", role);
+    return prep_tc_launch(X, Npos, D, center, role, stats_c, stats_q, perm, tiles, nullptr, tmeta, nt_alloc, stream);
+}
+
+// one pass for profiles that are queries AND candidates (same rows, same order): both roles' tiles, one set of balls
+extern "C" int gmd_prep_tc_grouped_both_f64(const double* X, int64_t Npos, int D, const double* center,
+                                            const float* stats_c, const float* stats_q, const uint32_t* perm,
+                                            void* qtiles, void* ctiles, float* tmeta, int nt_alloc, void* stream) {
+    return prep_tc_launch(X, Npos, D, center, 2, stats_c, stats_q, perm, qtiles, ctiles, tmeta, nt_alloc, stream);
 }
 
 extern "C" int gmd_prep_tc_perm_f64(const double* X, int64_t N, int D, const double* center, int role,

@@ -230,6 +230,10 @@ GMD_API int gmd_group_order(const int32_t* lead, const double* dist, int64_t N, 
 GMD_API int gmd_prep_tc_grouped_f64(const double* X, int64_t Npos, int D, const double* center, int role,
                      const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
                      float* tmeta, int nt_alloc, void* stream);
+/* one pass for profiles that serve as queries AND candidates (same rows, same order): both roles' tiles, one set of balls */
+GMD_API int gmd_prep_tc_grouped_both_f64(const double* X, int64_t Npos, int D, const double* center,
+                     const float* stats_c, const float* stats_q, const uint32_t* perm, void* qtiles, void* ctiles,
+                     float* tmeta, int nt_alloc, void* stream);
 GMD_API int gmd_tc_group_meta(const float* L, const float* grad, int ngroups, int D, const float* stats_c,
                      const float* stats_q, float* gmeta, int ng_alloc, void* stream);
 GMD_API int gmd_use_tc_prune(int64_t Nq, int64_t Nc, int k, int metric, int D);   /* the size policy of gmd_knn_f64 */
