@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "scan_impl.cuh"
@@ -326,6 +328,78 @@ struct StreamGuard {
 };
 }  // namespace
 
+// Pageable host memory <-> device through two pinned staging halves: the host-side copy of a piece is cut over a
+// few threads (one thread moves ~9 GB/s, the link ~55) and overlaps the DMA of the piece before it.  The halves are
+// allocated once per process (32 MB pinned) and guarded by a mutex: host-level calls copy one at a time.
+namespace {
+constexpr size_t BOUNCE_BYTES = (size_t)16 << 20;
+struct Bounce {
+    std::mutex mu;
+    void* half[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int ensure() {
+        for (int b = 0; b < 2; ++b) {
+            if (!half[b]) GMD_CUDA_CHECK(cudaHostAlloc(&half[b], BOUNCE_BYTES, cudaHostAllocDefault));
+            if (!ev[b]) GMD_CUDA_CHECK(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+        }
+        return GMD_OK;
+    }
+};
+Bounce g_bounce;
+
+void host_copy(void* dst, const void* src, size_t n) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::min<size_t>(std::min<unsigned>(8u, hw), std::max<size_t>(1, n >> 20));   // >= 1 MB per thread
+    if (nt <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t o = t * per;
+        if (o >= n) break;
+        th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, std::min(per, n - o)); });
+    }
+    memcpy(dst, src, std::min(per, n));
+    for (auto& x : th) x.join();
+}
+
+// caller holds g_bounce.mu
+int upload(void* dev, const void* host, size_t n, cudaStream_t st) {
+    Bounce& B = g_bounce;
+    int i = 0;
+    for (size_t o = 0; o < n; o += BOUNCE_BYTES, ++i) {
+        const int b = i & 1;
+        const size_t len = std::min(BOUNCE_BYTES, n - o);
+        if (i >= 2) GMD_CUDA_CHECK(cudaEventSynchronize(B.ev[b]));     // the half's previous piece has left
+        host_copy(B.half[b], (const char*)host + o, len);
+        GMD_CUDA_CHECK(cudaMemcpyAsync((char*)dev + o, B.half[b], len, cudaMemcpyHostToDevice, st));
+        GMD_CUDA_CHECK(cudaEventRecord(B.ev[b], st));
+    }
+    return GMD_OK;
+}
+
+int download(void* host, const void* dev, size_t n, cudaStream_t st) {
+    Bounce& B = g_bounce;
+    const size_t pieces = (n + BOUNCE_BYTES - 1) / BOUNCE_BYTES;
+    for (size_t i = 0; i <= pieces; ++i) {
+        if (i < pieces) {
+            const size_t o = i * BOUNCE_BYTES;
+            GMD_CUDA_CHECK(cudaMemcpyAsync(B.half[i & 1], (const char*)dev + o, std::min(BOUNCE_BYTES, n - o),
+                                           cudaMemcpyDeviceToHost, st));
+            GMD_CUDA_CHECK(cudaEventRecord(B.ev[i & 1], st));
+        }
+        if (i >= 1) {                                                  // the piece before: out of its half
+            const size_t o = (i - 1) * BOUNCE_BYTES;
+            GMD_CUDA_CHECK(cudaEventSynchronize(B.ev[(i - 1) & 1]));
+            host_copy((char*)host + o, B.half[(i - 1) & 1], std::min(BOUNCE_BYTES, n - o));
+        }
+    }
+    return GMD_OK;
+}
+}  // namespace
+
 extern "C" int gmd_knn_host_f64(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int k, int metric,
                                 int32_t* out_idx, double* out_dist) {
     GMD_REQUIRE(Q && C && out_idx, GMD_ERR_BAD_ARG, "knn_host: null pointer");
@@ -340,12 +414,29 @@ extern "C" int gmd_knn_host_f64(const double* Q, int64_t Nq, const double* C, in
     DevBuf dC, dQ, dI, dD, dW, dInfo;
     int rc;
     const size_t cb = (size_t)Nc * D * sizeof(double), qb = (size_t)Nq * D * sizeof(double);
+    // small problems: plain pageable copies (no staging, no lock)
+    const bool staged = cb + (same ? 0 : qb) + (size_t)Nq * k * 12 >= ((size_t)8 << 20);
+    std::unique_lock<std::mutex> lock(g_bounce.mu, std::defer_lock);
+    if (staged) {
+        lock.lock();
+        if ((rc = g_bounce.ensure()) != GMD_OK) return rc;
+    }
+    auto up = [&](void* dev, const void* host, size_t n) -> int {
+        if (staged) return upload(dev, host, n, st);
+        GMD_CUDA_CHECK(cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, st));
+        return GMD_OK;
+    };
+    auto down = [&](void* host, const void* dev, size_t n) -> int {
+        if (staged) return download(host, dev, n, st);
+        GMD_CUDA_CHECK(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, st));
+        return GMD_OK;
+    };
     if ((rc = dC.alloc(cb, st)) != GMD_OK) return rc;
-    GMD_CUDA_CHECK(cudaMemcpyAsync(dC.p, C, cb, cudaMemcpyHostToDevice, st));
+    if ((rc = up(dC.p, C, cb)) != GMD_OK) return rc;
     const double* dq = (const double*)dC.p;
     if (!same) {
         if ((rc = dQ.alloc(qb, st)) != GMD_OK) return rc;
-        GMD_CUDA_CHECK(cudaMemcpyAsync(dQ.p, Q, qb, cudaMemcpyHostToDevice, st));
+        if ((rc = up(dQ.p, Q, qb)) != GMD_OK) return rc;
         dq = (const double*)dQ.p;
     }
     const size_t wsb = gmd_knn_workspace_bytes(Nq, Nc, D, k);
@@ -358,9 +449,8 @@ extern "C" int gmd_knn_host_f64(const double* Q, int64_t Nq, const double* C, in
     if (rc != GMD_OK) return rc;
     int32_t info[2] = {0, 0};
     GMD_CUDA_CHECK(cudaMemcpyAsync(info, dInfo.p, sizeof(info), cudaMemcpyDeviceToHost, st));
-    GMD_CUDA_CHECK(cudaMemcpyAsync(out_idx, dI.p, (size_t)Nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (out_dist)
-        GMD_CUDA_CHECK(cudaMemcpyAsync(out_dist, dD.p, (size_t)Nq * k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if ((rc = down(out_idx, dI.p, (size_t)Nq * k * sizeof(int32_t))) != GMD_OK) return rc;
+    if (out_dist && (rc = down(out_dist, dD.p, (size_t)Nq * k * sizeof(double))) != GMD_OK) return rc;
     GMD_CUDA_CHECK(cudaStreamSynchronize(st));
     GMD_REQUIRE(info[1] == 0, GMD_ERR_NONFINITE, "non-finite value in an input profile");
     return GMD_OK;

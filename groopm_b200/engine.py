@@ -543,16 +543,23 @@ def bmu(nodes, x, device=None, return_dist: bool = False):
     return idx[:, 0]
 
 
-def knn_host(q: np.ndarray, c: Optional[np.ndarray], k: int, metric="euclidean"):
+def knn_host(q: np.ndarray, c: Optional[np.ndarray], k: int, metric="euclidean", out=None):
     """Same result through the pure C-ABI host entry point (no torch involved):
-    host float64 pointers in, host arrays out -- what a ctypes-only caller binds."""
+    host float64 pointers in, host arrays out -- what a ctypes-only caller binds.
+    ``out``: (int32 [nq, k], float64 [nq, k]) C-contiguous arrays to fill instead of new ones."""
     lib = _lib.lib()
     qa = np.ascontiguousarray(q, dtype=np.float64)
     ca = qa if c is None else np.ascontiguousarray(c, dtype=np.float64)
     if qa.ndim != 2 or ca.ndim != 2 or qa.shape[1] != ca.shape[1]:
         raise ValueError("XA and XB must be 2-dimensional with the same number of columns")
-    out_i = np.empty((qa.shape[0], k), dtype=np.int32)
-    out_d = np.empty((qa.shape[0], k), dtype=np.float64)
+    if out is None:
+        out_i = np.empty((qa.shape[0], k), dtype=np.int32)
+        out_d = np.empty((qa.shape[0], k), dtype=np.float64)
+    else:
+        out_i, out_d = out
+        if (out_i.dtype != np.int32 or out_d.dtype != np.float64 or out_i.shape != (qa.shape[0], k)
+                or out_d.shape != (qa.shape[0], k) or not out_i.flags.c_contiguous or not out_d.flags.c_contiguous):
+            raise ValueError("out: expected C-contiguous int32 and float64 arrays of shape (nq, k)")
     _lib.check(lib.gmd_knn_host_f64(qa.ctypes.data, qa.shape[0], ca.ctypes.data, ca.shape[0], qa.shape[1], int(k),
                                     _metric(metric), out_i.ctypes.data, out_d.ctypes.data))
     return out_i, out_d
