@@ -14,6 +14,7 @@ LIB = PKG / "libgmdist.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+FLAGS += os.environ.get("GMD_NVCC_FLAGS", "").split()     # e.g. -DGMD_TC_PROBES for the developer probe build
 
 
 def _stale(target: Path, deps) -> bool:

@@ -229,7 +229,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_tc_kernel(const unsigned cha
                                                               float* __restrict__ cand_val,
                                                               float* __restrict__ cand_tau) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // (an offset from the array, not an integer round trip: the compiler must keep seeing SHARED memory here, or
+    // every access below becomes a generic LD.E / ST.E)
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int nkb = NKB;
     constexpr int TILE_B = tile_bytes(nkb);
     unsigned char* Aimg = base;                          // the CTA's query tile: nkb x (hi, lo) + norms

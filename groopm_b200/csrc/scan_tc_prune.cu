@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
     for (int j = 0; j < QT; ++j) any_tile |= grpq[j] >= 0;
     if (!any_tile) return;                                 // nothing but padding (uniform: before any set-up)
 
-    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // (an offset from the array, not an integer round trip: the compiler must keep seeing SHARED memory here, or
+    // every access below becomes a generic LD.E / ST.E)
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int nkb = NKB;
     constexpr int TILE_B = tile_bytes(nkb);
     const int ns = p.ns, kk = p.kk, KQ = heap8_slots(kk), D = p.D;
@@ -410,7 +412,8 @@ __global__ void __launch_bounds__(prune_threads(QT), 1) scan_tc_prune_kernel(con
                 PROBE_T(d0);
                 PROBE_ADD(5, 1);
                 PROBE_ADD(6, qcnt);
-                const Drain2 ds = drain_fill8(hv, hx, kk, hn, thr, myq, TM, qcnt);
+                PROBE_ADD(7, __reduce_max_sync(FULLW, (unsigned)qcnt));   // the drain lasts as long as its fullest queue
+                const Drain2 ds = drain_fill8(smem_u32(hv), smem_u32(hx), kk, hn, thr, smem_u32(myq), TM * 8, qcnt);
                 thr = ds.thr;
                 hn = ds.hn;
                 qcnt = 0;

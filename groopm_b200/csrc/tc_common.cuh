@@ -228,62 +228,94 @@ __device__ __forceinline__ void argmax8(const float (&c)[8], float& m, int& at) 
     m = bt ? mh : ml;
     at = bt ? ih : il;
 }
-__device__ __forceinline__ void load8(const float* p, float (&c)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
+// The sets and queues live in shared memory, and drain_fill8 is a real function (it is called from a dozen
+// places of the selection loop): through generic pointers its accesses compile to LD.E / ST.E, which resolve the
+// address space on every access and are markedly slower than LDS / STS on the dependent chain of an insertion.
+// So it takes 32-bit shared-window addresses and says .shared itself.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void load8(uint32_t a, float (&c)[8]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "r"(a));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c[4]), "=f"(c[5]), "=f"(c[6]), "=f"(c[7]) : "r"(a + 16));
+}
+__device__ __forceinline__ void load8u(uint32_t a, uint32_t (&c)[8]) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(a));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]) : "r"(a + 16));
+}
+__device__ __forceinline__ void store8(uint32_t a, const float (&c)[8]) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "f"(c[4]), "f"(c[5]), "f"(c[6]), "f"(c[7]) : "memory");
+}
+__device__ __forceinline__ void store8u(uint32_t a, const uint32_t (&c)[8]) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]) : "memory");
 }
 
+// hv / hx: shared-window byte addresses of the thread's value / index arrays (slot s at + 4 s).
 // sift the pair (v, idx) down from node pos, everything in shared memory (building the heap)
-__device__ __forceinline__ void heap8_sift(float* hv, uint32_t* hx, int kk, int pos, float v, uint32_t idx) {
+__device__ __forceinline__ void heap8_sift(uint32_t hv, uint32_t hx, int kk, int pos, float v, uint32_t idx) {
     while (true) {
         const int c = 8 * pos + 1;
         if (c >= kk) break;
         float cv[8];
-        load8(hv + c + 7, cv);
+        load8(hv + 4 * (c + 7), cv);
         float m;
         int at;
         argmax8(cv, m, at);
         if (m <= v) break;
-        hv[pos + 7] = m;
-        hx[pos + 7] = hx[c + at + 7];
+        sts_f32(hv + 4 * (pos + 7), m);
+        sts_u32(hx + 4 * (pos + 7), lds_u32(hx + 4 * (c + at + 7)));
         pos = c + at;
     }
-    hv[pos + 7] = v;
-    hx[pos + 7] = idx;
+    sts_f32(hv + 4 * (pos + 7), v);
+    sts_u32(hx + 4 * (pos + 7), idx);
 }
 
 struct Drain2 {
     float thr;
     int hn;
 };
-// Fold a thread's parked hits (q[r * TM] = (index, value bits)) into its set.  While the set holds fewer
-// than kk entries they are appended; the kk-th one turns the array into a heap (one bottom-up pass).
-// thr: the threshold = the root's value once the set is full (+inf before).  kk <= 72.
-static __device__ __noinline__ Drain2 drain_fill8(float* hv, uint32_t* hx, int kk, int hn, float thr, const uint2* q,
-                                                  int stride, int n) {
+// Fold a thread's parked hits (entry r at q + r * stride bytes = (index, value bits)) into its set.  While the
+// set holds fewer than kk entries they are appended; the kk-th one turns the array into a heap (one bottom-up
+// pass).  thr: the threshold = the root's value once the set is full (+inf before).  kk <= 72.
+static __device__ __noinline__ Drain2 drain_fill8(uint32_t hv, uint32_t hx, int kk, int hn, float thr, uint32_t q,
+                                                  uint32_t stride, int n) {
     int r = 0;
     for (; r < n && hn < kk; ++r) {
-        const uint2 e = q[r * stride];
-        hv[hn + 7] = __uint_as_float(e.y);
-        hx[hn + 7] = e.x;
+        const uint2 e = lds_u32x2(q + r * stride);
+        sts_f32(hv + 4 * (hn + 7), __uint_as_float(e.y));
+        sts_u32(hx + 4 * (hn + 7), e.x);
         if (++hn == kk) {
-            for (int pos = (kk - 2) / 8; pos >= 0; --pos) heap8_sift(hv, hx, kk, pos, hv[pos + 7], hx[pos + 7]);
-            thr = hv[7];
+            for (int pos = (kk - 2) / 8; pos >= 0; --pos)
+                heap8_sift(hv, hx, kk, pos, lds_f32(hv + 4 * (pos + 7)), lds_u32(hx + 4 * (pos + 7)));
+            thr = lds_f32(hv + 28);
         }
     }
     if (r < n) {
         // the heap is live: root and first level in registers for the rest of the drain
-        float rv = hv[7], c[8];
-        uint32_t rx = hx[7], cx[8];
-        load8(hv + 8, c);
-        {
-            const uint4 a = *reinterpret_cast<const uint4*>(hx + 8), b = *reinterpret_cast<const uint4*>(hx + 12);
-            cx[0] = a.x, cx[1] = a.y, cx[2] = a.z, cx[3] = a.w, cx[4] = b.x, cx[5] = b.y, cx[6] = b.z, cx[7] = b.w;
-        }
-        uint2 e = q[r * stride];
+        float rv = lds_f32(hv + 28), c[8];
+        uint32_t rx = lds_u32(hx + 28), cx[8];
+        load8(hv + 32, c);
+        load8u(hx + 32, cx);
+        uint2 e = lds_u32x2(q + r * stride);
         for (; r < n; ++r) {
             const uint2 cur = e;
-            if (r + 1 < n) e = q[(r + 1) * stride];         // the next entry travels while this one is folded
+            if (r + 1 < n) e = lds_u32x2(q + (r + 1) * stride);   // the next entry travels while this one is folded
             const float v = __uint_as_float(cur.y);
             if (!(v < rv)) continue;
             float m;
@@ -304,15 +336,15 @@ static __device__ __noinline__ Drain2 drain_fill8(float* hv, uint32_t* hx, int k
             const int first = 8 * (ch + 1) + 1;             // its own children: nodes first .. first + 7
             if (first < kk) {
                 float g[8];
-                load8(hv + first + 7, g);
+                load8(hv + 4 * (first + 7), g);
                 float gm;
                 int gi;
                 argmax8(g, gm, gi);
                 if (gm > v) {
                     nv = gm;
-                    nx = hx[first + 7 + gi];
-                    hv[first + 7 + gi] = v;
-                    hx[first + 7 + gi] = cur.x;
+                    nx = lds_u32(hx + 4 * (first + 7 + gi));
+                    sts_f32(hv + 4 * (first + 7 + gi), v);
+                    sts_u32(hx + 4 * (first + 7 + gi), cur.x);
                 }
             }
 #pragma unroll
@@ -321,12 +353,10 @@ static __device__ __noinline__ Drain2 drain_fill8(float* hv, uint32_t* hx, int k
                 cx[i] = ch == i ? nx : cx[i];
             }
         }
-        hv[7] = rv;
-        hx[7] = rx;
-        *reinterpret_cast<float4*>(hv + 8) = make_float4(c[0], c[1], c[2], c[3]);
-        *reinterpret_cast<float4*>(hv + 12) = make_float4(c[4], c[5], c[6], c[7]);
-        *reinterpret_cast<uint4*>(hx + 8) = make_uint4(cx[0], cx[1], cx[2], cx[3]);
-        *reinterpret_cast<uint4*>(hx + 12) = make_uint4(cx[4], cx[5], cx[6], cx[7]);
+        sts_f32(hv + 28, rv);
+        sts_u32(hx + 28, rx);
+        store8(hv + 32, c);
+        store8u(hx + 32, cx);
         thr = rv;
     }
     Drain2 st;

@@ -341,7 +341,7 @@ class KnnPipeline:
                 "visited_fraction": visited / max(1, ctas * ntc),
                 # only a -DGMD_TC_PROBES build fills these: thread 0's SM cycles per CTA and phase
                 "probes": {n: c[4 + i] / max(ctas, 1) for i, n in enumerate(
-                    ("wait", "load", "select", "park", "drain", "drains", "entries", "-"))}}
+                    ("wait", "load", "select", "park", "drain", "drains", "entries", "longest"))}}
 
     # launches of the engine's own kernels in one run() (col_mean, prep x1/2, scan, refine, exact)
     @property
