@@ -342,25 +342,35 @@ __global__ void __launch_bounds__(256) group_key_kernel(const int32_t* __restric
         b = 0;
     }
     key[i] = g * NB + b;
-    if (grad && d == d) atomicMax(reinterpret_cast<int*>(grad) + g, __float_as_int(__double2float_ru(d)));
+    if (grad && d == d) {
+        // 500 addresses for a million rows: look first (a stale smaller value only costs the atomic it would have cost)
+        const int bits = __float_as_int(__double2float_ru(d));
+        if (bits > __ldcg(reinterpret_cast<const int*>(grad) + g)) atomicMax(reinterpret_cast<int*>(grad) + g, bits);
+    }
 }
 
 // One block.  Padded starts of a (group, shell) counting sort: group g's rows begin on a tile boundary.
 // start / cursor [nkeys], gstart[ngroups + 1] in TILES; gstart[ngroups] * tile = positions used.
+// A warp per group for the passes over the shells (coalesced reads of its NB <= 64 counts, sums and offsets by
+// shuffles), the block for the running sum over the groups.
+constexpr int SCAN_GROUPS_MAX = 4096;                  // = the cap of gmd_group_params
 __global__ void __launch_bounds__(1024) key_scan_padded_kernel(const int32_t* __restrict__ count, int ngroups, int NB,
                                                                int tile, int32_t* __restrict__ start,
                                                                int32_t* __restrict__ cursor,
                                                                int32_t* __restrict__ gstart) {
+    __shared__ int32_t gt[SCAN_GROUPS_MAX];            // tiles of every group, then their exclusive running sum
     __shared__ int32_t part[1024];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int g = warp; g < ngroups; g += 32) {
+        int32_t c = (lane < NB ? count[g * NB + lane] : 0) + (lane + 32 < NB ? count[g * NB + lane + 32] : 0);
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        if (lane == 0) gt[g] = (c + tile - 1) / tile;
+    }
+    __syncthreads();
     const int per = (ngroups + 1023) / 1024;
     const int a = min(ngroups, tid * per), b = min(ngroups, a + per);
-    int32_t sum = 0;                                   // padded sizes of this thread's groups, in tiles
-    for (int g = a; g < b; ++g) {
-        int32_t c = 0;
-        for (int x = 0; x < NB; ++x) c += count[g * NB + x];
-        sum += (c + tile - 1) / tile;
-    }
+    int32_t sum = 0;
+    for (int g = a; g < b; ++g) sum += gt[g];
     part[tid] = sum;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -371,17 +381,24 @@ __global__ void __launch_bounds__(1024) key_scan_padded_kernel(const int32_t* __
     }
     int32_t run = part[tid] - sum;                     // first tile of this thread's first group
     for (int g = a; g < b; ++g) {
+        const int32_t t = gt[g];
+        gt[g] = run;
         gstart[g] = run;
-        int32_t pos = run * tile, c = 0;
-        for (int x = 0; x < NB; ++x) {
-            start[g * NB + x] = pos;
-            cursor[g * NB + x] = pos;
-            pos += count[g * NB + x];
-            c += count[g * NB + x];
-        }
-        run += (c + tile - 1) / tile;
+        run += t;
     }
     if (tid == 1023) gstart[ngroups] = part[1023];
+    __syncthreads();
+    for (int g = warp; g < ngroups; g += 32) {
+        const int32_t c0 = lane < NB ? count[g * NB + lane] : 0, c1 = lane + 32 < NB ? count[g * NB + lane + 32] : 0;
+        int32_t s0 = c0, s1 = c1;                      // inclusive sums of the two halves of the shells
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t v0 = __shfl_up_sync(0xFFFFFFFFu, s0, o), v1 = __shfl_up_sync(0xFFFFFFFFu, s1, o);
+            if (lane >= o) s0 += v0, s1 += v1;
+        }
+        const int32_t half = __shfl_sync(0xFFFFFFFFu, s0, 31), pos = gt[g] * tile;
+        if (lane < NB) start[g * NB + lane] = cursor[g * NB + lane] = pos + s0 - c0;
+        if (lane + 32 < NB) start[g * NB + lane + 32] = cursor[g * NB + lane + 32] = pos + half + s1 - c1;
+    }
 }
 
 // group of every tile of a grouped order (the group of its first row; -1 for a tile of padding only)
@@ -529,6 +546,8 @@ extern "C" int gmd_group_order(const int32_t* lead, const double* dist, int64_t 
     GMD_REQUIRE(workspace_bytes >= gmd_group_order_workspace_bytes(ngroups), GMD_ERR_WORKSPACE,
                 "group_order: workspace %zu B < required %zu B", workspace_bytes,
                 gmd_group_order_workspace_bytes(ngroups));
+    GMD_REQUIRE(ngroups <= SCAN_GROUPS_MAX && gmd_group_shells() <= 64, GMD_ERR_UNSUPPORTED,
+                "group_order: %d groups exceed %d", ngroups, SCAN_GROUPS_MAX);
     cudaStream_t st = (cudaStream_t)stream;
     const int NB = gmd_group_shells(), nkeys = ngroups * NB;
     int32_t* count = (int32_t*)workspace;              // [nkeys]
