@@ -549,7 +549,7 @@ def engine_arm(args):
         traffic = None
         prof = ROOT / "profiles" / "scan_traffic.json"
         variant = "pruned" if pipe.prune else ("ordered" if pipe.order else "plain")
-        if prof.exists():
+        if prof.exists() and world == 1:                  # the capture is of the single-GPU launch (all query tiles)
             try:
                 traffic = json.loads(prof.read_text()).get(f"{args.workload}:{variant}")
             except (ValueError, OSError):

@@ -89,20 +89,33 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const double* __res
 }
 
 // distance from probe p (sample p * (ns / nprobe)) to its nearest DISTINCT sample; one block per probe
-__global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict__ S, int ns, int D, int nprobe,
-                                                       float* __restrict__ nn) {
-    __shared__ float part[8];
+__global__ void __launch_bounds__(1024) sample_nn_kernel(const float* __restrict__ S, int ns, int D, int nprobe,
+                                                        float* __restrict__ nn) {
+    __shared__ float part[32];
+    __shared__ float as[GMD_MAX_D];
     const int w = blockIdx.x;
     const int p = w * (ns / nprobe);
-    const float* a = S + (size_t)p * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) as[d] = S[(size_t)p * D + d];
+    __syncthreads();
     float best = __int_as_float(0x7f800000);
+    const bool pairs = (D & 1) == 0;                   // rows of an even D are 8-byte aligned
     for (int j = threadIdx.x; j < ns; j += blockDim.x) {
         const float* b = S + (size_t)j * D;
         float d2 = 0.0f;
+        if (pairs) {
+#pragma unroll 5
+            for (int d = 0; d < D; d += 2) {
+                const float2 v = *reinterpret_cast<const float2*>(b + d);
+                const float t0 = as[d] - v.x, t1 = as[d + 1] - v.y;
+                d2 = fmaf(t0, t0, d2);
+                d2 = fmaf(t1, t1, d2);
+            }
+        } else {
 #pragma unroll 6
-        for (int d = 0; d < D; ++d) {
-            const float t = a[d] - b[d];
-            d2 = fmaf(t, t, d2);
+            for (int d = 0; d < D; ++d) {
+                const float t = as[d] - b[d];
+                d2 = fmaf(t, t, d2);
+            }
         }
         if (d2 > 0.0f) best = fminf(best, d2);
     }
@@ -110,7 +123,7 @@ __global__ void __launch_bounds__(256) sample_nn_kernel(const float* __restrict_
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int x = 1; x < 8; ++x) best = fminf(best, part[x]);
+        for (int x = 1; x < (int)(blockDim.x >> 5); ++x) best = fminf(best, part[x]);
         nn[w] = sqrtf(best);
     }
 }
@@ -336,8 +349,9 @@ __global__ void __launch_bounds__(256) group_key_kernel(const int32_t* __restric
     const float R = __int_as_float(info[1]);
     int b = NB - 1;
     if (d == d && R > 0.0f) {
-        const double s = d / ((double)R * GMD_SHELL_WIDTH);
-        b = s < (double)(NB - 1) ? (int)s : NB - 1;
+        // (the shell only orders rows inside a group: single precision is plenty)
+        const float s = (float)d / (R * (float)GMD_SHELL_WIDTH);
+        b = s < (float)(NB - 1) ? (int)s : NB - 1;
     } else if (d == 0.0) {
         b = 0;
     }
@@ -489,7 +503,7 @@ extern "C" int gmd_group_leaders_f64(const double* X, int64_t N, int D, const do
     const long long ne = (long long)ns * D;
     gather_samples_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, stride, ns, D, center, S);
     GMD_CUDA_CHECK(cudaGetLastError());
-    sample_nn_kernel<<<(unsigned)nprobe, 256, 0, st>>>(S, ns, D, nprobe, nn);
+    sample_nn_kernel<<<(unsigned)nprobe, 1024, 0, st>>>(S, ns, D, nprobe, nn);
     GMD_CUDA_CHECK(cudaGetLastError());
     radius_kernel<<<1, LEAD_PROBES, 0, st>>>(nn, nprobe, rfac, info);
     GMD_CUDA_CHECK(cudaGetLastError());

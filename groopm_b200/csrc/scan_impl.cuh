@@ -761,6 +761,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_bmu_kernel(const ScanPa
     }
 
     // ---- merge the records of the 8 lanes (lc) that share each query row
+    uint32_t win[8];                                      // winning cell per row i (the same in the 8 lanes of a row)
+    float wb1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float b1 = best[i], b2 = second[i];
@@ -774,6 +776,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_bmu_kernel(const ScanPa
             k1 = take ? ok1 : k1;
             b1 = take ? ob1 : b1;
         }
+        win[i] = k1;
+        wb1[i] = b1;
         // lane lc proposes candidate j = lc of the winning cell
         const int ql = ((i >> 2) << 4) + (lq << 2) + (i & 3);
         const long long q = q0 + warp * 32 + ql;
@@ -787,25 +791,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_bmu_kernel(const ScanPa
             p.cand_val[ob] = real ? fmaxf(b1 + qnv, 0.0f) : INF;
             if (lc == 0) p.cand_tau[q] = (b2 < INF) ? fmaxf(b2 + qnv, 0.0f) : INF;
         }
-        if (p.best1) {
-            // which of the winning cell's 8 candidates it was: lane lc recomputes candidate lc from the tile in
-            // global memory (L1/L2 hits: callers with a few hundred candidates), 3 shuffles pick the minimum
-            // (every lane of the warp takes part; rows past Nq compute on tile 0 and write nothing)
-            const uint32_t wt = k1 >> 3, wl = k1 & 7u;
-            const uint32_t li = wt * GMD_TW + (wl << 2) + (((uint32_t)lc >> 2) << 5) + ((uint32_t)lc & 3u);
-            const float* ct = p.ctiles + (size_t)wt * TILE_F + (li - wt * GMD_TW);
-            const float* qc = Qs + (warp >> 1) * TILE_F + (warp & 1) * 32 + ql;   // already scaled by -2
-            float v = ct[D * GMD_TW];
+    }
+    if (p.best1) {
+        // which of the winning cell's 8 candidates it was: lane lc recomputes candidate lc of every row's winning
+        // cell from the tile in global memory (L1/L2 hits: callers with a few hundred candidates) -- the 8 rows'
+        // chains side by side -- and 3 shuffles per row pick the minimum (rows past Nq compute on tile 0 and
+        // write nothing; every lane of the warp takes part)
+        float v[8];
+        const float* ct[8];
+        const float* qc[8];
 #pragma unroll
-            for (int d = 0; d < D; ++d) v = fmaf(qc[d * GMD_TW], ct[d * GMD_TW], v);
-            v = ((long long)li < p.Nc && b1 < INF) ? v : INF;
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t wt = win[i] >> 3, wl = win[i] & 7u;
+            ct[i] = p.ctiles + (size_t)wt * TILE_F + (wl << 2) + (((uint32_t)lc >> 2) << 5) + ((uint32_t)lc & 3u);
+            qc[i] = Qs + (warp >> 1) * TILE_F + (warp & 1) * 32 + ((i >> 2) << 4) + (lq << 2) + (i & 3);   // scaled by -2
+            v[i] = ct[i][D * GMD_TW];
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(qc[i][d * GMD_TW], ct[i][d * GMD_TW], v[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t wt = win[i] >> 3, wl = win[i] & 7u;
+            const uint32_t li = wt * GMD_TW + (wl << 2) + (((uint32_t)lc >> 2) << 5) + ((uint32_t)lc & 3u);
+            float vv = ((long long)li < p.Nc && wb1[i] < INF) ? v[i] : INF;
             uint32_t bi = li;
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) {
-                const float ov = __shfl_xor_sync(FULL, v, o);
+                const float ov = __shfl_xor_sync(FULL, vv, o);
                 const uint32_t oi = __shfl_xor_sync(FULL, bi, o);
-                if (ov < v || (ov == v && oi < bi)) v = ov, bi = oi;
+                if (ov < vv || (ov == vv && oi < bi)) vv = ov, bi = oi;
             }
+            const long long q = q0 + warp * 32 + ((i >> 2) << 4) + (lq << 2) + (i & 3);
             if (lc == 0 && q < p.Nq) p.best1[q] = bi + (uint32_t)p.c_index_offset;
         }
     }

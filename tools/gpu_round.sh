@@ -24,7 +24,7 @@ fullcfg2) python tools/ncu_case.py 100000 10 16 > $OUT/plain_case2_$TAG.log 2>&1
    ncu --set full --clock-control none --import-source on -k regex:scan_tc_prune -s 1 -c 1 -f -o $OUT/scan_100k_d10_pruned_$TAG \
     python tools/ncu_case.py 100000 10 16 > $OUT/ncu_full2_$TAG.log 2>&1; echo "ncu full cfg2 rc=$?";;
 refine) python tools/ncu_case.py 1000000 30 32 > /dev/null 2>&1 &&
-   ncu --set full --clock-control none --import-source on -k regex:refine_kernel -s 2 -c 1 -f -o $OUT/refine_1m_$TAG \
+   ncu --set full --clock-control none --import-source on -k regex:refine_kernel -s 1 -c 1 -f -o $OUT/refine_1m_$TAG \
     python tools/ncu_case.py 1000000 30 32 > $OUT/ncu_refine_$TAG.log 2>&1; echo "ncu full refine rc=$?";;
 esac
 done
