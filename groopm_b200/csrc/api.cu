@@ -410,6 +410,21 @@ extern "C" int gmd_knn_host_f64(const double* Q, int64_t Nq, const double* C, in
     StreamGuard sg;
     GMD_CUDA_CHECK(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
     cudaStream_t st = sg.st;
+    {
+        // the device buffers of a call come from the stream-ordered pool; by default the pool hands freed memory
+        // back to the driver at the next synchronisation, and a loop of host-level calls then re-creates ~2 GB of
+        // mappings every time (measured: 65 to 900 ms per call).  Let the pool keep what it has.
+        static std::once_flag once;
+        std::call_once(once, [] {
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        });
+    }
     const bool same = (Q == C && Nq == Nc);
     DevBuf dC, dQ, dI, dD, dW, dInfo;
     int rc;
