@@ -307,30 +307,29 @@ static __device__ __noinline__ Drain2 drain_fill8(uint32_t hv, uint32_t hx, int 
         }
     }
     if (r < n) {
-        // the heap is live: root and first level in registers for the rest of the drain
-        float rv = lds_f32(hv + 28), c[8];
-        uint32_t rx = lds_u32(hx + 28), cx[8];
-        load8(hv + 32, c);
-        load8u(hx + 32, cx);
+        // the heap is live: the root in registers for the rest of the drain; the first level is read back from
+        // shared memory every step (two LDS.128 that issue right behind the previous step's stores) -- keeping it in
+        // registers cost 45 instructions of selects per step for the dynamically indexed update, more than the
+        // round trip it saved on a path that is as much issue- as latency-bound
+        float rv = lds_f32(hv + 28);
+        uint32_t rx = lds_u32(hx + 28);
         uint2 e = lds_u32x2(q + r * stride);
         for (; r < n; ++r) {
             const uint2 cur = e;
             if (r + 1 < n) e = lds_u32x2(q + (r + 1) * stride);   // the next entry travels while this one is folded
             const float v = __uint_as_float(cur.y);
             if (!(v < rv)) continue;
-            float m;
+            float c[8], m;
             int ch;
+            load8(hv + 32, c);
             argmax8(c, m, ch);
             if (m <= v) {                                   // larger than every child: it is the new root
                 rv = v;
                 rx = cur.x;
                 continue;
             }
-            uint32_t mx = cx[0];
-#pragma unroll
-            for (int i = 1; i < 8; ++i) mx = ch == i ? cx[i] : mx;
             rv = m;                                         // the largest child moves up
-            rx = mx;
+            rx = lds_u32(hx + 32 + 4 * ch);
             float nv = v;                                   // what takes that child's place
             uint32_t nx = cur.x;
             const int first = 8 * (ch + 1) + 1;             // its own children: nodes first .. first + 7
@@ -347,16 +346,11 @@ static __device__ __noinline__ Drain2 drain_fill8(uint32_t hv, uint32_t hx, int 
                     sts_u32(hx + 4 * (first + 7 + gi), cur.x);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                c[i] = ch == i ? nv : c[i];
-                cx[i] = ch == i ? nx : cx[i];
-            }
+            sts_f32(hv + 32 + 4 * ch, nv);
+            sts_u32(hx + 32 + 4 * ch, nx);
         }
         sts_f32(hv + 28, rv);
         sts_u32(hx + 28, rx);
-        store8(hv + 32, c);
-        store8u(hx + 32, cx);
         thr = rv;
     }
     Drain2 st;
