@@ -54,6 +54,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_int32), _vp]),
     "gmd_group_order_workspace_bytes": (_sz, [_int]),
     "gmd_group_order": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "gmd_group_order_pad": (_int, [_vp, _vp, _i64, _int, _vp, _int, _int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "gmd_prep_tc_grouped_f64": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "gmd_prep_tc_grouped_both_f64": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "gmd_tc_group_meta": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp]),

@@ -67,7 +67,7 @@ Layout carve(void* base, int64_t Nq, int64_t Nc, int D, int relation) {
     gmd_group_params(Nc, &L.ns, &L.cap);
     const int TM = gmd_tc::TM;
     L.cap_pos_c = gmd_group_positions(Nc, L.cap, TM);
-    L.cap_pos_q = gmd_group_positions(Nq, L.cap, TM);
+    L.cap_pos_q = gmd_group_positions(Nq, L.cap, 2 * TM);   // (query groups may be padded to pairs of tiles)
     L.lead_ws_bytes = gmd_group_leaders_workspace_bytes(L.ns, D);
     L.lead_ws = c.take<char>(L.lead_ws_bytes);
     L.Lt = c.take<float>((size_t)D * L.cap);
@@ -98,6 +98,9 @@ Layout carve(void* base, int64_t Nq, int64_t Nc, int D, int relation) {
     L.bytes = c.off;
     return L;
 }
+
+// tiles a CTA of the pruned scan owns (gmd_scan_tc_prune_f32: two with one K block)
+int query_pad(int D) { return tc_nkb(D) == 1 ? 2 : 1; }
 
 int relation_of(const double* Q, int64_t Nq, const double* C, int64_t Nc, int D, int64_t* q_row0) {
     *q_row0 = -1;
@@ -130,7 +133,7 @@ extern "C" int gmd_use_tc_prune(int64_t Nq, int64_t Nc, int k, int metric, int D
 extern "C" size_t gmd_tc_grouped_tiles_bytes(int64_t N, int64_t Nc, int D) {
     int ns, cap;
     gmd_group_params(Nc, &ns, &cap);
-    return gmd_tc_tiles_bytes(gmd_group_positions(N, cap, gmd_tc::TM), D);
+    return gmd_tc_tiles_bytes(gmd_group_positions(N, cap, 2 * gmd_tc::TM), D);   // enough for pairs of tiles per group
 }
 
 extern "C" size_t gmd_tc_grouped_workspace_bytes(int64_t Nq, int64_t Nc, int D) {
@@ -206,9 +209,13 @@ static int stage_grouped(const double* Q, int64_t Nq, const double* C, int64_t N
             idx_q = L.idx_q;
             dist_q = L.dist_q;
         }
-        npos_q = gmd_group_positions(Nq, nlead, TM);
-        if ((rc = gmd_group_order(idx_q, dist_q, Nq, nlead, L.info, TM, L.key_q, nullptr, L.perm_q, npos_q, L.gstart_q,
-                                  L.tgroup_q, L.order_ws, L.order_ws_bytes, stream)) != GMD_OK)
+        // a query order of its own: groups padded to PAIRS of tiles where the scan gives a CTA two query tiles, so that
+        // no CTA straddles two groups (and walks two windows) -- what happens to half of them once a group holds two
+        // or three query tiles (row-sharded callers, results streamed in runs)
+        const int pad_q = query_pad(D);
+        npos_q = gmd_group_positions(Nq, nlead, TM * pad_q);
+        if ((rc = gmd_group_order_pad(idx_q, dist_q, Nq, nlead, L.info, TM, pad_q, L.key_q, nullptr, L.perm_q, npos_q,
+                                      L.gstart_q, L.tgroup_q, L.order_ws, L.order_ws_bytes, stream)) != GMD_OK)
             return rc;
         perm_q = L.perm_q;
         tgroup_q = L.tgroup_q;
@@ -293,11 +300,12 @@ extern "C" int gmd_tc_restage_queries_f64(const double* Q, int64_t Nq, const dou
                 GMD_ERR_BAD_ARG, "restage_queries: the descriptor does not belong to this workspace and shape");
     const int TM = gmd_tc::TM;
     const int nlead = g->ngroups;
-    const int64_t npos_q = gmd_group_positions(Nq, nlead, TM);
+    const int pad_q = query_pad(D);
+    const int64_t npos_q = gmd_group_positions(Nq, nlead, TM * pad_q);
     const int nt_q = (int)(L.cap_pos_q / TM);
     int rc;
-    if ((rc = gmd_group_order(L.idx_c + q_row0, L.dist_c + q_row0, Nq, nlead, L.info, TM, L.key_q, nullptr, L.perm_q,
-                              npos_q, L.gstart_q, L.tgroup_q, L.order_ws, L.order_ws_bytes, stream)) != GMD_OK)
+    if ((rc = gmd_group_order_pad(L.idx_c + q_row0, L.dist_c + q_row0, Nq, nlead, L.info, TM, pad_q, L.key_q, nullptr,
+                                  L.perm_q, npos_q, L.gstart_q, L.tgroup_q, L.order_ws, L.order_ws_bytes, stream)) != GMD_OK)
         return rc;
     if ((rc = gmd_prep_tc_grouped_f64(Q, npos_q, D, center, 0, stats_c, stats_q, L.perm_q, qtiles, L.tmeta_q, nt_q,
                                       stream)) != GMD_OK)

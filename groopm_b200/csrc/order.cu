@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(256) group_key_kernel(const int32_t* __restric
 // shuffles), the block for the running sum over the groups.
 constexpr int SCAN_GROUPS_MAX = 4096;                  // = the cap of gmd_group_params
 __global__ void __launch_bounds__(1024) key_scan_padded_kernel(const int32_t* __restrict__ count, int ngroups, int NB,
-                                                               int tile, int32_t* __restrict__ start,
+                                                               int tile, int pad, int32_t* __restrict__ start,
                                                                int32_t* __restrict__ cursor,
                                                                int32_t* __restrict__ gstart) {
     __shared__ int32_t gt[SCAN_GROUPS_MAX];            // tiles of every group, then their exclusive running sum
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(1024) key_scan_padded_kernel(const int32_t* __
     for (int g = warp; g < ngroups; g += 32) {
         int32_t c = (lane < NB ? count[g * NB + lane] : 0) + (lane + 32 < NB ? count[g * NB + lane + 32] : 0);
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-        if (lane == 0) gt[g] = (c + tile - 1) / tile;
+        if (lane == 0) gt[g] = ((c + tile - 1) / tile + pad - 1) / pad * pad;   // whole tiles, a multiple of pad of them
     }
     __syncthreads();
     const int per = (ngroups + 1023) / 1024;
@@ -551,9 +551,20 @@ extern "C" int64_t gmd_group_positions(int64_t N, int ngroups, int tile) {
 extern "C" int gmd_group_order(const int32_t* lead, const double* dist, int64_t N, int ngroups, const int32_t* info,
                                int tile, int32_t* key, float* grad, uint32_t* perm, int64_t npos, int32_t* gstart,
                                int32_t* tgroup, void* workspace, size_t workspace_bytes, void* stream) {
+    return gmd_group_order_pad(lead, dist, N, ngroups, info, tile, 1, key, grad, perm, npos, gstart, tgroup, workspace,
+                               workspace_bytes, stream);
+}
+
+// pad: every group takes a multiple of `pad` tiles (a scan whose CTA owns `pad` neighbouring query tiles then never
+// has a CTA straddling two groups); gstart and tgroup stay in units of one tile.
+extern "C" int gmd_group_order_pad(const int32_t* lead, const double* dist, int64_t N, int ngroups, const int32_t* info,
+                                   int tile, int pad, int32_t* key, float* grad, uint32_t* perm, int64_t npos,
+                                   int32_t* gstart, int32_t* tgroup, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
     GMD_REQUIRE(lead && dist && info && key && perm && gstart && tgroup && workspace, GMD_ERR_BAD_ARG,
                 "group_order: null pointer");
-    GMD_REQUIRE(N > 0 && N < 0x7FFFFFFFll && ngroups >= 1 && tile >= 1 && npos >= gmd_group_positions(N, ngroups, tile) &&
+    GMD_REQUIRE(pad >= 1 && pad <= 8, GMD_ERR_BAD_ARG, "group_order: bad pad %d", pad);
+    GMD_REQUIRE(N > 0 && N < 0x7FFFFFFFll && ngroups >= 1 && tile >= 1 && npos >= gmd_group_positions(N, ngroups, tile * pad) &&
                     npos < 0xFFFFFFFFll,
                 GMD_ERR_BAD_ARG, "group_order: bad sizes (N=%lld groups=%d positions=%lld)", (long long)N, ngroups,
                 (long long)npos);
@@ -576,7 +587,7 @@ extern "C" int gmd_group_order(const int32_t* lead, const double* dist, int64_t 
     GMD_CUDA_CHECK(cudaGetLastError());
     key_hist_kernel<<<grid, 256, 0, st>>>(key, N, nkeys, count, bad);
     GMD_CUDA_CHECK(cudaGetLastError());
-    key_scan_padded_kernel<<<1, 1024, 0, st>>>(count, ngroups, NB, tile, start, cursor, gstart);
+    key_scan_padded_kernel<<<1, 1024, 0, st>>>(count, ngroups, NB, tile, pad, start, cursor, gstart);
     GMD_CUDA_CHECK(cudaGetLastError());
     key_scatter_kernel<<<grid, 256, 0, st>>>(key, N, nkeys, cursor, perm);
     GMD_CUDA_CHECK(cudaGetLastError());

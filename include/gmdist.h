@@ -227,6 +227,11 @@ GMD_API size_t gmd_group_order_workspace_bytes(int ngroups);
 GMD_API int gmd_group_order(const int32_t* lead, const double* dist, int64_t N, int ngroups, const int32_t* info,
                      int tile, int32_t* key, float* grad, uint32_t* perm, int64_t npos, int32_t* gstart,
                      int32_t* tgroup, void* workspace, size_t workspace_bytes, void* stream);
+/* the same with every group padded to a multiple of `pad` tiles (gstart / tgroup stay in units of one tile; positions:
+ * gmd_group_positions(N, ngroups, tile * pad)): for scans whose CTA owns `pad` neighbouring query tiles */
+GMD_API int gmd_group_order_pad(const int32_t* lead, const double* dist, int64_t N, int ngroups, const int32_t* info,
+                     int tile, int pad, int32_t* key, float* grad, uint32_t* perm, int64_t npos, int32_t* gstart,
+                     int32_t* tgroup, void* workspace, size_t workspace_bytes, void* stream);
 GMD_API int gmd_prep_tc_grouped_f64(const double* X, int64_t Npos, int D, const double* center, int role,
                      const float* stats_c, const float* stats_q, const uint32_t* perm, void* tiles,
                      float* tmeta, int nt_alloc, void* stream);
