@@ -20,6 +20,7 @@ the profiles and D2H of the neighbour indices + distances inside the timed regio
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import json
 import os
 import statistics
@@ -87,6 +88,46 @@ def emit(line: dict):
     else:
         sys.stdout.flush()
         os.write(_REAL_STDOUT, text.encode())
+
+
+class Watchdog:
+    """Every leg of the single-GPU bench gets a generous deadline.  If one does not finish (a hung kernel, a copy
+    that never returns), the thread stacks go to stderr and the JSON line is printed with what was measured BEFORE
+    that leg -- the headline number is the first thing measured -- plus a "watchdog" key naming the leg; then the
+    process leaves without tearing CUDA down.  A run that finishes normally never sees it."""
+
+    def __init__(self):
+        self.line = None
+        self.name = "start-up"
+        self.deadline = time.monotonic() + 600.0
+        self.done = False
+
+    def start(self):
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def leg(self, name: str, seconds: float):
+        self.name = name
+        self.deadline = time.monotonic() + seconds
+
+    def _run(self):
+        while not self.done:
+            time.sleep(0.5)
+            if self.done or time.monotonic() <= self.deadline:
+                continue
+            try:
+                faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+            except Exception:                                    # noqa: BLE001 -- nothing may stop the line
+                pass
+            msg = f"leg '{self.name}' did not finish in time; the line holds what was measured before it"
+            sys.stderr.write("bench.py watchdog: " + msg + "\n")
+            sys.stderr.flush()
+            line = self.line
+            if line is not None:
+                line = dict(line)
+                line["watchdog"] = msg
+                emit(line)
+                os._exit(0)
+            os._exit(3)
 
 
 def base_config(workload):
@@ -197,15 +238,17 @@ def _scan_record(pipe, name, nq, nc, d, ms, scan_ms, tc_peak, fp32_peak, metric=
     return rec
 
 
-def secondary_workloads(engine, synth, torch, tc_peak, fp32_peak):
+def secondary_workloads(engine, synth, torch, tc_peak, fp32_peak, out=None, tick=None):
     """The other single-GPU configurations of BASELINE.json, device-resident, each with its own roofline
     object: configs[4] without pruning (what the tensor pipeline does when nothing can be skipped),
     configs[1] 100 k x 10 k=16 both metrics, configs[2] BMU of 1 M contigs on a 64 x 64 mesh, configs[3]
     500 k x 136 raw signatures (k = 16 graph + bin-vs-bin medians), and the latency of the small calls."""
     from groopm_b200 import _lib, dropin
-    out = []
+    out = [] if out is None else out          # (the caller's list: finished records are visible at once)
+    tick = tick or (lambda name, seconds: None)
 
     def run(name, q, c, k, metric, steps=10, **kw):
+        tick(name, 300.0)
         same = c is None
         qd = torch.from_numpy(q).cuda()
         cd = qd if same else torch.from_numpy(c).cuda()
@@ -230,6 +273,7 @@ def secondary_workloads(engine, synth, torch, tc_peak, fp32_peak):
     sigs = synth.quantise(synth.kmer_sigs(500_000, 4), 34)
     sd = run("cfg4_500k_x136_k16_euclidean", sigs, None, 16, "euclidean", steps=2)
     torch.cuda.synchronize()
+    tick("cfg4 bin-vs-bin medians", 180.0)
     pairs_idx = [(np.arange(a * 2000, (a + 1) * 2000), np.arange(b * 2000, (b + 1) * 2000))
                  for a in range(8) for b in ((a + 1) % 250, (a + 7) % 250, (a + 31) % 250, (a + 64) % 250,
                                              (a + 100) % 250, (a + 200) % 250)]
@@ -243,6 +287,7 @@ def secondary_workloads(engine, synth, torch, tc_peak, fp32_peak):
     del sd, sigs
 
     # small-call latency against the scipy calls they replace (same host, same arrays)
+    tick("small-call latencies", 180.0)
     from scipy.spatial import KDTree as SpKDTree
     from scipy.spatial.distance import cdist as sp_cdist
 
@@ -420,8 +465,10 @@ def engine_arm(args):
     prune = {"auto": None, "on": True, "off": False}[args.prune]
     tc_peak, tc_burst, hbm_peak, peak_src = _peaks()
 
-    def measure(workload, steps, warmup, sample_clocks):
-        """The step of `workload` on this rank's shard: device-resident and end-to-end timings."""
+    def measure(workload, steps, warmup, sample_clocks, progress=None):
+        """The step of `workload` on this rank's shard: device-resident and end-to-end timings.
+        progress(next_leg, seconds, partial_result): called after every leg (the watchdog's view of the run)."""
+        progress = progress or (lambda name, seconds, res: None)
         n, d, k, metric, seed = WORKLOADS[workload]
         x = synth.cfg_knn_rows(n, d, seed)                   # every rank draws the same array
         r0, r1 = gdist.shard_bounds(n, world, rank)
@@ -477,6 +524,11 @@ def engine_arm(args):
         exact_rows = pipe.exact_row_count()
         stats = pipe.prune_stats() if pipe.prune else None
         res_idx, res_dist = pipe.out_idx[:n_local].clone(), pipe.out_dist[:n_local].clone()
+        res = dict(n=n, d=d, k=k, metric=metric, n_local=n_local, pipe=pipe, dev_ms=dev_ms, scan_ms=scan_ms,
+                   scan_ms_max=scan_ms_max, exact_rows=exact_rows, stats=stats, e2e_s=None, clocks=None,
+                   cabi_ms=None, verified=0, ok=None, x=x, h2d=int(x_host.numel() * 8 * world),
+                   d2h=int((out_idx_host.numel() * 4 + out_dist_host.numel() * 8) * world))
+        progress("end to end through engine.knn(numpy)", 300.0, res)
 
         # ---- (B) end to end through the public API with host buffers
         for _ in range(warmup):
@@ -488,6 +540,8 @@ def engine_arm(args):
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         clocks = sampler.stop() if sampler else None
+        res.update(e2e_s=e2e_s, clocks=clocks)
+        progress("C-ABI host entry point gmd_knn_host_f64", 240.0, res)
 
         # ---- (C) the C-ABI host entry point (gmd_knn_host_f64: library-owned buffers, pageable copies), N = 1
         cabi_ms = None
@@ -500,6 +554,8 @@ def engine_arm(args):
                 engine.knn_host(x, None, k, metric, out=outs)
             cabi_ms = (time.perf_counter() - t0) / 3 * 1e3
 
+        res.update(cabi_ms=cabi_ms)
+        progress("verification against the oracle", 240.0, res)
         # ---- (D) verification outside the timed regions: sampled rows of THIS rank's result against the
         # reference's scipy arithmetic (oracle.knn as the checker)
         verified = 0
@@ -514,33 +570,22 @@ def engine_arm(args):
             verified = len(rows)
         verified = int(sum_over_ranks(float(verified)))
         all_ok = sum_over_ranks(0.0 if ok else 1.0) == 0.0
-        return dict(n=n, d=d, k=k, metric=metric, n_local=n_local, pipe=pipe, dev_ms=dev_ms, scan_ms=scan_ms,
-                    scan_ms_max=scan_ms_max, exact_rows=exact_rows, stats=stats, e2e_s=e2e_s, clocks=clocks,
-                    cabi_ms=cabi_ms, verified=verified, ok=all_ok, x=x,
-                    h2d=int(x_host.numel() * 8 * world),
-                    d2h=int((out_idx_host.numel() * 4 + out_dist_host.numel() * 8) * world))
+        res.update(verified=verified, ok=all_ok)
+        progress("secondary workloads", 300.0, res)
+        return res
 
+    wd = Watchdog()
+    if world == 1:
+        wd.start()
+    wd.leg("FP32 peak probe", 180.0)
     peak_probe = engine.fp32_peak_tflops()                   # measured FFMA2 peak of this GPU (uniform operand)
-    m = measure(args.workload, args.steps, args.warmup, True)
-    extra = []
-    if world == 8 and args.workload == "cfg5_1m_x30_k32" and not args.no_secondary:
-        # BASELINE configs[4] at its largest size rides along on the 8-GPU line
-        m4 = measure("cfg5_4m_x30_k32", 3, 2, False)
-        if rank == 0:
-            pairs4 = float(m4["n"]) ** 2
-            extra.append({"workload": "cfg5_4m_x30_k32", "n_gpus": world, "ms_per_step": m4["dev_ms"] / 3,
-                          "pairs_per_s": pairs4 * 3 / (m4["dev_ms"] * 1e-3),
-                          "e2e_ms_per_step": m4["e2e_s"] / 3 * 1e3, "scan_ms": m4["scan_ms_max"],
-                          "exact_rows_rank0": m4["exact_rows"], "verified_rows": m4["verified"],
-                          "verified": m4["ok"],
-                          "tiles_visited_fraction": m4["stats"]["visited_fraction"] if m4["stats"] else None})
 
-    rc = 0
-    if rank == 0:
+    def build_line(m):
+        """The JSON line from a (possibly partial) result of measure(): legs not yet run read as null."""
         n, d, k, metric, pipe = m["n"], m["d"], m["k"], m["metric"], m["pipe"]
         pairs = float(n) * float(n)
         value = pairs * args.steps / (m["dev_ms"] * 1e-3)
-        e2e_value = pairs * args.steps / m["e2e_s"]
+        e2e_value = pairs * args.steps / m["e2e_s"] if m["e2e_s"] else None
         # roofline of the dominant kernel: 2*D flop per pair (SURVEY.md 8d), one launch covers this rank's
         # n_local x n pairs
         launch_flop = 2.0 * d * float(m["n_local"]) * float(n)
@@ -594,12 +639,13 @@ def engine_arm(args):
             "verification": "sampled rows of every rank's result == oracle.knn (scipy float64), bit for bit, outside "
                             "the timed regions",
         })
-        line = {
+        return {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["dev_ms"] / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16x3" if tc else "f32", "data": "synthetic",
             "config": cfg,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": m["e2e_s"] / args.steps * 1e3,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "ms_per_step": m["e2e_s"] / args.steps * 1e3 if m["e2e_s"] else None,
                     "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                     "call": "engine.knn(numpy float64 rows) -> numpy (indices, distances)" if world == 1 else
                             "dist.sharded_knn between pinned host buffers on every rank",
@@ -608,18 +654,50 @@ def engine_arm(args):
             "clocks": m["clocks"],
             "roofline": roofline,
         }
-        if not m["ok"]:
+
+    def progress(name, seconds, res):
+        if rank == 0:
+            wd.line = build_line(res)
+        wd.leg(name, seconds)
+
+    wd.leg("device-resident timing of the step", 420.0)
+    m = measure(args.workload, args.steps, args.warmup, True, progress)
+    extra = []
+    if world == 8 and args.workload == "cfg5_1m_x30_k32" and not args.no_secondary:
+        # BASELINE configs[4] at its largest size rides along on the 8-GPU line
+        m4 = measure("cfg5_4m_x30_k32", 3, 2, False)
+        if rank == 0:
+            pairs4 = float(m4["n"]) ** 2
+            extra.append({"workload": "cfg5_4m_x30_k32", "n_gpus": world, "ms_per_step": m4["dev_ms"] / 3,
+                          "pairs_per_s": pairs4 * 3 / (m4["dev_ms"] * 1e-3),
+                          "e2e_ms_per_step": m4["e2e_s"] / 3 * 1e3, "scan_ms": m4["scan_ms_max"],
+                          "exact_rows_rank0": m4["exact_rows"], "verified_rows": m4["verified"],
+                          "verified": m4["ok"],
+                          "tiles_visited_fraction": m4["stats"]["visited_fraction"] if m4["stats"] else None})
+
+    rc = 0
+    if rank == 0:
+        n, d, k, metric = m["n"], m["d"], m["k"], m["metric"]
+        line = build_line(m)
+        if m["ok"] is False:
             rc = 1
         if world == 1 and not args.no_secondary:
             del m["x"]
-            extra += secondary_workloads(engine, synth, torch, tc_peak, peak_probe)
+            line["config"]["secondary"] = extra           # filled in place: the watchdog's line sees finished records
+            line["roofline"]["secondary"] = extra
+            wd.line = line
+            secondary_workloads(engine, synth, torch, tc_peak, peak_probe, out=extra, tick=wd.leg)
         if extra:
             line["config"]["secondary"] = extra
             line["roofline"]["secondary"] = extra
         if world == 1 and not args.no_cpu_baseline:
+            wd.line = line
+            wd.leg("cpu baseline (oracle, one thread)", 300.0)
             x = synth.cfg_knn_rows(n, d, WORKLOADS[args.workload][4])
             line["cpu_baseline"] = cpu_baseline_leg(x, k, metric)
+        wd.done = True
         emit(line)
+    wd.done = True
     if world > 1:
         tdist.destroy_process_group()
     return rc
